@@ -1,0 +1,145 @@
+/*
+ * liblsnet_sm100.so — C ABI of the B200-native LSNet training hot path.
+ *
+ * Every entry point: plain pointers + sizes, no torch types; device pointers unless marked host; returns 0 on
+ * success, non-zero on failure with a thread-local message from lsnet_last_error().  No allocation inside:
+ * callers pass outputs and workspaces.  Kernels are enqueued on `stream` (a cudaStream_t passed as void*).
+ * Activations are NHWC ("pixel-major"): a row is one pixel, `ld*` arguments are row pitches in ELEMENTS.
+ *
+ * Each function names the reference interface it replaces (paths relative to /root/reference/code).  The
+ * reference's own native boundary for this path is the pybind module `deform_conv_ext`
+ * (mmdet/ops/dcn/src/deform_conv_ext.cpp:227-250) plus `sigmoid_focal_loss_ext`; everything else on the path is
+ * PyTorch Python.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ */
+#ifndef LSNET_B200_H_
+#define LSNET_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status ------------------------------------------------------------------------------------------------ */
+const char* lsnet_last_error(void);             /* message of the last failing call on this thread */
+unsigned long long lsnet_launch_count(void);    /* kernels launched by this library since load */
+int lsnet_abi_version(void);
+int lsnet_require_sm100(void);                  /* 0 iff the current CUDA device is compute capability 10.x */
+
+/* ---- tcgen05 GEMM / implicit-GEMM convolution ----------------------------------------------------------------
+ * out[M,N] = A[M,K] . Bw[N,K]^T (+ bias[N]) (ReLU);  bf16 operands, fp32 accumulation in TMEM, out bf16 or fp32.
+ * Replaces the per-sample `addmm_` of the reference (mmdet/ops/dcn/src/cuda/deform_conv_cuda.cpp:673-678, 890-895,
+ * and the bias add :689-691) when A is the DCN column matrix, and 1x1 convolutions (nn.Conv2d in
+ * mmdet/models/necks/fpn.py:117-133, mmdet/models/dense_heads/lsnet_head.py:160-184) when A is an NHWC map.
+ * Needs N % 16 == 0, K % 8 == 0, 16-byte aligned row pitches. */
+int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M,
+                    int N, int K, const float* bias, int relu, int out_fp32, void* stream);
+
+/* Stride-1 "same" convolution as an implicit GEMM: x NHWC bf16 [B,H,W,C] (pixel pitch ldp), Wt bf16
+ * [N, kh*kw*C] (tap-major, channel-minor), out [B*H*W, ldc].  One shifted TMA box per filter tap; zero padding is
+ * the TMA out-of-bounds fill.  Replaces the cuDNN nn.Conv2d 3x3 calls of FPN (necks/fpn.py:146-155) and LSHead
+ * (dense_heads/lsnet_head.py:167-184, conv_offset of ModulatedDeformConvPack ops/dcn/deform_conv.py:511-519) and,
+ * with transposed/flipped weights, their input gradients.  Needs C % 64 == 0, N % 16 == 0. */
+int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt, int N, int kh,
+                           int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out, long long ldc,
+                           const float* bias, int relu, int out_fp32, void* stream);
+
+/* out[M,N] (fp32) += A[P,M]^T . Bm[P,N]  (reduction over the P rows = pixels; split-K, fp32 red.global.add; the
+ * caller zero-fills `out`).  Weight-gradient GEMM: replaces `grad_weight[g].addmm_(grad_output, columns^T)`
+ * (deform_conv_cuda.cpp:782-787, 1113-1124).  Needs M % 8 == 0, N % 8 == 0. */
+int lsnet_gemm_tn_bf16(const void* A, long long lda, const void* Bm, long long ldb, float* out, long long ldc, int P,
+                       int M, int N, void* stream);
+
+/* dw[N, kh*kw, C] (fp32) += sum_pixels dy[p, n] * x[p + tap, c]: weight gradient of lsnet_conv2d_nhwc_bf16. */
+int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B, int H, int W,
+                                 int C, int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, float* dw,
+                                 void* stream);
+
+/* ---- deformable convolution sampling ---------------------------------------------------------------------------
+ * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
+ * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel
+ * g*2*kh*kw + 2*k + {0:dy, 1:dx}; mask: fp32 [B*Ho*Wo, ldm], channel g*kh*kw + k; col: bf16 [B*Ho*Wo, kh*kw*C].
+ * Replaces deformable_im2col / pyramid_deformable_im2col / modulated_deformable_im2col_cuda
+ * (mmdet/ops/dcn/src/cuda/deform_conv_cuda_kernel.cu:190-332, 647-680, 847-910, 1046-1076), i.e. the sampling half
+ * of deform_conv_forward / pyramid_deform_conv_forward / modulated_deform_conv_forward
+ * (ops/dcn/src/deform_conv_ext.cpp:74-147). */
+int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, long long ldx, const float* offset,
+                          long long ldo, const float* mask, long long ldm, int Ho, int Wo, int kh, int kw,
+                          int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float scale_h,
+                          float scale_w, int deformable_groups, void* col, long long ldcol, void* stream);
+
+/* Adjoint: gcol bf16 [B*Ho*Wo, kh*kw*C] (= dY . W) -> dx fp32 NHWC (ACCUMULATED: caller zero-fills; may be NULL),
+ * doffset fp32 [B*Ho*Wo, lddo], dmask fp32 [B*Ho*Wo, lddm] (NULL without mask).  Replaces *_col2im and
+ * *_col2im_coord (deform_conv_cuda_kernel.cu:333-448, 486-615, 912-1044), the sampling half of
+ * deform_conv_backward_input / pyramid_deform_conv_backward_input / modulated_deform_conv_backward
+ * (deform_conv_ext.cpp:92-224). */
+int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const void* x, int B, int H, int W, int C, long long ldx,
+                          const float* offset, long long ldo, const float* mask, long long ldm, int Ho, int Wo,
+                          int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                          float scale_h, float scale_w, int deformable_groups, float* dx, long long lddx,
+                          float* doffset, long long lddo, float* dmask, long long lddm, void* stream);
+
+/* ---- cross-IOU loss ----------------------------------------------------------------------------------------------
+ * loss_type: 0 bbox, 1 polygon, 2 keypoint.  Dense form = CrossIOULoss.forward / cross_iou_loss
+ * (mmdet/models/losses/cross_iou_loss.py:61-172): pred/target [N,D] fp32, pos_inds [N,D] u8, weight_row [N]
+ * (= weight.mean(-1)), anchor_pts [N,2], bbox_gt [N,4], vs [N,L].  row_loss[n] = weight_row[n] * loss_n. */
+int lsnet_cross_iou_fwd(int loss_type, const float* pred, const float* target, const unsigned char* pos_inds,
+                        const float* weight_row, const float* anchor_pts, const float* bbox_gt, const float* vs, int N,
+                        int D, int L, float eps, float alpha, int stride, float* row_loss, void* stream);
+/* dpred[n,d] = (*scale) * weight_row[n] * d loss_n / d pred[n,d]   (scale: device scalar) */
+int lsnet_cross_iou_bwd(int loss_type, const float* pred, const float* target, const unsigned char* pos_inds,
+                        const float* weight_row, const float* anchor_pts, const float* bbox_gt, const float* vs, int N,
+                        int D, int L, float eps, float alpha, int stride, const float* scale, float* dpred,
+                        void* stream);
+/* Fused per-level form used by LSHead.loss (dense_heads/lsnet_head.py:1064-1102, 402-454): rows are the (b,h,w)
+ * pixels of an NHWC prediction map; targets are rebuilt from assign[b, level_off + pix] (index into the per-image GT
+ * tables gt_pts [B,Gmax,2*NP], gt_bbox [B,Gmax,4], gt_vs [B,Gmax,L]).  backward == 0: row_loss; else dpred. */
+int lsnet_cross_iou_level(int loss_type, int backward, const float* pred, long long ldp, int D, const int* assign,
+                          long long assign_ld, int level_off, int B, int Hl, int Wl, float stride, float base_scale,
+                          const float* gt_pts, const float* gt_bbox, const float* gt_vs, int Gmax, int NP, int L,
+                          float eps, float alpha, int pstride, float* row_loss, const float* scale, float* dpred,
+                          void* stream);
+/* LSHead.get_bbox_gt_reg / get_poly_gt_reg (lsnet_head.py:402-454), dense rows. */
+int lsnet_directional_targets(const float* gt_rows, const float* anchor_pts, const float* weight_row, int N, int NP,
+                              float* target, unsigned char* pos_inds, void* stream);
+
+/* ---- sigmoid focal loss: SigmoidFocalLossForward/Backward (mmdet/ops/sigmoid_focal_loss/src/cuda/
+ * sigmoid_focal_loss_cuda.cu:23-97, sigmoid_focal_loss_ext.cpp).  labels int32, background = C. ------------------ */
+int lsnet_focal_partial_count(long long N, int C);   /* host: number of partial sums lsnet_focal_fwd writes */
+int lsnet_focal_fwd(const float* logits, long long ldl, const int* labels, const float* weight, long long N, int C,
+                    float gamma, float alpha, float* partial, void* stream);
+int lsnet_focal_bwd(const float* logits, long long ldl, const int* labels, const float* weight, long long N, int C,
+                    float gamma, float alpha, const float* scale, float* dlogits, long long ldd, void* stream);
+
+/* ---- landmark-target assignment (bit-exact integers on tie-free inputs) -----------------------------------------
+ * Pyramid description (host arrays): level_h/level_w/level_stride [num_levels]; points of level l are
+ * (w*stride, h*stride, stride) (mmdet/core/anchor/point_generator.py:17-25).  valid_hw: device int [B,num_levels,2].
+ * gt_bbox [B,Gmax,4], gt_count [B] (device).  assign: int32 [B, sum_l H_l*W_l], -1 = background, else GT index.  */
+/* CentroidAssigner.assign, iou_type='center', pos_num=1 (mmdet/core/bbox/assigners/centroid_assigner.py:26-93). */
+int lsnet_centroid_assign(int num_levels, const int* level_h, const int* level_w, const float* level_stride,
+                          const int* valid_hw, const float* gt_bbox, const int* gt_count, int B, int Gmax, float scale,
+                          float* ws_best_d, int* ws_best_i, int* assign, void* stream);
+/* ATSSAssigner.assign (mmdet/core/bbox/assigners/atss_assigner.py:29-164); boxes [B,total,4] predicted init boxes;
+ * ws_keys: u64 [B,total] workspace; max_overlaps may be NULL. */
+int lsnet_atss_assign(int num_levels, const int* level_h, const int* level_w, const float* level_stride,
+                      const int* valid_hw, const float* boxes, const float* gt_bbox, const int* gt_count, int B,
+                      int Gmax, int topk, unsigned long long* ws_keys, int* assign, float* max_overlaps, void* stream);
+/* LSHead._target_single label scatter (lsnet_head.py:834-898): labels int32 (background = num_classes),
+ * label_weights, per-image positive counts num_pos [B]. */
+int lsnet_assign_targets(int num_levels, const int* level_h, const int* level_w, const float* level_stride,
+                         const int* valid_hw, const int* assign, const int* gt_labels, int B, int Gmax,
+                         int num_classes, int* labels, float* label_weights, int* num_pos, void* stream);
+/* extreme_points2bbox / vectors2bbox + centre shift (lsnet_head.py:321-370, 1333-1361). */
+int lsnet_pred_boxes(const float* pred, long long ldp, int NP, int polygon, int B, int Hl, int Wl, float stride,
+                     int level_off, int total_points, float* boxes, void* stream);
+
+/* ---- host-side parity hooks (CPU, no device): the row arithmetic the loss kernels run ----------------------- */
+float lsnet_host_cross_iou_row(int loss_type, const float* pred, const float* target, const unsigned char* pos_inds,
+                               int D, const float* anchor, const float* bbox_gt, const float* vs, float eps,
+                               float alpha, int stride, float* grad);
+float lsnet_host_focal_elem(float x, int t, int d, float gamma, float alpha, float* grad);
+void lsnet_host_directional_target_row(const float* gt, int NP, const float* anchor, int positive, float* target,
+                                       unsigned char* sel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSNET_B200_H_ */

@@ -1,0 +1,616 @@
+// tcgen05 / TMEM / TMA GEMM family for the LSNet hot path (sm_100a only).
+//
+//  gemm_kmajor<BN>  C[M,N] = A[M,K] . B[N,K]^T (+bias, ReLU), bf16 in, fp32 accumulate in TMEM.
+//     A is either a plain row-major [M,K] matrix (DCN column matrix, 1x1 convs, dY for bwd-data) or -- conv mode --
+//     an NHWC activation read through a 4-D tensor map with one shifted TMA box per filter tap (implicit GEMM,
+//     zero padding = TMA out-of-bounds fill).  Replaces reference K2/K3 (deform_conv_cuda.cpp:673-691) and the
+//     cuDNN convs of FPN / LSHead (necks/fpn.py:165-217, dense_heads/lsnet_head.py:502-755).
+//  gemm_mnmajor     C[M,N] += A[K,M]^T . B[K,N]  (reduction over rows = pixels), both operands MN-major in smem,
+//     split-K over pixel ranges with fp32 red.global.add.  Replaces the weight-gradient GEMMs
+//     (deform_conv_cuda.cpp:782-787, 1113-1124) and conv weight grads.
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
+// warps2-5 = epilogue (each owns the TMEM lane quarter warp_idx%4).  Persistent over output tiles; smem ring of
+// kStages {A,B} tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "lsnet_internal.h"
+
+namespace lsn {
+
+constexpr int BM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int BK = 64;        // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int kThreads = 192;
+
+struct GemmArgs {
+  int M, N;            // logical output extent (N multiple of 16)
+  int num_k_iters;     // K/64, or taps * C/64 in conv mode
+  int m_tiles, n_tiles;
+  // conv mode (A through a 4-D NHWC map); ignored when conv == 0
+  int conv, H, W, tiles_h, tiles_w, TH, TW, kw, cblks, pad_h, pad_w, dil_h, dil_w;
+  void* out;           // [M, ldc] bf16 or fp32
+  long long ldc;
+  int out_fp32, relu;
+  const float* bias;   // [N] or null
+};
+
+template <int BN>
+struct KCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmArgs p) {
+  using Cfg = KCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);   // one elected lane per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int n0 = nt * BN;
+        int m0 = mt * BM, b = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          const int per_img = p.tiles_h * p.tiles_w;
+          b = mt / per_img;
+          const int r = mt % per_img;
+          h0 = (r / p.tiles_w) * p.TH;
+          w0 = (r % p.tiles_w) * p.TW;
+        }
+        for (int it = 0; it < p.num_k_iters; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.conv) {
+            const int tap = it / p.cblks, cb = it % p.cblks;
+            const int dy = tap / p.kw, dx = tap % p.kw;
+            tma_load_4d(sA, &tmA, &full_bar[stage], cb * BK, w0 - p.pad_w + dx * p.dil_w,
+                        h0 - p.pad_h + dy * p.dil_h, b);
+          } else {
+            tma_load_2d(sA, &tmA, &full_bar[stage], it * BK, m0);
+          }
+          tma_load_2d(sB, &tmB, &full_bar[stage], it * BK, n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int it = 0; it < p.num_k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sB = sA + Cfg::kABytes;
+          const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sB, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B along K inside the 128-B swizzle row = +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem slot when these MMAs retire
+          if (it == p.num_k_iters - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;     // accumulator row handled by this thread
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int n0 = nt * BN;
+      long long row;
+      bool valid;
+      if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        const int b = mt / per_img, rr = mt % per_img;
+        const int h = (rr / p.tiles_w) * p.TH + r / p.TW;
+        const int w = (rr % p.tiles_w) * p.TW + r % p.TW;
+        valid = (h < p.H) && (w < p.W);
+        row = (static_cast<long long>(b) * p.H + h) * p.W + w;
+      } else {
+        row = static_cast<long long>(mt) * BM + r;
+        valid = row < p.M;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c, v);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (valid && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (col0 + j < p.N)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (col0 + j < p.N)
+                *reinterpret_cast<uint4*>(o + j) =
+                    make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
+                               pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// MN-major split-K GEMM:  C[M,N] += sum_{p in split} A[p, m] * B[p, n]   (A: [P, M] row-major, B: [P, N] row-major)
+// In conv mode B rows are the NHWC pixels shifted by the filter tap (4-D map), A rows the dY pixels (4-D map, no
+// shift); the K "pixel" loop walks TH x TW = 64-pixel patches.  Output fp32 with red.global.add (C pre-zeroed).
+// ---------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  int M, N;              // M = C_out, N = columns of B handled per tap (C_in or 9*C for DCN columns)
+  int m_tiles, n_tiles;  // tiles of 128 x BNW
+  int taps;              // 1 (plain) or kh*kw (conv)
+  int splits;            // split-K factor over pixel chunks
+  int k_chunks;          // total 64-pixel chunks (plain: ceil(P/64); conv: B * tiles_h * tiles_w)
+  int conv, tiles_h, tiles_w, TH, TW, kw, pad_h, pad_w, dil_h, dil_w;
+  float* out;            // [M, taps, N] fp32 (row stride ldc = taps*N)
+  long long ldc;
+};
+
+constexpr int BNW = 256;
+constexpr int kWStages = 4;
+constexpr int kWABytes = BK * BM * 2;    // 64 pixels x 128 couts
+constexpr int kWBBytes = BK * BNW * 2;   // 64 pixels x 256 cins
+constexpr int kWStageBytes = kWABytes + kWBBytes;
+constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes);
+  uint64_t* empty_bar = full_bar + kWStages;
+  uint64_t* tfull_bar = empty_bar + kWStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item = (tap, m_tile, n_tile, split)
+  const int items = p.taps * p.m_tiles * p.n_tiles * p.splits;
+  const int chunks_per_split = (p.k_chunks + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int t = item;
+        const int split = t % p.splits; t /= p.splits;
+        const int nt = t % p.n_tiles; t /= p.n_tiles;
+        const int mt = t % p.m_tiles; t /= p.m_tiles;
+        const int tap = t;
+        const int c_begin = split * chunks_per_split;
+        const int c_end = min(p.k_chunks, c_begin + chunks_per_split);
+        const int dy = p.conv ? tap / p.kw : 0, dx = p.conv ? tap % p.kw : 0;
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * kWStageBytes;
+          uint8_t* sB = sA + kWABytes;
+          mbar_expect_tx(&full_bar[stage], kWStageBytes);
+          if (p.conv) {
+            const int per_img = p.tiles_h * p.tiles_w;
+            const int b = ch / per_img, rr = ch % per_img;
+            const int h0 = (rr / p.tiles_w) * p.TH, w0 = (rr % p.tiles_w) * p.TW;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_4d(sA + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, w0, h0, b);
+#pragma unroll
+            for (int j = 0; j < BNW / 64; ++j)
+              tma_load_4d(sB + j * (BK * 128), &tmB, &full_bar[stage], nt * BNW + j * 64,
+                          w0 - p.pad_w + dx * p.dil_w, h0 - p.pad_h + dy * p.dil_h, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, ch * BK);
+#pragma unroll
+            for (int j = 0; j < BNW / 64; ++j)
+              tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], nt * BNW + j * 64, ch * BK);
+          }
+          if (++stage == kWStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BNW, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int c_begin = split * chunks_per_split;
+        const int c_end = min(p.k_chunks, c_begin + chunks_per_split);
+        if (c_end <= c_begin) continue;   // empty split: epilogue skips it too
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BNW);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kWStageBytes);
+          const uint32_t sB = sA + kWABytes;
+          // MN-major: LBO = distance between 64-wide M/N chunks (one TMA box = 64 rows x 128 B), SBO = 8 K rows
+          const uint64_t adesc = umma_desc_sw128(sA, BK * 128, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sB, BK * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // 16 K rows = 2 swizzle atoms of 8 rows = +2048 B -> +128 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, ((ch - c_begin) | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ch == c_end - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == kWStages) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int t = item;
+      const int split = t % p.splits; t /= p.splits;
+      const int nt = t % p.n_tiles; t /= p.n_tiles;
+      const int mt = t % p.m_tiles; t /= p.m_tiles;
+      const int tap = t;
+      const int c_begin = split * chunks_per_split;
+      const int c_end = min(p.k_chunks, c_begin + chunks_per_split);
+      if (c_end <= c_begin) continue;
+      const int m = mt * BM + r;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BNW);
+#pragma unroll 1
+      for (int c = 0; c < BNW; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c, v);
+        tmem_ld_wait();
+        const int col0 = nt * BNW + c;
+        if (m < p.M && col0 < p.N) {
+          float* o = p.out + static_cast<long long>(m) * p.ldc + static_cast<long long>(tap) * p.N + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =========================================================================================================
+// Host side: tensor maps + launch
+// =========================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// rank-2 bf16 map over a row-major [rows, cols] matrix with row pitch ld (elements); box = [box_cols, box_rows]
+static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                       uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(2d) failed: %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+                                          (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return 0;
+}
+// rank-4 bf16 map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1]
+static int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
+                         uint32_t TW, uint32_t TH) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {ldp * 2, W * ldp * 2, H * W * ldp * 2};
+  cuuint32_t box[4] = {64, TW, TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(4d) failed: %d", (int)r);
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// choose a spatial patch TH x TW = pixels with the least padding waste
+static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
+  long long best = -1;
+  for (int th = 1; th <= pixels; th <<= 1) {
+    int tw = pixels / th;
+    if (tw > 256 || th > 256) continue;
+    long long cover = static_cast<long long>((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
+    if (best < 0 || cover < best) { best = cover; *TH = th; *TW = tw; }
+  }
+}
+
+template <int BN>
+static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = KCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kmajor_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_kmajor<%d>): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int tiles = a.m_tiles * a.n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kmajor_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm_kmajor<%d> launch: %s", BN, cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+static int dispatch_kmajor(const CUtensorMap& tmA, const void* Bw, int N, int K, long long ldb, GemmArgs& a,
+                           cudaStream_t st) {
+  int BN = N >= 256 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  a.n_tiles = (N + BN - 1) / BN;
+  CUtensorMap tmB;
+  if (int rc = make_map_2d(&tmB, Bw, N, K, ldb, 64, BN)) return rc;
+  switch (BN) {
+    case 256: return launch_kmajor<256>(tmA, tmB, a, st);
+    case 128: return launch_kmajor<128>(tmA, tmB, a, st);
+    case 64: return launch_kmajor<64>(tmA, tmB, a, st);
+    default: return launch_kmajor<32>(tmA, tmB, a, st);
+  }
+}
+
+}  // namespace lsn
+
+using namespace lsn;
+
+extern "C" int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc,
+                               int M, int N, int K, const float* bias, int relu, int out_fp32, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((N % 16) || (K % 8) || (lda % 8) || (ldb % 8) || (ldc % (out_fp32 ? 4 : 8)))
+    return set_error("lsnet_gemm_bf16: need N%%16==0, K%%8==0 and 16-byte aligned pitches (N=%d K=%d lda=%lld ldb=%lld ldc=%lld)",
+                     N, K, lda, ldb, ldc);
+  CUtensorMap tmA;
+  if (int rc = make_map_2d(&tmA, A, M, K, lda, 64, BM)) return rc;
+  GemmArgs a{};
+  a.M = M; a.N = N; a.num_k_iters = (K + BK - 1) / BK; a.m_tiles = (M + BM - 1) / BM;
+  a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  return dispatch_kmajor(tmA, Bw, N, K, ldb, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt,
+                                      int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out,
+                                      long long ldc, const float* bias, int relu, int out_fp32, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  if ((C % 64) || (N % 16) || (ldp % 8) || (ldc % (out_fp32 ? 4 : 8)))
+    return set_error("lsnet_conv2d_nhwc_bf16: need C%%64==0, N%%16==0, aligned pitches (C=%d N=%d)", C, N);
+  // "same" geometry only: output grid == input grid (stride 1, 2*pad == dil*(k-1))
+  if (2 * pad_h != dil_h * (kh - 1) || 2 * pad_w != dil_w * (kw - 1))
+    return set_error("lsnet_conv2d_nhwc_bf16: only stride-1 'same' convolutions are supported");
+  int TH = 8, TW = 16;
+  pick_patch(H, W, BM, &TH, &TW);
+  CUtensorMap tmA;
+  if (int rc = make_map_nhwc(&tmA, x, B, H, W, C, ldp, TW, TH)) return rc;
+  GemmArgs a{};
+  a.conv = 1; a.H = H; a.W = W; a.TH = TH; a.TW = TW;
+  a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
+  a.kw = kw; a.cblks = C / 64; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h; a.dil_w = dil_w;
+  a.M = B * H * W; a.N = N; a.num_k_iters = kh * kw * a.cblks; a.m_tiles = B * a.tiles_h * a.tiles_w;
+  a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  return dispatch_kmajor(tmA, Wt, N, kh * kw * C, static_cast<long long>(kh) * kw * C, a,
+                         static_cast<cudaStream_t>(stream));
+}
+
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArgs& a, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_mnmajor): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int base = a.taps * a.m_tiles * a.n_tiles;
+  int splits = (num_sms() + base - 1) / base;
+  if (splits > a.k_chunks) splits = a.k_chunks;
+  if (splits < 1) splits = 1;
+  a.splits = splits;
+  int items = base * splits;
+  int grid = items < num_sms() ? items : num_sms();
+  gemm_mnmajor_kernel<<<grid, kThreads, kWSmemBytes, st>>>(tmA, tmB, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("gemm_mnmajor launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+// out[M,N] (fp32, pre-zeroed by the caller or accumulated into) += A[P,M]^T . B[P,N]
+extern "C" int lsnet_gemm_tn_bf16(const void* A, long long lda, const void* Bm, long long ldb, float* out,
+                                  long long ldc, int P, int M, int N, void* stream) {
+  if (P <= 0 || M <= 0 || N <= 0) return 0;
+  if ((M % 8) || (N % 8) || (lda % 8) || (ldb % 8) || (ldc % 4))
+    return set_error("lsnet_gemm_tn_bf16: need M%%8==0, N%%8==0 and aligned pitches");
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_2d(&tmA, A, P, M, lda, 64, 64)) return rc;
+  if (int rc = make_map_2d(&tmB, Bm, P, N, ldb, 64, 64)) return rc;
+  WgradArgs a{};
+  a.M = M; a.N = N; a.m_tiles = (M + BM - 1) / BM; a.n_tiles = (N + BNW - 1) / BNW; a.taps = 1;
+  a.k_chunks = (P + BK - 1) / BK; a.conv = 0; a.out = out; a.ldc = ldc;
+  return launch_wgrad(tmA, tmB, a, static_cast<cudaStream_t>(stream));
+}
+
+// dW[N_out, kh*kw, C] (fp32) += sum_pixels dY[p, n] * X[p + tap, c]     (stride-1 'same' conv weight gradient)
+extern "C" int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B, int H,
+                                            int W, int C, int N, int kh, int kw, int pad_h, int pad_w, int dil_h,
+                                            int dil_w, float* dw, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  if ((C % 8) || (N % 8) || (ldy % 8) || (ldx % 8)) return set_error("lsnet_conv2d_wgrad_nhwc_bf16: alignment");
+  int TH = 4, TW = 16;
+  pick_patch(H, W, BK, &TH, &TW);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_nhwc(&tmA, dy, B, H, W, N, ldy, TW, TH)) return rc;
+  if (int rc = make_map_nhwc(&tmB, x, B, H, W, C, ldx, TW, TH)) return rc;
+  WgradArgs a{};
+  a.M = N; a.N = C; a.m_tiles = (N + BM - 1) / BM; a.n_tiles = (C + BNW - 1) / BNW; a.taps = kh * kw;
+  a.conv = 1; a.TH = TH; a.TW = TW; a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
+  a.k_chunks = B * a.tiles_h * a.tiles_w; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h;
+  a.dil_w = dil_w; a.out = dw; a.ldc = static_cast<long long>(kh) * kw * C;
+  return launch_wgrad(tmA, tmB, a, static_cast<cudaStream_t>(stream));
+}
