@@ -37,7 +37,7 @@ int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb,
  * [N, kh*kw*C] (tap-major, channel-minor), out [B*H*W, ldc].  One shifted TMA box per filter tap; zero padding is
  * the TMA out-of-bounds fill.  Replaces the cuDNN nn.Conv2d 3x3 calls of FPN (necks/fpn.py:146-155) and LSHead
  * (dense_heads/lsnet_head.py:167-184, conv_offset of ModulatedDeformConvPack ops/dcn/deform_conv.py:511-519) and,
- * with transposed/flipped weights, their input gradients.  Needs C % 64 == 0, N % 16 == 0. */
+ * with transposed/flipped weights, their input gradients.  Needs C % 8 == 0 (weights packed with C padded to 64 per tap), N % 16 == 0. */
 int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt, int N, int kh,
                            int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out, long long ldc,
                            const float* bias, int relu, int out_fp32, void* stream);

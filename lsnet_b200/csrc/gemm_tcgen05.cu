@@ -540,8 +540,9 @@ extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C,
                                       int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out,
                                       long long ldc, const float* bias, int relu, int out_fp32, void* stream) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  if ((C % 64) || (N % 16) || (ldp % 8) || (ldc % (out_fp32 ? 4 : 8)))
-    return set_error("lsnet_conv2d_nhwc_bf16: need C%%64==0, N%%16==0, aligned pitches (C=%d N=%d)", C, N);
+  if ((C % 8) || (N % 16) || (ldp % 8) || (ldc % (out_fp32 ? 4 : 8)))
+    return set_error("lsnet_conv2d_nhwc_bf16: need C%%8==0, N%%16==0, aligned pitches (C=%d N=%d)", C, N);
+  const int cblks = (C + 63) / 64;   // weights are packed with C padded to 64 per tap; A's channel tail is TMA zero-fill
   // "same" geometry only: output grid == input grid (stride 1, 2*pad == dil*(k-1))
   if (2 * pad_h != dil_h * (kh - 1) || 2 * pad_w != dil_w * (kw - 1))
     return set_error("lsnet_conv2d_nhwc_bf16: only stride-1 'same' convolutions are supported");
@@ -552,10 +553,10 @@ extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C,
   GemmArgs a{};
   a.conv = 1; a.H = H; a.W = W; a.TH = TH; a.TW = TW;
   a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
-  a.kw = kw; a.cblks = C / 64; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h; a.dil_w = dil_w;
+  a.kw = kw; a.cblks = cblks; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h; a.dil_w = dil_w;
   a.M = B * H * W; a.N = N; a.num_k_iters = kh * kw * a.cblks; a.m_tiles = B * a.tiles_h * a.tiles_w;
   a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
-  return dispatch_kmajor(tmA, Wt, N, kh * kw * C, static_cast<long long>(kh) * kw * C, a,
+  return dispatch_kmajor(tmA, Wt, N, kh * kw * cblks * 64, static_cast<long long>(kh) * kw * cblks * 64, a,
                          static_cast<cudaStream_t>(stream));
 }
 

@@ -1,0 +1,59 @@
+"""Autograd convolution on the tcgen05 implicit-GEMM kernels: stride-1 'same' k x k convs and 1x1 convs over
+pixel-major (channels_last) bf16 activations.  Forward, input-gradient (same kernel, flipped/transposed weights) and
+weight-gradient (MN-major split-K kernel) all run in liblsnet_sm100.so; only the tiny bias-gradient column sum and the
+weight re-packing use torch ops."""
+import torch
+from torch.autograd import Function
+
+from . import gemm as G
+
+
+class _ConvSame(Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad, dil, relu, out_fp32):
+        co, ci, kh, kw = weight.shape
+        x = G.as_nhwc(x, torch.bfloat16)
+        if x.shape[1] % 8:
+            x = G.pad_channels_nhwc(x, 8)
+        wp = G.pack_conv_weight(weight.detach())
+        npad = wp.shape[0]
+        b = None
+        if bias is not None:
+            b = torch.zeros(npad, device=x.device, dtype=torch.float32)
+            b[:co] = bias.detach().float()
+        out = G.conv2d_nhwc(x, wp, kh, kw, pad, dil, b, relu, torch.float32 if out_fp32 else torch.bfloat16,
+                            n_valid=co)
+        ctx.save_for_backward(x, weight, out if relu else None)
+        ctx.cfg = (pad, dil, relu, bias is not None, ci)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, out = ctx.saved_tensors
+        pad, dil, relu, has_bias, ci = ctx.cfg
+        co, _, kh, kw = weight.shape
+        if relu:
+            gy = gy * (out > 0).to(gy.dtype)
+        gyp = G.pad_channels_nhwc(gy, 8, torch.bfloat16)           # (B, co_pad8, H, W) pixel-major bf16
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = G.pack_conv_weight(weight.detach(), flip_transpose=True)
+            gx = G.conv2d_nhwc(gyp, wt, kh, kw, pad, dil, None, False, torch.bfloat16, n_valid=ci)
+        if ctx.needs_input_grad[1]:
+            dw = G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil)       # (co_pad, taps, C_pad8)
+            gw = dw[:co, :, :ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.float().sum(dim=(0, 2, 3))
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d_same(x, weight, bias=None, padding=1, dilation=1, relu=False, out_fp32=False):
+    """nn.Conv2d(stride=1, padding=dilation*(k-1)/2) semantics on (B,C,H,W) tensors (any layout; converted to
+    channels_last bf16).  Returns a (B,Cout,H,W) channels_last view."""
+    return _ConvSame.apply(x, weight, bias, padding, dilation, relu, out_fp32)
+
+
+def linear_nhwc(x, weight, bias=None, relu=False, out_fp32=False):
+    """1x1 convolution."""
+    return _ConvSame.apply(x, weight, bias, 0, 1, relu, out_fp32)

@@ -1,0 +1,145 @@
+"""Deformable convolutions on liblsnet_sm100.so with the reference's call signatures
+(mmdet/ops/dcn/deform_conv.py:290-292): ``deform_conv``, ``modulated_deform_conv``, ``pyramid_deform_conv``.
+
+forward  : bilinear-offset gather -> bf16 column matrix [pixels, taps*C]  (lsnet_dcn_im2col_bf16)
+           tcgen05 GEMM columns x W^T (+bias)                               (lsnet_gemm_bf16)
+backward : dCol = dY x W  (lsnet_gemm_bf16) -> scatter to dX / reduce to dOffset, dMask (lsnet_dcn_col2im_bf16)
+           dW = dY^T x columns (lsnet_gemm_tn_bf16, MN-major split-K); the forward's column matrix is kept
+           (HBM is plentiful on B200) instead of being re-gathered as the reference does
+           (deform_conv_cuda.cpp:770-773).
+groups == 1 only (all LSHead sites); the grouped backbone sites (X-101, groups=64) are SURVEY §8 "next".
+"""
+import torch
+from torch.autograd import Function
+from torch.nn.modules.utils import _pair
+
+from .. import lib as L
+from . import gemm as G
+
+
+def _pix_major(t, min_ld_mult=1):
+    """(B,C,H,W) fp32 tensor -> (tensor, ld) with pixel-major memory (channel stride 1)."""
+    B, C, H, W = t.shape
+    ld = t.stride(3)
+    ok = t.stride(1) == 1 and t.stride(2) == W * ld and (B == 1 or t.stride(0) == H * W * ld)
+    if not ok or t.dtype != torch.float32:
+        t = t.float().contiguous(memory_format=torch.channels_last)
+        ld = t.stride(3)
+    return t, ld
+
+
+def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg):
+    B, H, W, C, ldx = G.nhwc_geom(x)
+    offset, ldo = _pix_major(offset)
+    ldm = 0
+    if mask is not None:
+        mask, ldm = _pix_major(mask)
+    col = torch.empty((B * Ho * Wo, kh * kw * C), device=x.device, dtype=torch.bfloat16)
+    L.call('lsnet_dcn_im2col_bf16', L.ptr(x), L.c_int(B), L.c_int(H), L.c_int(W), L.c_int(C), L.c_ll(ldx),
+           L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.c_int(Ho), L.c_int(Wo), L.c_int(kh), L.c_int(kw),
+           L.c_int(stride[0]), L.c_int(stride[1]), L.c_int(pad[0]), L.c_int(pad[1]), L.c_int(dil[0]), L.c_int(dil[1]),
+           L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(col), L.c_ll(col.stride(0)), L.stream())
+    return col
+
+
+def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True):
+    B, H, W, C, ldx = G.nhwc_geom(x)
+    offset, ldo = _pix_major(offset)
+    ldm = 0
+    if mask is not None:
+        mask, ldm = _pix_major(mask)
+    taps = kh * kw
+    dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32) if need_dx else None
+    doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
+    dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
+    L.call('lsnet_dcn_col2im_bf16', L.ptr(gcol), L.c_ll(gcol.stride(0)), L.ptr(x), L.c_int(B), L.c_int(H), L.c_int(W),
+           L.c_int(C), L.c_ll(ldx), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.c_int(Ho), L.c_int(Wo),
+           L.c_int(kh), L.c_int(kw), L.c_int(stride[0]), L.c_int(stride[1]), L.c_int(pad[0]), L.c_int(pad[1]),
+           L.c_int(dil[0]), L.c_int(dil[1]), L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(dx), L.c_ll(C),
+           L.ptr(doff), L.c_ll(dg * 2 * taps), L.ptr(dmask), L.c_ll(dg * taps), L.stream())
+    return (dx.permute(0, 3, 1, 2) if dx is not None else None, doff.permute(0, 3, 1, 2),
+            dmask.permute(0, 3, 1, 2) if dmask is not None else None)
+
+
+def _out_hw(H, W, kh, kw, stride, pad, dil):
+    return ((H + 2 * pad[0] - (dil[0] * (kh - 1) + 1)) // stride[0] + 1,
+            (W + 2 * pad[1] - (dil[1] * (kw - 1) + 1)) // stride[1] + 1)
+
+
+class _DCN(Function):
+
+    @staticmethod
+    def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32):
+        if groups != 1:
+            raise NotImplementedError('lsnet_b200 DCN: groups > 1 (X-101 backbone sites) is not built yet')
+        co, ci, kh, kw = weight.shape
+        x = G.as_nhwc(x, torch.bfloat16)
+        B, _, H, W = x.shape
+        src = offset if out_from_offset else x
+        Ho, Wo = _out_hw(src.shape[2], src.shape[3], kh, kw, stride, pad, dil)
+        if offset.shape[2] != Ho or offset.shape[3] != Wo:
+            raise ValueError(f'offset grid {tuple(offset.shape[2:])} != output grid {(Ho, Wo)}')
+        cfg = (Ho, Wo, kh, kw, stride, pad, dil, scales, dg)
+        col = dcn_im2col(x, offset.detach(), None if mask is None else mask.detach(), *cfg)
+        wp = weight.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
+        npad = (co + 15) // 16 * 16
+        if npad != co:
+            wp = torch.cat([wp, wp.new_zeros(npad - co, wp.shape[1])], 0)
+        b = None
+        if bias is not None:
+            b = torch.zeros(npad, device=x.device, dtype=torch.float32)
+            b[:co] = bias.detach().float()
+        out = G.gemm(col, wp.contiguous(), b, False, torch.float32 if out_fp32 else torch.bfloat16)
+        ctx.save_for_backward(x, offset, mask, weight, col)
+        ctx.cfg, ctx.has_bias = cfg, bias is not None
+        return out.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, offset, mask, weight, col = ctx.saved_tensors
+        Ho, Wo, kh, kw = ctx.cfg[:4]
+        co, ci = weight.shape[:2]
+        B = x.shape[0]
+        gyp = G.pad_channels_nhwc(gy, 8, torch.bfloat16)
+        cop = gyp.shape[1]
+        gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
+        gx = goff = gmask = gw = gb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
+            # B operand [N = taps*ci, K = co]: W^T, K-major
+            wt = weight.detach().permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
+            if cop != co:
+                wt = torch.cat([wt, wt.new_zeros(wt.shape[0], cop - co)], 1)
+            gcol = G.gemm(gy2, wt.contiguous(), None, False, torch.bfloat16)
+            gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
+                                         need_dx=ctx.needs_input_grad[0])
+            if gx is not None:
+                gx = gx.to(torch.bfloat16)
+        if ctx.needs_input_grad[3]:
+            dw = G.gemm_tn(gy2, col)                                   # [cop, taps*ci] fp32
+            gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[4]:
+            gb = gy.float().sum(dim=(0, 2, 3))
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None
+
+
+def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
+                out_fp32=False):
+    """DCNv1 — DeformConvFunction.apply (mmdet/ops/dcn/deform_conv.py:15-111)."""
+    return _DCN.apply(x, offset, None, weight, None, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
+                      groups, deformable_groups, False, out_fp32)
+
+
+def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                          deformable_groups=1, out_fp32=False):
+    """DCNv2 — ModulatedDeformConvFunction.apply (mmdet/ops/dcn/deform_conv.py:114-185)."""
+    return _DCN.apply(x, offset, mask, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
+                      groups, deformable_groups, False, out_fp32)
+
+
+def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                        im2col_step=64, out_fp32=False):
+    """LSNet pyramid DCN — PyramidDeformConvFunction.apply (mmdet/ops/dcn/deform_conv.py:188-287); scales =
+    (scale_h, scale_w); the output grid is the offset grid (:215-217)."""
+    scales = _pair(scales)
+    return _DCN.apply(x, offset, None, weight, None, _pair(stride), _pair(padding), _pair(dilation),
+                      (float(scales[0]), float(scales[1])), groups, deformable_groups, True, out_fp32)
