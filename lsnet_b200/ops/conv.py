@@ -5,7 +5,7 @@ weight re-packing use torch ops."""
 import torch
 from torch.autograd import Function
 
-from . import gemm as G
+from . import gemm_ops as G
 
 
 class _ConvSame(Function):

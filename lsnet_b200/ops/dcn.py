@@ -14,7 +14,7 @@ from torch.autograd import Function
 from torch.nn.modules.utils import _pair
 
 from .. import lib as L
-from . import gemm as G
+from . import gemm_ops as G
 
 
 def _pix_major(t, min_ld_mult=1):
