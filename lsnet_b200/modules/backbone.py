@@ -1,0 +1,160 @@
+"""ResNet / ResNeXt trunks with the reference's constructor arguments and parameter names
+(mmdet/models/backbones/resnet.py:305-646, resnext.py:9-131).  The plain convolutions stay on cuDNN (bf16,
+channels_last) in this round — SURVEY.md §8 row f4 ("next"); the DCNv2 ``conv2`` sites (stage_with_dcn) are built
+through CONV_LAYERS and so land on the B200 deformable kernels (groups == 1 only for now)."""
+import torch
+import torch.nn as nn
+import torch.utils.checkpoint as cp
+
+from ..registry import BACKBONES, build_conv_layer
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, style='pytorch', with_cp=False,
+                 dcn=None, groups=1, base_width=4, base_channels=64):
+        super().__init__()
+        assert style in ('pytorch', 'caffe')
+        width = planes if groups == 1 else int(planes * (base_width / base_channels)) * groups   # resnext.py:33-37
+        s1, s2 = (1, stride) if style == 'pytorch' else (stride, 1)
+        self.with_cp, self.with_dcn = with_cp, dcn is not None
+        self.conv1 = nn.Conv2d(inplanes, width, 1, stride=s1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        fallback = False
+        if dcn is not None:
+            dcn = dict(dcn)
+            fallback = dcn.pop('fallback_on_stride', False)
+        if dcn is None or fallback:
+            self.conv2 = nn.Conv2d(width, width, 3, stride=s2, padding=dilation, dilation=dilation, groups=groups,
+                                   bias=False)
+        else:
+            self.conv2 = build_conv_layer(dcn, width, width, kernel_size=3, stride=s2, padding=dilation,
+                                          dilation=dilation, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, planes * self.expansion, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+
+    norm3 = property(lambda self: self.bn3)
+
+    def _inner(self, x):
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return out + (x if self.downsample is None else self.downsample(x))
+
+    def forward(self, x):
+        out = cp.checkpoint(self._inner, x, use_reentrant=False) if self.with_cp and x.requires_grad else self._inner(x)
+        return self.relu(out)
+
+
+@BACKBONES.register_module()
+class ResNet(nn.Module):
+    arch_settings = {50: (Bottleneck, (3, 4, 6, 3)), 101: (Bottleneck, (3, 4, 23, 3)), 152: (Bottleneck, (3, 8, 36, 3))}
+
+    def __init__(self, depth, in_channels=3, stem_channels=64, base_channels=64, num_stages=4, strides=(1, 2, 2, 2),
+                 dilations=(1, 1, 1, 1), out_indices=(0, 1, 2, 3), style='pytorch', deep_stem=False, avg_down=False,
+                 frozen_stages=-1, conv_cfg=None, norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True,
+                 dcn=None, stage_with_dcn=(False, False, False, False), plugins=None, with_cp=False,
+                 zero_init_residual=True, groups=1, base_width=4):
+        super().__init__()
+        if depth not in self.arch_settings:
+            raise KeyError(f'invalid depth {depth} for resnet')
+        if deep_stem or avg_down or plugins is not None or conv_cfg is not None:
+            raise NotImplementedError('deep_stem / avg_down / plugins / conv_cfg are not on the LSNet path')
+        assert norm_cfg.get('type', 'BN') == 'BN'
+        block, stage_blocks = self.arch_settings[depth]
+        self.depth, self.out_indices, self.frozen_stages = depth, out_indices, frozen_stages
+        self.norm_eval, self.zero_init_residual, self.dcn = norm_eval, zero_init_residual, dcn
+        self.norm_requires_grad = norm_cfg.get('requires_grad', True)
+        self.conv1 = nn.Conv2d(in_channels, stem_channels, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(stem_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.res_layers = []
+        inplanes = stem_channels
+        for i, nblocks in enumerate(stage_blocks[:num_stages]):
+            planes = base_channels * 2 ** i
+            layers = []
+            for j in range(nblocks):
+                stride = strides[i] if j == 0 else 1
+                down = None
+                if j == 0 and (stride != 1 or inplanes != planes * block.expansion):
+                    down = nn.Sequential(nn.Conv2d(inplanes, planes * block.expansion, 1, stride=stride, bias=False),
+                                         nn.BatchNorm2d(planes * block.expansion))
+                layers.append(block(inplanes, planes, stride, dilations[i], down, style, with_cp,
+                                    dcn if stage_with_dcn[i] else None, groups, base_width, base_channels))
+                inplanes = planes * block.expansion
+            name = f'layer{i + 1}'
+            self.add_module(name, nn.Sequential(*layers))
+            self.res_layers.append(name)
+        if not self.norm_requires_grad:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+        self._freeze_stages()
+        self.feat_dim = inplanes
+
+    def _freeze_stages(self):          # resnet.py:569-585
+        if self.frozen_stages >= 0:
+            self.bn1.eval()
+            for m in (self.conv1, self.bn1):
+                for p in m.parameters():
+                    p.requires_grad = False
+        for i in range(1, self.frozen_stages + 1):
+            m = getattr(self, f'layer{i}')
+            m.eval()
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def init_weights(self, pretrained=None):   # resnet.py:587-617
+        if isinstance(pretrained, str):
+            sd = torch.load(pretrained, map_location='cpu')
+            self.load_state_dict(sd.get('state_dict', sd), strict=False)
+            return
+        if pretrained is not None:
+            raise TypeError('pretrained must be a str or None')
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm)):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        for m in self.modules():
+            if isinstance(m, Bottleneck):
+                if hasattr(m.conv2, 'conv_offset'):
+                    nn.init.constant_(m.conv2.conv_offset.weight, 0)
+                    nn.init.constant_(m.conv2.conv_offset.bias, 0)
+                if self.zero_init_residual:
+                    nn.init.constant_(m.bn3.weight, 0)
+
+    def forward(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        outs = []
+        for i, name in enumerate(self.res_layers):
+            x = getattr(self, name)(x)
+            if i in self.out_indices:
+                outs.append(x)
+        return tuple(outs)
+
+    def train(self, mode=True):        # resnet.py:636-646
+        super().train(mode)
+        self._freeze_stages()
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+        return self
+
+
+@BACKBONES.register_module()
+class ResNeXt(ResNet):
+    """resnext.py:76-131: Bottleneck width = planes * base_width / 64 * groups."""
+
+    def __init__(self, groups=1, base_width=4, **kwargs):
+        super().__init__(groups=groups, base_width=base_width, **kwargs)

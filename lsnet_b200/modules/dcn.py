@@ -1,0 +1,144 @@
+"""nn.Module wrappers of the deformable convolutions with the reference's constructor arguments, parameter names
+and registry names (mmdet/ops/dcn/deform_conv.py:295-630): ``DeformConv``, ``DeformConvPack`` ('DCN'),
+``ModulatedDeformConv``, ``ModulatedDeformConvPack`` ('DCNv2'), ``PyramidDeformConv``."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.utils import _pair, _single
+
+from .. import ops
+from ..registry import CONV_LAYERS
+
+
+class _DeformBase(nn.Module):
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super().__init__()
+        assert in_channels % groups == 0, f'in_channels {in_channels} is not divisible by groups {groups}'
+        assert out_channels % groups == 0, f'out_channels {out_channels} is not divisible by groups {groups}'
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride, self.padding, self.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.transposed, self.output_padding = False, _single(0)   # nn.Conv2d compatibility (ConvModule copies them)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+
+class DeformConv(_DeformBase):
+    """deform_conv.py:295-357 (DCNv1, no bias)."""
+
+    def __init__(self, *args, bias=False, **kwargs):
+        assert not bias
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x, offset):
+        ph = max(self.kernel_size[0] - x.size(2), 0)
+        pw = max(self.kernel_size[1] - x.size(3), 0)
+        if ph or pw:   # deform_conv.py:341-349
+            x = F.pad(x, (0, pw, 0, ph))
+            offset = F.pad(offset, (0, pw, 0, ph))
+        out = ops.deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                              self.deformable_groups)
+        if ph or pw:
+            out = out[:, :, :out.size(2) - ph, :out.size(3) - pw]
+        return out
+
+
+@CONV_LAYERS.register_module('DCN')
+class DeformConvPack(DeformConv):
+    """deform_conv.py:360-435: offsets from a zero-initialised conv."""
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 2 * self.kernel_size[0] *
+                                     self.kernel_size[1], kernel_size=self.kernel_size, stride=self.stride,
+                                     padding=self.padding, dilation=self.dilation, bias=True)
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        offset = _offset_conv(self, x)
+        return ops.deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                               self.deformable_groups)
+
+
+class ModulatedDeformConv(_DeformBase):
+    """deform_conv.py:438-485 (DCNv2)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, deformable_groups)
+        self.with_bias = bias
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter('bias', None)
+
+    def forward(self, x, offset, mask):
+        return ops.modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                         self.dilation, self.groups, self.deformable_groups)
+
+
+def _offset_conv(m, x):
+    """conv_offset through the tcgen05 implicit-GEMM kernel when it is a stride-1 'same' conv, else cuDNN."""
+    k, s, p, d = m.kernel_size, m.stride, m.padding, m.dilation
+    if s == (1, 1) and k[0] == k[1] and p[0] == p[1] and d[0] == d[1] and 2 * p[0] == d[0] * (k[0] - 1) and x.is_cuda:
+        return ops.conv2d_same(x, m.conv_offset.weight, m.conv_offset.bias, padding=p[0], dilation=d[0], out_fp32=True)
+    return m.conv_offset(x)
+
+
+@CONV_LAYERS.register_module('DCNv2')
+class ModulatedDeformConvPack(ModulatedDeformConv):
+    """deform_conv.py:488-562: offsets + mask from one zero-initialised 3x3 conv (27 channels)."""
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 3 * self.kernel_size[0] *
+                                     self.kernel_size[1], kernel_size=self.kernel_size, stride=self.stride,
+                                     padding=self.padding, dilation=self.dilation, bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        out = _offset_conv(self, x)
+        n = self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
+        # chunk(3) + cat(o1, o2) keeps the channel order (deform_conv.py:528-531): offsets = first 2n channels
+        offset, mask = out[:, :2 * n], torch.sigmoid(out[:, 2 * n:3 * n])
+        return ops.modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,
+                                         self.dilation, self.groups, self.deformable_groups)
+
+
+class PyramidDeformConv(_DeformBase):
+    """deform_conv.py:565-630: the sampling grid lives on the offset map's level, x is another FPN level."""
+
+    def __init__(self, *args, bias=False, **kwargs):
+        assert not bias
+        super().__init__(*args, **kwargs)
+
+    def forward(self, x, offset, scale_h, scale_w):
+        ph = max(self.kernel_size[0] - x.size(2), 0)
+        pw = max(self.kernel_size[1] - x.size(3), 0)
+        if ph or pw:
+            x = F.pad(x, (0, pw, 0, ph))
+            offset = F.pad(offset, (0, pw, 0, ph))
+        out = ops.pyramid_deform_conv(x, offset, self.weight, (scale_h, scale_w), self.stride, self.padding,
+                                      self.dilation, self.groups, self.deformable_groups)
+        if ph or pw:
+            out = out[:, :, :out.size(2) - ph, :out.size(3) - pw]
+        return out

@@ -1,0 +1,79 @@
+"""LSDetector: backbone -> neck -> LSHead.forward_train, with the reference's registry name, constructor arguments,
+``forward`` / ``train_step`` / ``_parse_losses`` contract (mmdet/models/detectors/lsnet.py:14-56, single_stage.py:16-57,
+base.py:161-243).  Inference (simple_test / aug_test_vote) is SURVEY §8 row f3 ("next")."""
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from ..registry import DETECTORS, build_backbone, build_head, build_neck
+
+
+@DETECTORS.register_module()
+class LSDetector(nn.Module):
+
+    def __init__(self, backbone, neck, bbox_head, train_cfg=None, test_cfg=None, pretrained=None):
+        super().__init__()
+        self.backbone = build_backbone(dict(backbone))
+        self.neck = build_neck(dict(neck)) if neck is not None else None
+        head_cfg = dict(bbox_head)
+        head_cfg.update(train_cfg=train_cfg, test_cfg=test_cfg)
+        self.bbox_head = build_head(head_cfg)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.init_weights(pretrained=pretrained)
+
+    with_neck = property(lambda self: self.neck is not None)
+
+    def init_weights(self, pretrained=None):       # single_stage.py:34-49
+        self.backbone.init_weights(pretrained=pretrained)
+        if self.with_neck:
+            self.neck.init_weights()
+        self.bbox_head.init_weights()
+
+    def extract_feat(self, img):
+        """single_stage.py:51-57.  The trunk runs in bf16 channels_last (cuDNN) under autocast."""
+        img = img.contiguous(memory_format=torch.channels_last)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=img.is_cuda):
+            x = self.backbone(img)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+    def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_masks=None, gt_extremes=None, gt_keypoints=None,
+                      gt_bboxes_ignore=None):
+        x = self.extract_feat(img)
+        return self.bbox_head.forward_train(x, img_metas, gt_bboxes, gt_extremes, gt_keypoints, gt_masks, gt_labels,
+                                            gt_bboxes_ignore)
+
+    def forward(self, img, img_metas, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        raise NotImplementedError('LSDetector test-time paths are not built (SURVEY §8 row f3)')
+
+    def _parse_losses(self, losses, sync_log=False):
+        """base.py:176-209.  The reference all-reduces and .item()s every logged scalar each step; here the scalars
+        stay on the device and are reduced lazily in ONE collective when ``sync_log`` is set (logging interval)."""
+        log_vars = OrderedDict()
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            elif isinstance(value, (list, tuple)):
+                log_vars[name] = sum(v.mean() for v in value)
+            else:
+                raise TypeError(f'{name} is not a tensor or list of tensors')
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        if sync_log:
+            flat = torch.stack([v.detach().float() for v in log_vars.values()])
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(flat.div_(dist.get_world_size()))
+            vals = flat.tolist()
+            log_vars = OrderedDict((k, v) for k, v in zip(log_vars.keys(), vals))
+        return loss, log_vars
+
+    def train_step(self, data, optimizer=None, sync_log=False):
+        """base.py:211-243."""
+        losses = self(**data)
+        loss, log_vars = self._parse_losses(losses, sync_log)
+        return dict(loss=loss, log_vars=log_vars, num_samples=len(data['img_metas']))

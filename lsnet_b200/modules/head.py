@@ -1,0 +1,411 @@
+"""LSHead on the B200 kernels — same registry name, constructor arguments, parameter names and output contract as the
+reference (mmdet/models/dense_heads/lsnet_head.py:17-1437), but the whole target/loss side is batched over images and
+levels on the device with no host synchronisation:
+
+  forward      towers (DCNv2 -> GN -> ReLU), init regression, pyramid-DCN feature aggregation over 3 FPN levels,
+               refine regression + classification                     (lsnet_head.py:479-755)
+  loss         CentroidAssigner (init) -> predicted init boxes -> ATSSAssigner (refine) -> label scatter ->
+               focal + cross-IOU per level                            (lsnet_head.py:757-1437)
+
+Tensors between kernels are pixel-major (channels_last): bf16 feature maps, fp32 prediction maps.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..registry import HEADS, build_assigner, build_loss, build_sampler
+from .dcn import ModulatedDeformConvPack, PyramidDeformConv
+
+
+def _cfg_get(cfg, key, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class B200Conv2d(nn.Conv2d):
+    """nn.Conv2d whose stride-1 'same' forward runs on the tcgen05 implicit-GEMM kernel (parameter names unchanged)."""
+
+    def forward(self, x, relu=False, out_fp32=False):
+        k, p, d = self.kernel_size, self.padding, self.dilation
+        assert self.stride == (1, 1) and self.groups == 1 and 2 * p[0] == d[0] * (k[0] - 1) and k[0] == k[1]
+        return ops.conv2d_same(x, self.weight, self.bias, padding=p[0], dilation=d[0], relu=relu, out_fp32=out_fp32)
+
+
+class _ConvReLU(nn.Sequential):
+    """nn.Sequential(Conv2d, ReLU) with the ReLU fused into the GEMM epilogue; keeps the '.0.weight' key."""
+
+    def __init__(self, cin, cout):
+        super().__init__(B200Conv2d(cin, cout, 1, 1, 0), nn.ReLU())
+
+    def forward(self, x):
+        return self[0](x, relu=True)
+
+
+class DCNConvModule(nn.Module):
+    """lsnet_head.py:1830-1849 — the GroupNorm is named ``bn`` in the reference."""
+
+    def __init__(self, in_channels=256, out_channels=256, kernel_size=3, dilation=1, num_groups=1, dcn_pad=1):
+        super().__init__()
+        self.conv = ModulatedDeformConvPack(in_channels, out_channels, kernel_size, 1, dcn_pad)
+        self.bn = nn.GroupNorm(num_groups, out_channels)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return ops.group_norm_nhwc(self.conv(x), self.bn.num_groups, self.bn.weight, self.bn.bias, self.bn.eps, relu=True)
+
+
+class NormConvModule(nn.Module):
+    """conv_module_type='norm': ConvModule(conv 3x3 -> GN -> ReLU) (lsnet_head.py:118-119)."""
+
+    def __init__(self, cin, cout, num_groups):
+        super().__init__()
+        self.conv = B200Conv2d(cin, cout, 3, 1, 1, bias=False)
+        self.gn = nn.GroupNorm(num_groups, cout)
+
+    def forward(self, x):
+        return ops.group_norm_nhwc(self.conv(x), self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps, relu=True)
+
+
+BRANCHES = {'bbox': ['bbox'], 'segm': ['segm'], 'pose_bbox': ['bbox', 'pose'], 'pose_kbox': ['pose']}
+LOSS_KIND = {'bbox': 'bbox', 'segm': 'polygon', 'pose': 'keypoint'}
+
+
+@HEADS.register_module()
+class LSHead(nn.Module):
+
+    def __init__(self, num_classes, in_channels, point_feat_channels=256, num_kernel_points=9, gradient_mul=0.1,
+                 point_strides=[8, 16, 32, 64, 128], point_base_scale=4, task='bbox', num_vectors=4,
+                 conv_module_type='norm',
+                 loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                 loss_bbox_init=dict(type='CrossIOULoss', loss_weight=1.0),
+                 loss_bbox_refine=dict(type='CrossIOULoss', loss_weight=2.0), loss_segm_init=None,
+                 loss_segm_refine=None, loss_pose_init=None, loss_pose_refine=None,
+                 # AnchorFreeHead kwargs (anchor_free_head.py:42-61)
+                 feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64), dcn_on_last_conv=False,
+                 conv_bias='auto', background_label=None, loss_bbox=None, conv_cfg=None, norm_cfg=None,
+                 train_cfg=None, test_cfg=None):
+        super().__init__()
+        assert task in BRANCHES
+        self.task, self.num_vectors, self.num_kernel_points = task, num_vectors, num_kernel_points
+        self.num_classes, self.cls_out_channels = num_classes, num_classes
+        self.in_channels, self.feat_channels, self.point_feat_channels = in_channels, feat_channels, point_feat_channels
+        self.stacked_convs, self.conv_module_type, self.norm_cfg = stacked_convs, conv_module_type, norm_cfg
+        self.background_label = num_classes if background_label is None else background_label
+        assert self.background_label == 0 or self.background_label == num_classes   # anchor_free_head.py:79-83
+        self.gradient_mul, self.point_base_scale, self.point_strides = gradient_mul, point_base_scale, list(point_strides)
+        self.fpn_levels = list(range(len(self.point_strides)))
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.dcn_kernel = int(np.sqrt(num_kernel_points))
+        self.dcn_pad = int((self.dcn_kernel - 1) / 2)
+        assert self.dcn_kernel * self.dcn_kernel == num_kernel_points, 'The points number should be a square number.'
+        assert self.dcn_kernel % 2 == 1, 'The points number should be an odd square number.'
+        base = np.arange(-self.dcn_pad, self.dcn_pad + 1).astype(np.float64)
+        base_offset = np.stack([np.repeat(base, self.dcn_kernel), np.tile(base, self.dcn_kernel)], axis=1).reshape(-1)
+        self.register_buffer('dcn_base_offset', torch.tensor(base_offset, dtype=torch.float32).view(1, -1, 1, 1),
+                             persistent=False)
+        if train_cfg:
+            init_cfg, refine_cfg = _cfg_get(train_cfg, 'init'), _cfg_get(train_cfg, 'refine')
+            self.init_assigner = build_assigner(dict(_cfg_get(init_cfg, 'assigner')))
+            self.refine_assigner = build_assigner(dict(_cfg_get(refine_cfg, 'assigner')))
+            self.sampler = build_sampler(dict(type='PseudoSampler'), context=self)
+        self.loss_cls = build_loss(dict(loss_cls))
+        for br in BRANCHES[task]:
+            cfg_i, cfg_r = {'bbox': (loss_bbox_init, loss_bbox_refine), 'segm': (loss_segm_init, loss_segm_refine),
+                            'pose': (loss_pose_init, loss_pose_refine)}[br]
+            setattr(self, f'loss_{br}_init', build_loss(dict(cfg_i)))
+            setattr(self, f'loss_{br}_refine', build_loss(dict(cfg_r)))
+        self._init_layers()
+
+    # ------------------------------------------------------------------------------------------ layers
+    def _tower(self):
+        groups = self.norm_cfg['num_groups']
+        mods = nn.ModuleList()
+        for i in range(self.stacked_convs):
+            chn = self.in_channels if i == 0 else self.feat_channels
+            if self.conv_module_type == 'norm':
+                mods.append(NormConvModule(chn, self.feat_channels, groups))
+            else:
+                mods.append(DCNConvModule(chn, self.feat_channels, self.dcn_kernel, 1, groups, self.dcn_pad))
+        return mods
+
+    def _out_dims(self, br):
+        if br == 'bbox':   # lsnet_head.py:170-176, 207-211
+            return 4 * (4 + 1) + (self.num_kernel_points - 4 - 1) * 2, 4 * (4 + 1)
+        d = (self.num_vectors + 1) * 4
+        return d, d
+
+    def _init_layers(self):            # lsnet_head.py:93-257
+        c, pc, groups = self.feat_channels, self.point_feat_channels, self.norm_cfg['num_groups']
+        self.relu = nn.ReLU(inplace=True)
+        self.softplus = nn.Softplus()
+        self.cls_GN = nn.GroupNorm(groups, c)
+        self.cls_convs = self._tower()
+        for br in BRANCHES[self.task]:
+            setattr(self, f'{br}_GN', nn.GroupNorm(groups, c))
+            setattr(self, f'{br}_convs', self._tower())
+        self.pts_cls_conv = PyramidDeformConv(c, pc, self.dcn_kernel, 1, self.dcn_pad)
+        self.pts_cls_out = B200Conv2d(pc, self.cls_out_channels, 1, 1, 0)
+        self.cls_af_dcn_conv = _ConvReLU(3 * pc, pc)
+        self.cls_feat_conv = B200Conv2d(c, pc, 3, 1, 1)
+        for br in BRANCHES[self.task]:
+            d_init, d_ref = self._out_dims(br)
+            setattr(self, f'pts_{br}_init_conv', B200Conv2d(c, pc, 3, 1, 1))
+            setattr(self, f'pts_{br}_init_out', B200Conv2d(pc, d_init, 1, 1, 0))
+            setattr(self, f'pts_{br}_refine_conv', PyramidDeformConv(c, pc, self.dcn_kernel, 1, self.dcn_pad))
+            setattr(self, f'pts_{br}_refine_out', B200Conv2d(pc, d_ref, 1, 1, 0))
+            setattr(self, f'{br}_af_dcn_conv', _ConvReLU(3 * pc, pc))
+            setattr(self, f'{br}_feat_conv', B200Conv2d(c, pc, 3, 1, 1))
+
+    def init_weights(self):            # lsnet_head.py:259-319
+        def normal(m, std=0.01, bias=0.):
+            nn.init.normal_(m.weight, 0, std)
+            if getattr(m, 'bias', None) is not None:
+                nn.init.constant_(m.bias, bias)
+
+        def kaiming(m):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+        towers = ['cls'] + BRANCHES[self.task]
+        for t in towers:
+            for m in getattr(self, f'{t}_convs'):
+                normal(m.conv)
+        kaiming(self.pts_cls_conv)
+        normal(self.pts_cls_out, bias=float(-np.log((1 - 0.01) / 0.01)))
+        normal(self.cls_feat_conv)
+        normal(self.cls_af_dcn_conv[0])
+        for br in BRANCHES[self.task]:
+            normal(getattr(self, f'pts_{br}_init_conv'))
+            normal(getattr(self, f'pts_{br}_init_out'))
+            kaiming(getattr(self, f'pts_{br}_refine_conv'))
+            normal(getattr(self, f'pts_{br}_refine_out'))
+            normal(getattr(self, f'{br}_feat_conv'))
+            normal(getattr(self, f'{br}_af_dcn_conv')[0])
+
+    # ------------------------------------------------------------------------------------------ forward
+    @staticmethod
+    def _signed_pairs(t):
+        """max over each (-,+) slot pair, '-' slot wins ties and is negated (lsnet_head.py:374-377)."""
+        r = t.reshape(t.shape[0], -1, 2, *t.shape[2:])
+        val, ind = r.max(dim=2)
+        return torch.where(ind == 0, -val, val)
+
+    def get_pred_reg(self, raw_reg1, raw_reg2):
+        """lsnet_head.py:372-400: the 9 signed (y,x) sampling points handed to the pyramid DCNs."""
+        if raw_reg2 is not None:
+            return torch.cat((self._signed_pairs(raw_reg1), raw_reg2), dim=1)
+        r = raw_reg1.reshape(raw_reg1.shape[0], -1, 4, *raw_reg1.shape[2:])
+        cts, polys = r[:, -1:], r[:, :-1]
+        if self.task == 'segm':
+            sel = polys[:, ::math.ceil(self.num_vectors / (self.num_kernel_points - 1))]
+        else:
+            sel = polys[:, 1::2]
+        offs = torch.cat([sel, cts], dim=1)
+        offs = offs.reshape(offs.shape[0], -1, 2, *offs.shape[3:])
+        val, ind = offs.max(dim=2)
+        return torch.where(ind == 0, -val, val)
+
+    def forward_single1(self, x):
+        """lsnet_head.py:502-598 for one level: towers + init regression -> (cls_feat, {br: (feat, init_sp, dcn_off)})."""
+        cls_feat = x
+        for m in self.cls_convs:
+            cls_feat = m(cls_feat)
+        out = {}
+        for br in BRANCHES[self.task]:
+            feat = x
+            for m in getattr(self, f'{br}_convs'):
+                feat = m(feat)
+            hid = getattr(self, f'pts_{br}_init_conv')(feat, relu=True)
+            o = getattr(self, f'pts_{br}_init_out')(hid, out_fp32=True)
+            if br == 'bbox':
+                sp = self.softplus(o[:, :20])
+                reg = self.get_pred_reg(sp, o[:, 20:])
+            else:
+                sp = self.softplus(o)
+                reg = self.get_pred_reg(sp, None)
+            reg = (1 - self.gradient_mul) * reg.detach() + self.gradient_mul * reg
+            out[br] = (feat, sp, reg - self.dcn_base_offset)
+        return cls_feat, out
+
+    def forward(self, feats):
+        L = len(feats)
+        lvl = [self.forward_single1(f) for f in feats]
+        cls_feats = [c for c, _ in lvl]
+        brs = BRANCHES[self.task]
+        cls_driver = brs[-1]      # pts_cls_conv follows the pose offsets when both branches exist (:680-681)
+        outs = {'cls': []}
+        for br in brs:
+            outs[br + '_init'] = [lvl[l][1][br][1] for l in range(L)]
+            outs[br + '_refine'] = []
+        for l in range(L):
+            lvls = [l, l + 1, l + 2] if l == 0 else ([l, l - 1, l - 2] if l == L - 1 else [l, l - 1, l + 1])
+            bh, bw = cls_feats[l].shape[2:]
+            offs = {br: lvl[l][1][br][2] for br in brs}
+            raws = {br: [] for br in brs}
+            cls_raws = []
+            for lv in lvls:
+                sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
+                sc = offs[brs[0]].new_tensor([sh, sw] * self.num_kernel_points).view(1, -1, 1, 1)
+                for br in brs:
+                    # the reference scales views of the offset tensor in place, so the factors accumulate over the
+                    # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
+                    offs[br] = offs[br] * sc
+                    raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw))
+                cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw))
+            for br in brs:
+                t = getattr(self, f'{br}_af_dcn_conv')(torch.cat(raws[br], dim=1))
+                t = t + getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0])
+                gn = getattr(self, f'{br}_GN')
+                t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True)
+                t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
+                outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
+            t = self.cls_af_dcn_conv(torch.cat(cls_raws, dim=1)) + self.cls_feat_conv(cls_feats[l])
+            t = ops.group_norm_nhwc(t, self.cls_GN.num_groups, self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True)
+            outs['cls'].append(self.pts_cls_out(t, out_fp32=True))
+        none = [None] * L
+        return (outs['cls'], outs.get('bbox_init', none), outs.get('bbox_refine', none), outs.get('segm_init', none),
+                outs.get('segm_refine', none), outs.get('pose_init', none), outs.get('pose_refine', none))
+
+    # ------------------------------------------------------------------------------------------ loss
+    def forward_train(self, x, img_metas, gt_bboxes, gt_extremes=None, gt_keypoints=None, gt_masks=None,
+                      gt_labels=None, gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
+        outs = self(x)
+        return self.loss(*outs, gt_bboxes, gt_extremes, gt_keypoints, gt_masks, gt_labels, img_metas,
+                         gt_bboxes_ignore=gt_bboxes_ignore)
+
+    @staticmethod
+    def _pack(rows, width, device, dtype=torch.float32):
+        """list of per-image (G_i, width) tensors -> padded [B, Gmax, width] device tensor."""
+        B, Gmax = len(rows), max(1, max(int(r.shape[0]) for r in rows))
+        out = torch.zeros((B, Gmax, width), dtype=dtype)
+        host = all(not r.is_cuda for r in rows)
+        if host:
+            for i, r in enumerate(rows):
+                out[i, :r.shape[0]] = r.reshape(r.shape[0], width).to(dtype)
+            return out.to(device, non_blocking=True)
+        out = out.to(device)
+        for i, r in enumerate(rows):
+            out[i, :r.shape[0]] = r.reshape(r.shape[0], width).to(device=device, dtype=dtype)
+        return out
+
+    def get_border_center(self, gt_bboxes_list):     # lsnet_head.py:1677-1697
+        res = []
+        for b in gt_bboxes_list:
+            x1, y1, x2, y2 = b.unbind(1)
+            cx, cy = (x2 + x1) / 2.0, (y2 + y1) / 2.0
+            res.append(torch.stack([cx, y1, x1, cy, cx, y2, x2, cy, cx, cy], dim=1))
+        return res
+
+    def process_polygons(self, gt_masks_list):
+        """lsnet_head.py:1717-1756: per instance keep the largest polygon component, append the extent centre.
+        Accepts PolygonMasks-like objects (.masks) or pre-processed (G, 2n+2) tensors."""
+        polys, boxes = [], []
+        for gm in gt_masks_list:
+            if torch.is_tensor(gm):
+                P = gm[:, :-2].reshape(gm.shape[0], -1, 2)
+            else:
+                inst = []
+                for comps in gm.masks:
+                    areas = [0.5 * abs(float(np.dot(c.reshape(-1, 2)[:, 0], np.roll(c.reshape(-1, 2)[:, 1], 1)) -
+                                             np.dot(c.reshape(-1, 2)[:, 1], np.roll(c.reshape(-1, 2)[:, 0], 1))))
+                             for c in comps]
+                    best = 0
+                    for ci in range(1, len(comps)):      # strict '<' keeps the first maximum (:1728-1734)
+                        if areas[best] < areas[ci]:
+                            best = ci
+                    inst.append(torch.as_tensor(np.asarray(comps[best]).reshape(-1, 2), dtype=torch.float32))
+                P = torch.stack(inst)
+            xmin, ymin = P[:, :, 0].min(1)[0], P[:, :, 1].min(1)[0]
+            xmax, ymax = P[:, :, 0].max(1)[0], P[:, :, 1].max(1)[0]
+            ct = torch.stack([(xmin + xmax) / 2, (ymin + ymax) / 2], 1).unsqueeze(1)
+            polys.append(torch.cat([P, ct], dim=1).reshape(P.shape[0], -1))
+            boxes.append(torch.stack([xmin, ymin, xmax, ymax], 1))
+        return polys, boxes
+
+    @staticmethod
+    def process_keypoints_with_bbox(gt_bboxes_list, gt_kps_vs_list):     # lsnet_head.py:1758-1785
+        kps, vss = [], []
+        for b, k in zip(gt_bboxes_list, gt_kps_vs_list):
+            x, y, v = k[:, 0::3], k[:, 1::3], k[:, 2::3]
+            ct = torch.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2], 1)
+            kps.append(torch.cat((torch.stack((x, y), dim=2).reshape(k.size(0), -1), ct), 1))
+            vss.append(v)
+        return kps, vss
+
+    def loss(self, cls_scores, bbox_pts_preds_init, bbox_pts_preds_refine, segm_pts_preds_init, segm_pts_preds_refine,
+             pose_pts_preds_init, pose_pts_preds_refine, gt_bboxes, gt_extremes, gt_keypoints_vs, gt_masks, gt_labels,
+             img_metas, gt_bboxes_ignore=None, return_aux=False):
+        dev = cls_scores[0].device
+        task, brs = self.task, BRANCHES[self.task]
+        preds = {'bbox': (bbox_pts_preds_init, bbox_pts_preds_refine), 'segm': (segm_pts_preds_init, segm_pts_preds_refine),
+                 'pose': (pose_pts_preds_init, pose_pts_preds_refine)}
+        tables, gt_vs = {}, None
+        if task in ('bbox', 'pose_bbox'):
+            if gt_extremes is None:
+                gt_extremes = self.get_border_center(gt_bboxes)
+            tables['bbox'] = self._pack(gt_extremes, 10, dev)
+        if task == 'segm':
+            polys, gt_bboxes = self.process_polygons(gt_masks)
+            tables['segm'] = self._pack(polys, polys[0].shape[1], dev)
+        if task in ('pose_bbox', 'pose_kbox'):
+            if task == 'pose_kbox':
+                raise NotImplementedError('pose_kbox target preparation is not built yet')
+            kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
+            tables['pose'] = self._pack(kps, kps[0].shape[1], dev)
+            gt_vs = self._pack(vss, vss[0].shape[1], dev)
+        gt_bb = self._pack(gt_bboxes, 4, dev)
+        gt_cnt = torch.tensor([int(b.shape[0]) for b in gt_bboxes], dtype=torch.int32).to(dev, non_blocking=True)
+        gt_lab = None
+        if gt_labels is not None:
+            gt_lab = self._pack([l.view(-1, 1) for l in gt_labels], 1, dev, torch.int32).squeeze(-1).contiguous()
+
+        sizes = [tuple(c.shape[-2:]) for c in cls_scores]
+        pyr = ops.Pyramid(sizes, self.point_strides, [m['pad_shape'][:2] for m in img_metas], dev)
+        init_acfg = _cfg_get(_cfg_get(self.train_cfg, 'init'), 'assigner')
+        ref_acfg = _cfg_get(_cfg_get(self.train_cfg, 'refine'), 'assigner')
+        # ---- init stage: nearest centre point of the GT's scale level (get_targets(stage='init')) ----
+        a_init = ops.centroid_assign(pyr, gt_bb, gt_cnt, float(_cfg_get(init_acfg, 'scale', 4)))
+        _, _, npos_init = ops.assign_targets(pyr, a_init, gt_lab, self.num_classes)
+        # ---- refine stage: ATSS on the boxes decoded from the detached init predictions (:1333-1374) ----
+        prim = brs[0]
+        with torch.no_grad():
+            boxes = ops.pred_boxes(pyr, [p.detach() for p in preds[prim][0]], polygon=(prim != 'bbox'))
+        a_ref = ops.atss_assign(pyr, boxes, gt_bb, gt_cnt, int(_cfg_get(ref_acfg, 'topk', 9)))
+        labels, lweights, npos_ref = ops.assign_targets(pyr, a_ref, gt_lab, self.num_classes)
+        # num_total_pos = sum_i max(n_pos_i, 1), per GPU (lsnet_head.py:984)
+        avg_init = npos_init.clamp(min=1).sum().float()
+        avg_ref = npos_ref.clamp(min=1).sum().float()
+
+        losses = {'loss_cls': []}
+        for br in brs:
+            losses[f'loss_{br}_init'], losses[f'loss_{br}_refine'] = [], []
+        B = cls_scores[0].shape[0]
+        for l, s in enumerate(self.point_strides):
+            off, P = int(pyr.offsets[l]), pyr.num_level[l]
+            cs = cls_scores[l]
+            Bc, C, H, W = cs.shape
+            rows = torch.as_strided(cs, (B * H * W, C), (cs.stride(3), 1))
+            lab = labels[:, off:off + P].reshape(-1)
+            lw = lweights[:, off:off + P].reshape(-1)
+            losses['loss_cls'].append(self.loss_cls(rows, lab, lw, avg_factor=avg_ref))
+            for br in brs:
+                kind = LOSS_KIND[br]
+                for stage, a, avg in (('init', a_init, avg_init), ('refine', a_ref, avg_ref)):
+                    mod = getattr(self, f'loss_{br}_{stage}')
+                    pred = preds[br][0 if stage == 'init' else 1][l]
+                    total = ops.cross_iou_level_loss(pred, a, off, float(s), float(self.point_base_scale), tables[br],
+                                                     gt_bb, gt_vs if kind == 'keypoint' else None, loss_type=kind,
+                                                     eps=mod.eps, alpha=mod.alpha, pstride=mod.stride)
+                    losses[f'loss_{br}_{stage}'].append(mod.loss_weight * total / avg)
+        if return_aux:
+            return losses, dict(assign_init=a_init, assign_refine=a_ref, labels=labels, label_weights=lweights,
+                                npos_init=npos_init, npos_refine=npos_ref, boxes=boxes)
+        return losses
+
+    def get_bboxes(self, *args, **kwargs):
+        raise NotImplementedError('inference decode (lsnet_head.py:1439-1668) is SURVEY §8 row f3 ("next")')

@@ -4,3 +4,4 @@ from .dcn import deform_conv, modulated_deform_conv, pyramid_deform_conv, dcn_im
 from .loss import (cross_iou_loss_rows, cross_iou_level_loss, sigmoid_focal_loss_sum,  # noqa: F401
                    directional_targets)
 from .assign import (Pyramid, centroid_assign, atss_assign, assign_targets, pred_boxes)  # noqa: F401
+from .norm import group_norm_nhwc  # noqa: F401
