@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of one LSNet training step (R50-FPN, 800x1333 -> padded 800x1344, batch 4 per GPU, bf16),
+BASELINE.json's metric on BASELINE.json's configs[1], on N GPUs of one node (one process per GPU, NCCL).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU arm: the oracle port of the reference path on the host cores
+
+A "step" = forward + cross-IOU/focal loss + backward + grad-clip + SGD(momentum) on one synthetic batch.
+``value``  : inputs already resident in HBM (K steps, CUDA events, barrier + synchronize on both sides, max over ranks)
+``e2e``    : the same K steps through the public API with HOST (pinned) image tensors: H2D copy of the batch and a
+             D2H read of the loss inside the timed region, every step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'images/sec training step, LSNet R50-FPN 800x1333'
+WORKLOAD = 'LSNet-bbox R50-FPN 800x1333 (padded 800x1344) bf16, batch 4/GPU, synthetic COCO-shaped'
+IMG_HW = (800, 1333)
+BATCH = 4
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2])
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step_factory(threads):
+    """The reference path restated for the CPU (oracle/): one training step = LSDetector fwd + loss + bwd + clip +
+    SGD on a bounded sample.  Returns (step_fn, sample_description, images_per_step_equivalent)."""
+    from oracle import init as oinit
+    from oracle import lsnet_oracle as O
+    from lsnet_b200.data import synthetic_batch
+    torch.set_num_threads(threads)
+    sd = oinit.make_state_dict('bbox', seed=0)
+    keys = O.trainable_keys(sd)
+    mom = {}
+
+    def run(hw, step):
+        b = synthetic_batch(step, batch=1, img_hw=hw)
+        for k in keys:
+            sd[k].requires_grad_(True)
+            sd[k].grad = None
+        losses = O.detector_losses(sd, b['img'], b['gt_bboxes'], b['gt_labels'], b['img_metas'], task='bbox',
+                                   gt_extremes=b['gt_extremes'])
+        total, _ = O.parse_losses(losses)
+        total.backward()
+        grads = {k: sd[k].grad for k in keys if sd[k].grad is not None}
+        for k in keys:
+            sd[k].requires_grad_(False)
+        O.sgd_step(sd, grads, mom)
+        return float(total)
+    return run
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    run = cpu_reference_step_factory(threads)
+    # calibrate on a small image, then pick the largest sample that keeps (warmup+steps) within ~4 minutes
+    t0 = time.perf_counter(); run((384, 512), 0); t_small = time.perf_counter() - t0
+    full_px, small_px = 800 * 1344, 384 * 512
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    scale = min(1.0, budget / (t_small * full_px / small_px))
+    if scale >= 1.0:
+        hw, sample = IMG_HW, '1 image 800x1333 per step (full resolution)'
+    else:
+        f = max(scale, small_px / full_px) ** 0.5
+        hw = (max(384, int(800 * f) // 32 * 32), max(512, int(1333 * f) // 32 * 32))
+        sample = f'1 image {hw[0]}x{hw[1]} per step; value scaled by pixel count to 800x1344-equivalent images'
+    eq = (((hw[0] + 31) // 32 * 32) * ((hw[1] + 31) // 32 * 32)) / full_px
+    for w in range(args.warmup):
+        run(hw, w)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        run(hw, args.warmup + s)
+    dt = time.perf_counter() - t0
+    value = args.steps * eq / dt
+    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload=WORKLOAD, cpu_sample=sample),
+                cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
+                e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from lsnet_b200 import lib as L
+    from lsnet_b200.data import MODEL_CFG, synthetic_batch, to_device
+    from lsnet_b200.train import Trainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(0)
+    tr = Trainer(MODEL_CFG['bbox_r50'], device=dev, distributed=distributed)
+    nb = 4
+    host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True) for s in range(nb)]
+    resident = [to_device(b, dev) for b in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms)
+
+    for w in range(max(args.warmup, 3)):
+        tr.step(resident[w % nb])
+    lib = L.load()
+    lib.lsnet_launch_count.restype = ctypes.c_ulonglong
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    # ---- value: inputs resident in HBM; kernel-class timing (CUDA events on the launch stream) enabled ----
+    lib.lsnet_timing_reset()
+    lib.lsnet_timing_enable(1)
+    l0 = L.launch_count()
+    ms = timed(lambda s: tr.step(resident[s % nb]), args.steps)
+    launches = L.launch_count() - l0
+    lib.lsnet_timing_enable(0)
+    classes = {}
+    for cls, name in enumerate(['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)',
+                                'dcn_im2col(gather)', 'dcn_col2im(scatter)']):
+        tms, n, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+        lib.lsnet_timing_collect(cls, ctypes.byref(tms), ctypes.byref(n), ctypes.byref(work))
+        classes[name] = dict(ms=tms.value, launches=n.value, work=work.value)
+    lib.lsnet_timing_reset()
+    # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
+    h2d = host[0]['img'].numel() * 4
+
+    def e2e_step(s):
+        b = to_device(host[s % nb], dev)
+        loss, _ = tr.step(b)
+        loss.item()
+    ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    imgs = BATCH * world * args.steps
+    value, e2e = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
+    # dominant kernel class = the one with the largest share of the timed region
+    dom = max(classes, key=lambda k: classes[k]['ms'])
+    c = classes[dom]
+    per_launch_ms = c['ms'] / max(1, c['launches'])
+    if 'gemm' in dom:
+        achieved = c['work'] / (c['ms'] / 1e3) / 1e12 if c['ms'] > 0 else 0.0
+        roof = dict(bound='tensor', kernel=dom, achieved=achieved, peak=peaks['tf_sustained'], unit='TFLOP/s',
+                    frac=achieved / peaks['tf_sustained'], traffic=None)
+    else:
+        achieved = c['work'] / (c['ms'] / 1e3) / 1e9 if c['ms'] > 0 else 0.0
+        roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peaks['hbm'], unit='GB/s',
+                    frac=achieved / peaks['hbm'], traffic=None)
+    roof.update(peak_source=peaks['src'] + (' sustained' if 'gemm' in dom else ''),
+                share_of_step=c['ms'] / ms, avg_launch_ms=per_launch_ms, launches=c['launches'],
+                classes={k: dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
+                                 achieved=(v['work'] / (v['ms'] / 1e3) / (1e12 if 'gemm' in k else 1e9)) if v['ms'] > 0 else 0.0,
+                                 unit='TFLOP/s' if 'gemm' in k else 'GB/s') for k, v in classes.items()})
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            run = cpu_reference_step_factory(threads)
+            hw = (384, 640)
+            run(hw, 0)
+            t0 = time.perf_counter(); n = 0
+            while time.perf_counter() - t0 < 15.0 and n < 8:
+                run(hw, 1 + n); n += 1
+            dt = time.perf_counter() - t0
+            eq = (384 * 640) / (800 * 1344)
+            cpu = dict(value=n * eq / dt, unit='images/s', cores=threads, kind='port',
+                       sample=f'{n} training steps on 1 image 384x640 (oracle port of the reference path, fp32); value '
+                              'scaled by pixel count to 800x1344-equivalent images/s')
+        except Exception as e:   # the baseline must never take the GPU number down with it
+            cpu = dict(value=None, unit='images/s', cores=os.cpu_count(), kind='port', sample=f'failed: {e!r}')
+    line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                data='synthetic',
+                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
+                            l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
+                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights'),
+                e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clk)
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

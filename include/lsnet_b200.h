@@ -24,6 +24,13 @@ unsigned long long lsnet_launch_count(void);    /* kernels launched by this libr
 int lsnet_abi_version(void);
 int lsnet_require_sm100(void);                  /* 0 iff the current CUDA device is compute capability 10.x */
 
+/* Optional device timing per kernel class (0 tcgen05 GEMM/conv, 1 weight-gradient GEMM, 2 DCN gather, 3 DCN scatter):
+ * when enabled every launch of the class is bracketed by CUDA events on its own stream; collect() returns the summed
+ * elapsed ms, the launch count and the summed algorithmic work (FLOPs for 0/1, bytes for 2/3) since the last reset. */
+void lsnet_timing_enable(int on);
+int lsnet_timing_collect(int kernel_class, double* total_ms, long long* launches, double* work);
+void lsnet_timing_reset(void);
+
 /* ---- tcgen05 GEMM / implicit-GEMM convolution ----------------------------------------------------------------
  * out[M,N] = A[M,K] . Bw[N,K]^T (+ bias[N]) (ReLU);  bf16 operands, fp32 accumulation in TMEM, out bf16 or fp32.
  * Replaces the per-sample `addmm_` of the reference (mmdet/ops/dcn/src/cuda/deform_conv_cuda.cpp:673-678, 890-895,

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "lsnet_internal.h"
 
 namespace lsn {
@@ -23,6 +25,47 @@ int check_launch(const char* what) {
   return 0;
 }
 }  // namespace lsn
+
+// ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launch stream ---------------
+namespace lsn {
+struct TimedLaunch { int cls; cudaEvent_t a, b; double work; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+bool timing_on() { return g_timing; }
+int timing_begin(int cls, double work, cudaStream_t st) {
+  if (!g_timing) return -1;
+  TimedLaunch t{cls, get_event(), get_event(), work};
+  cudaEventRecord(t.a, st);
+  g_timed.push_back(t);
+  return static_cast<int>(g_timed.size()) - 1;
+}
+void timing_end(int h, cudaStream_t st) {
+  if (h >= 0) cudaEventRecord(g_timed[h].b, st);
+}
+}  // namespace lsn
+
+extern "C" void lsnet_timing_enable(int on) { lsn::g_timing = on != 0; }
+// Sums elapsed ms / launches / algorithmic work (FLOPs or bytes) of one kernel class since the last reset; syncs.
+extern "C" int lsnet_timing_collect(int cls, double* total_ms, long long* launches, double* work) {
+  *total_ms = 0; *launches = 0; *work = 0;
+  for (auto& t : lsn::g_timed) {
+    if (t.cls != cls) continue;
+    if (cudaEventSynchronize(t.b) != cudaSuccess) return lsn::set_error("timing: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    *total_ms += ms; *launches += 1; *work += t.work;
+  }
+  return 0;
+}
+extern "C" void lsnet_timing_reset(void) {
+  for (auto& t : lsn::g_timed) { lsn::g_pool.push_back(t.a); lsn::g_pool.push_back(t.b); }
+  lsn::g_timed.clear();
+}
 
 extern "C" const char* lsnet_last_error(void) { return lsn::g_err; }
 extern "C" unsigned long long lsnet_launch_count(void) { return lsn::g_launches; }

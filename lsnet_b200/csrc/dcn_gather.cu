@@ -230,8 +230,13 @@ extern "C" int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, 
   DcnGeom g{B, H, W, C, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, scale_h, scale_w,
             deformable_groups, ldx, ldo, ldm, ldcol};
   dim3 grid((Wo + PATCH_W - 1) / PATCH_W, (Ho + PATCH_H - 1) / PATCH_H, B);
+  const double taps = kh * kw, px = static_cast<double>(B) * Ho * Wo;
+  // algorithmic bytes: x read once (B*H*W*2C) + offsets/mask (4*(2+[mask])*taps per px) + bf16 columns written
+  const double bytes = static_cast<double>(B) * H * W * 2.0 * C + px * 4.0 * taps * (mask ? 3 : 2) + px * 2.0 * taps * C;
+  const int th = timing_begin(TC_IM2COL, bytes, static_cast<cudaStream_t>(stream));
   dcn_im2col_kernel<<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), offset, mask, static_cast<__nv_bfloat16*>(col), g);
+  timing_end(th, static_cast<cudaStream_t>(stream));
   return check_launch("dcn_im2col");
 }
 
@@ -247,8 +252,14 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
   DcnGeom g{B, H, W, C, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, scale_h, scale_w,
             deformable_groups, ldx, ldo, ldm, ldcol};
   dim3 grid((Wo + PATCH_W - 1) / PATCH_W, (Ho + PATCH_H - 1) / PATCH_H, B);
+  const double taps = kh * kw, px = static_cast<double>(B) * Ho * Wo;
+  // algorithmic bytes: dCol read (2*taps*C per px) + x read + offsets/mask read + dX written (fp32) + dOffset/dMask
+  const double bytes = px * 2.0 * taps * C + static_cast<double>(B) * H * W * (2.0 * C + (dx ? 4.0 * C : 0.0)) +
+                       px * 4.0 * taps * (mask ? 3 : 2) * 2.0;
+  const int th = timing_begin(TC_COL2IM, bytes, static_cast<cudaStream_t>(stream));
   dcn_col2im_kernel<<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
       dmask, g, lddx, lddo, lddm);
+  timing_end(th, static_cast<cudaStream_t>(stream));
   return check_launch("dcn_col2im");
 }

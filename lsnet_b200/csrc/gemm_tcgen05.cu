@@ -497,7 +497,9 @@ static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   }
   int tiles = a.m_tiles * a.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
+  const int th = timing_begin(TC_GEMM, 2.0 * a.M * a.N * a.num_k_iters * BK, st);
   gemm_kmajor_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  timing_end(th, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_kmajor<%d> launch: %s", BN, cudaGetErrorString(e));
   count_launch();
@@ -575,7 +577,9 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArg
   a.splits = splits;
   int items = base * splits;
   int grid = items < num_sms() ? items : num_sms();
+  const int th = timing_begin(TC_WGRAD, 2.0 * a.M * a.N * a.taps * a.k_chunks * BK, st);
   gemm_mnmajor_kernel<<<grid, kThreads, kWSmemBytes, st>>>(tmA, tmB, a);
+  timing_end(th, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm_mnmajor launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -8,4 +8,8 @@ int set_error(const char* fmt, ...);
 // every kernel launch of this library bumps the counter reported by lsnet_launch_count()
 void count_launch();
 int check_launch(const char* what);
+// kernel classes for the optional device timing (api.cu)
+enum { TC_GEMM = 0, TC_WGRAD = 1, TC_IM2COL = 2, TC_COL2IM = 3 };
+int timing_begin(int cls, double work, cudaStream_t st);
+void timing_end(int handle, cudaStream_t st);
 }  // namespace lsn
