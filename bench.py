@@ -21,7 +21,12 @@ import sys
 import threading
 import time
 
-import torch
+# The CPU arm mixes two OpenMP runtimes (torch's bundled libgomp and the system one behind oracle/dcn_ref.c); with
+# active spinning they fight over the cores, so make idle workers sleep.  Must be set before either is loaded.
+os.environ.setdefault('OMP_WAIT_POLICY', 'PASSIVE')
+os.environ.setdefault('GOMP_SPINCOUNT', '0')
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -30,6 +35,23 @@ METRIC = 'images/sec training step, LSNet R50-FPN 800x1333'
 WORKLOAD = 'LSNet-bbox R50-FPN 800x1333 (padded 800x1344) bf16, batch 4/GPU, synthetic COCO-shaped'
 IMG_HW = (800, 1333)
 BATCH = 4
+
+
+def usable_cores():
+    """Host cores this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_threads():
+    # beyond ~32 threads the CPU path (many small convs / per-image target code) stops scaling and starts thrashing
+    return max(1, min(usable_cores(), 32))
 
 
 def _peaks():
@@ -94,6 +116,11 @@ def cpu_reference_step_factory(threads):
     from oracle import lsnet_oracle as O
     from lsnet_b200.data import synthetic_batch
     torch.set_num_threads(threads)
+    os.environ['OMP_NUM_THREADS'] = str(threads)
+    try:
+        ctypes.CDLL('libgomp.so.1').omp_set_num_threads(threads)   # the C restatement's runtime
+    except OSError:
+        pass
     sd = oinit.make_state_dict('bbox', seed=0)
     keys = O.trainable_keys(sd)
     mom = {}
@@ -118,7 +145,7 @@ def cpu_reference_step_factory(threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     run = cpu_reference_step_factory(threads)
     # calibrate on a small image, then pick the largest sample that keeps (warmup+steps) within ~4 minutes
     t0 = time.perf_counter(); run((384, 512), 0); t_small = time.perf_counter() - t0
@@ -242,7 +269,7 @@ def run_gpu(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            threads = os.cpu_count() or 1
+            threads = cpu_threads()
             run = cpu_reference_step_factory(threads)
             hw = (384, 640)
             run(hw, 0)
@@ -255,7 +282,7 @@ def run_gpu(args, rank, world, local_rank):
                        sample=f'{n} training steps on 1 image 384x640 (oracle port of the reference path, fp32); value '
                               'scaled by pixel count to 800x1344-equivalent images/s')
         except Exception as e:   # the baseline must never take the GPU number down with it
-            cpu = dict(value=None, unit='images/s', cores=os.cpu_count(), kind='port', sample=f'failed: {e!r}')
+            cpu = dict(value=None, unit='images/s', cores=cpu_threads(), kind='port', sample=f'failed: {e!r}')
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                 data='synthetic',

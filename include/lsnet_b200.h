@@ -60,6 +60,17 @@ int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, l
                                  int C, int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, float* dw,
                                  void* stream);
 
+/* ---- GroupNorm (+ residual add, + ReLU) over pixel-major bf16 maps: nn.GroupNorm(32, 256) sites of FPN / LSHead
+ * (mmdet/models/necks/fpn.py:117-133; mmdet/models/dense_heads/lsnet_head.py:97-113, 700-708, 1843).
+ * y = relu?(GN(x (+ x2))).  stats: double [B, G, 2] workspace written by fwd and read by bwd.  (C/G) % 8 == 0. */
+int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2, long long ldx2, int B, int HW, int C, int G,
+                        const float* gamma, const float* beta, float eps, int relu, double* stats, void* y,
+                        long long ldy, void* stream);
+int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy, long long lddy,
+                        int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
+                        const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
+                        void* stream);
+
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel

@@ -1,0 +1,285 @@
+// GroupNorm (+ optional residual add, + optional ReLU) over pixel-major bf16 maps, forward and backward (sm_100a).
+// Replaces the nn.GroupNorm calls that sit between every pair of hot kernels in FPN / LSHead
+// (mmdet/models/necks/fpn.py:117-133 ConvModule norm, dense_heads/lsnet_head.py:97-113,700-708,1843) — SURVEY §8 row f1.
+// HBM-bound streaming kernels: forward reads x twice (statistics, apply) and writes y once; backward reads x, dy twice
+// and writes dx once.  Statistics: fp32 partial sums per CTA, fp64 atomics across CTAs (no cancellation trouble for
+// E[x^2]-E[x]^2 at 134k elements per group), one thread = one 16-byte vector = 8 channels of ONE group.
+#include "common.cuh"
+#include "lsnet_internal.h"
+
+namespace lsn {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_PIX_PER_CTA = 128;
+
+struct GnArgs {
+  int B, HW, C, G;          // C/G % 8 == 0
+  long long ldx, ldx2, ldy;
+  float eps;
+  int relu;
+};
+
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                            pack_bf16x2(f[6], f[7]));
+}
+
+// grid (ceil(HW / GN_PIX_PER_CTA), B).  stats[b][g] = {sum, sumsq} (double, pre-zeroed)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2, const GnArgs a,
+                double* __restrict__ stats) {
+  extern __shared__ float sm[];   // [vecs_per_pixel][2] partial per vector column
+  const int vpp = a.C / 8;        // 16-byte vectors per pixel
+  const int cpg8 = (a.C / a.G) / 8;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * GN_PIX_PER_CTA, p1 = min(a.HW, p0 + GN_PIX_PER_CTA);
+  for (int i = threadIdx.x; i < vpp * 2; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  // thread -> (vector column v, pixel lane): consecutive threads walk consecutive vectors of a pixel (coalesced)
+  const int total = (p1 - p0) * vpp;
+  float s = 0.f, ss = 0.f;
+  int my_v = -1;
+  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+    const int v = i % vpp, p = p0 + i / vpp;
+    if (my_v >= 0 && v != my_v) {   // only when GN_THREADS % vpp != 0: flush and switch column
+      atomicAdd(&sm[2 * my_v], s); atomicAdd(&sm[2 * my_v + 1], ss); s = ss = 0.f;
+    }
+    my_v = v;
+    float f[8];
+    ld8(x + (static_cast<long long>(b) * a.HW + p) * a.ldx + v * 8, f);
+    if (x2) {
+      float f2[8];
+      ld8(x2 + (static_cast<long long>(b) * a.HW + p) * a.ldx2 + v * 8, f2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s += f[e]; ss += f[e] * f[e]; }
+  }
+  if (my_v >= 0) { atomicAdd(&sm[2 * my_v], s); atomicAdd(&sm[2 * my_v + 1], ss); }
+  __syncthreads();
+  for (int g = threadIdx.x; g < a.G; g += GN_THREADS) {
+    float gs = 0.f, gss = 0.f;
+    for (int j = 0; j < cpg8; ++j) { gs += sm[2 * (g * cpg8 + j)]; gss += sm[2 * (g * cpg8 + j) + 1]; }
+    atomicAdd(&stats[(static_cast<long long>(b) * a.G + g) * 2], static_cast<double>(gs));
+    atomicAdd(&stats[(static_cast<long long>(b) * a.G + g) * 2 + 1], static_cast<double>(gss));
+  }
+}
+
+__device__ __forceinline__ void mean_rstd(const double* stats, int b, int g, const GnArgs& a, float* mean, float* rstd) {
+  const double n = static_cast<double>(a.HW) * (a.C / a.G);
+  const double m = stats[(static_cast<long long>(b) * a.G + g) * 2] / n;
+  double var = stats[(static_cast<long long>(b) * a.G + g) * 2 + 1] / n - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  *mean = static_cast<float>(m);
+  *rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+}
+
+// y = relu?((x (+x2) - mean) * rstd * gamma + beta)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2, const GnArgs a,
+                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ y) {
+  const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
+  const long long total = static_cast<long long>(a.B) * a.HW * vpp;
+  for (long long i = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * GN_THREADS) {
+    const int v = static_cast<int>(i % vpp);
+    const long long px = i / vpp;
+    const int b = static_cast<int>(px / a.HW);
+    float mean, rstd;
+    mean_rstd(stats, b, v / cpg8, a, &mean, &rstd);
+    float f[8];
+    ld8(x + px * a.ldx + v * 8, f);
+    if (x2) {
+      float f2[8];
+      ld8(x2 + px * a.ldx2 + v * 8, f2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float o = (f[e] - mean) * rstd * gm[e] + bt[e];
+      f[e] = a.relu ? fmaxf(o, 0.f) : o;
+    }
+    st8(y + px * a.ldy + v * 8, f);
+  }
+}
+
+// Backward pass 1: per (b,g): s1 = sum dy'*gamma, s2 = sum dy'*gamma*xhat;  per channel: dgamma += dy'*xhat,
+// dbeta += dy'   (dy' = dy * [y > 0] when relu).  bstats (double, pre-zeroed) [B][G][2]; dgamma/dbeta fp32 pre-zeroed.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2,
+                    const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
+                    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    double* __restrict__ bstats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];   // per channel: dgamma, dbeta [2*C]; per vector column: s1, s2 [2*vpp]
+  const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
+  float* sm_dg = sm;
+  float* sm_db = sm + a.C;
+  float* sm_s = sm + 2 * a.C;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * GN_PIX_PER_CTA, p1 = min(a.HW, p0 + GN_PIX_PER_CTA);
+  for (int i = threadIdx.x; i < 2 * a.C + 2 * vpp; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  const int total = (p1 - p0) * vpp;
+  float dg[8], db[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dg[e] = db[e] = 0.f;
+  int my_v = -1;
+  auto flush = [&]() {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { atomicAdd(&sm_dg[my_v * 8 + e], dg[e]); atomicAdd(&sm_db[my_v * 8 + e], db[e]); dg[e] = db[e] = 0.f; }
+    atomicAdd(&sm_s[2 * my_v], s1); atomicAdd(&sm_s[2 * my_v + 1], s2); s1 = s2 = 0.f;
+  };
+  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+    const int v = i % vpp, p = p0 + i / vpp;
+    if (my_v >= 0 && v != my_v) flush();
+    my_v = v;
+    const long long px = static_cast<long long>(b) * a.HW + p;
+    float mean, rstd;
+    mean_rstd(stats, b, v / cpg8, a, &mean, &rstd);
+    float f[8], d[8];
+    ld8(x + px * a.ldx + v * 8, f);
+    if (x2) {
+      float f2[8];
+      ld8(x2 + px * a.ldx2 + v * 8, f2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
+    }
+    ld8(dy + px * lddy + v * 8, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gm = __ldg(gamma + v * 8 + e);
+      const float xh = (f[e] - mean) * rstd;
+      float dd = d[e];
+      if (a.relu && !(xh * gm + __ldg(beta + v * 8 + e) > 0.f)) dd = 0.f;
+      dg[e] += dd * xh;
+      db[e] += dd;
+      s1 += dd * gm;
+      s2 += dd * gm * xh;
+    }
+  }
+  if (my_v >= 0) flush();
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += GN_THREADS) {
+    atomicAdd(&dgamma[c], sm_dg[c]);
+    atomicAdd(&dbeta[c], sm_db[c]);
+  }
+  for (int g = threadIdx.x; g < a.G; g += GN_THREADS) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int j = 0; j < cpg8; ++j) { t1 += sm_s[2 * (g * cpg8 + j)]; t2 += sm_s[2 * (g * cpg8 + j) + 1]; }
+    atomicAdd(&bstats[(static_cast<long long>(b) * a.G + g) * 2], static_cast<double>(t1));
+    atomicAdd(&bstats[(static_cast<long long>(b) * a.G + g) * 2 + 1], static_cast<double>(t2));
+  }
+}
+
+// Backward pass 2: dx = rstd * (dy'*gamma - (s1 + xhat*s2)/n)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2,
+                    const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
+                    const double* __restrict__ stats, const double* __restrict__ bstats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ dx,
+                    long long lddx) {
+  const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
+  const float inv_n = 1.f / (static_cast<float>(a.HW) * (a.C / a.G));
+  const long long total = static_cast<long long>(a.B) * a.HW * vpp;
+  for (long long i = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * GN_THREADS) {
+    const int v = static_cast<int>(i % vpp);
+    const long long px = i / vpp;
+    const int b = static_cast<int>(px / a.HW), g = v / cpg8;
+    float mean, rstd;
+    mean_rstd(stats, b, g, a, &mean, &rstd);
+    const float s1 = static_cast<float>(bstats[(static_cast<long long>(b) * a.G + g) * 2]);
+    const float s2 = static_cast<float>(bstats[(static_cast<long long>(b) * a.G + g) * 2 + 1]);
+    float f[8], d[8];
+    ld8(x + px * a.ldx + v * 8, f);
+    if (x2) {
+      float f2[8];
+      ld8(x2 + px * a.ldx2 + v * 8, f2);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
+    }
+    ld8(dy + px * lddy + v * 8, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gm = __ldg(gamma + v * 8 + e);
+      const float xh = (f[e] - mean) * rstd;
+      float dd = d[e];
+      if (a.relu && !(xh * gm + __ldg(beta + v * 8 + e) > 0.f)) dd = 0.f;
+      f[e] = rstd * (dd * gm - (s1 + xh * s2) * inv_n);
+    }
+    st8(dx + px * lddx + v * 8, f);
+  }
+}
+
+static int gn_check(const char* who, int C, int G, long long ldx, long long ldy) {
+  if (G < 1 || C % G || (C / G) % 8 || (ldx % 8) || (ldy % 8) || C > 4096)
+    return set_error("%s: needs (C/G) %% 8 == 0 and 16-byte aligned pitches (C=%d G=%d)", who, C, G);
+  return 0;
+}
+static int gn_grid(long long total_vec) {
+  long long blocks = (total_vec + GN_THREADS - 1) / GN_THREADS;
+  return static_cast<int>(blocks < 148 * 8 ? (blocks < 1 ? 1 : blocks) : 148 * 8);
+}
+
+}  // namespace lsn
+
+using namespace lsn;
+
+extern "C" int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2, long long ldx2, int B, int HW, int C,
+                                   int G, const float* gamma, const float* beta, float eps, int relu, double* stats,
+                                   void* y, long long ldy, void* stream) {
+  if (B <= 0 || HW <= 0) return 0;
+  if (int rc = gn_check("lsnet_groupnorm_fwd", C, G, ldx, ldy)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GnArgs a{B, HW, C, G, ldx, ldx2, ldy, eps, relu};
+  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * G, st);
+  dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
+  gn_stats_kernel<<<grid, GN_THREADS, sizeof(float) * 2 * (C / 8), st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats);
+  if (int rc = check_launch("gn_stats")) return rc;
+  gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8)), GN_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats, gamma, beta,
+      static_cast<__nv_bfloat16*>(y));
+  return check_launch("gn_apply");
+}
+
+extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
+                                   long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
+                                   float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
+                                   float* dgamma, float* dbeta, void* stream) {
+  if (B <= 0 || HW <= 0) return 0;
+  if (int rc = gn_check("lsnet_groupnorm_bwd", C, G, ldx, lddx)) return rc;
+  if (lddy % 8) return set_error("lsnet_groupnorm_bwd: dy pitch must be a multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GnArgs a{B, HW, C, G, ldx, ldx2, 0, eps, relu};
+  cudaMemsetAsync(ws_bstats, 0, sizeof(double) * 2 * B * G, st);
+  cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
+  cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
+  dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
+  gn_bwd_stats_kernel<<<grid, GN_THREADS, sizeof(float) * (2 * C + 2 * (C / 8)), st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
+      static_cast<const __nv_bfloat16*>(dy), lddy, a, stats, gamma, beta, ws_bstats, dgamma, dbeta);
+  if (int rc = check_launch("gn_bwd_stats")) return rc;
+  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8)), GN_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
+      static_cast<const __nv_bfloat16*>(dy), lddy, a, stats, ws_bstats, gamma, beta, static_cast<__nv_bfloat16*>(dx),
+      lddx);
+  return check_launch("gn_bwd_apply");
+}

@@ -10,6 +10,28 @@ import torch.nn as nn
 from ..registry import DETECTORS, build_backbone, build_head, build_neck
 
 
+def parse_losses(losses, sync_log=False):
+    """BaseDetector._parse_losses (mmdet/models/detectors/base.py:176-209).  The reference all-reduces and .item()s
+    every logged scalar each step; here the scalars stay on the device and are reduced lazily in ONE collective when
+    ``sync_log`` is set (logging interval)."""
+    log_vars = OrderedDict()
+    for name, value in losses.items():
+        if isinstance(value, torch.Tensor):
+            log_vars[name] = value.mean()
+        elif isinstance(value, (list, tuple)):
+            log_vars[name] = sum(v.mean() for v in value)
+        else:
+            raise TypeError(f'{name} is not a tensor or list of tensors')
+    loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+    log_vars['loss'] = loss
+    if sync_log:
+        flat = torch.stack([v.detach().float() for v in log_vars.values()])
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(flat.div_(dist.get_world_size()))
+        log_vars = OrderedDict((k, v) for k, v in zip(log_vars.keys(), flat.tolist()))
+    return loss, log_vars
+
+
 @DETECTORS.register_module()
 class LSDetector(nn.Module):
 
@@ -52,25 +74,7 @@ class LSDetector(nn.Module):
         raise NotImplementedError('LSDetector test-time paths are not built (SURVEY §8 row f3)')
 
     def _parse_losses(self, losses, sync_log=False):
-        """base.py:176-209.  The reference all-reduces and .item()s every logged scalar each step; here the scalars
-        stay on the device and are reduced lazily in ONE collective when ``sync_log`` is set (logging interval)."""
-        log_vars = OrderedDict()
-        for name, value in losses.items():
-            if isinstance(value, torch.Tensor):
-                log_vars[name] = value.mean()
-            elif isinstance(value, (list, tuple)):
-                log_vars[name] = sum(v.mean() for v in value)
-            else:
-                raise TypeError(f'{name} is not a tensor or list of tensors')
-        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
-        log_vars['loss'] = loss
-        if sync_log:
-            flat = torch.stack([v.detach().float() for v in log_vars.values()])
-            if dist.is_available() and dist.is_initialized():
-                dist.all_reduce(flat.div_(dist.get_world_size()))
-            vals = flat.tolist()
-            log_vars = OrderedDict((k, v) for k, v in zip(log_vars.keys(), vals))
-        return loss, log_vars
+        return parse_losses(losses, sync_log)
 
     def train_step(self, data, optimizer=None, sync_log=False):
         """base.py:211-243."""

@@ -259,13 +259,14 @@ class LSHead(nn.Module):
                 cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw))
             for br in brs:
                 t = getattr(self, f'{br}_af_dcn_conv')(torch.cat(raws[br], dim=1))
-                t = t + getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0])
                 gn = getattr(self, f'{br}_GN')
-                t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True)
+                t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
+                                        residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
                 t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
                 outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
-            t = self.cls_af_dcn_conv(torch.cat(cls_raws, dim=1)) + self.cls_feat_conv(cls_feats[l])
-            t = ops.group_norm_nhwc(t, self.cls_GN.num_groups, self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True)
+            t = ops.group_norm_nhwc(self.cls_af_dcn_conv(torch.cat(cls_raws, dim=1)), self.cls_GN.num_groups,
+                                    self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
+                                    residual=self.cls_feat_conv(cls_feats[l]))
             outs['cls'].append(self.pts_cls_out(t, out_fp32=True))
         none = [None] * L
         return (outs['cls'], outs.get('bbox_init', none), outs.get('bbox_refine', none), outs.get('segm_init', none),

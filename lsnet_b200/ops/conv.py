@@ -16,12 +16,11 @@ class _ConvSame(Function):
         x = G.as_nhwc(x, torch.bfloat16)
         if x.shape[1] % 8:
             x = G.pad_channels_nhwc(x, 8)
-        wp = G.pack_conv_weight(weight.detach())
+        wp = G.cached_pack(weight, 'fwd', G.pack_conv_weight)
         npad = wp.shape[0]
         b = None
         if bias is not None:
-            b = torch.zeros(npad, device=x.device, dtype=torch.float32)
-            b[:co] = bias.detach().float()
+            b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
         out = G.conv2d_nhwc(x, wp, kh, kw, pad, dil, b, relu, torch.float32 if out_fp32 else torch.bfloat16,
                             n_valid=co)
         ctx.save_for_backward(x, weight, out if relu else None)
@@ -38,7 +37,7 @@ class _ConvSame(Function):
         gyp = G.pad_channels_nhwc(gy, 8, torch.bfloat16)           # (B, co_pad8, H, W) pixel-major bf16
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = G.pack_conv_weight(weight.detach(), flip_transpose=True)
+            wt = G.cached_pack(weight, 'bwd', lambda t: G.pack_conv_weight(t, flip_transpose=True))
             gx = G.conv2d_nhwc(gyp, wt, kh, kw, pad, dil, None, False, torch.bfloat16, n_valid=ci)
         if ctx.needs_input_grad[1]:
             dw = G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil)       # (co_pad, taps, C_pad8)

@@ -81,15 +81,18 @@ class _DCN(Function):
             raise ValueError(f'offset grid {tuple(offset.shape[2:])} != output grid {(Ho, Wo)}')
         cfg = (Ho, Wo, kh, kw, stride, pad, dil, scales, dg)
         col = dcn_im2col(x, offset.detach(), None if mask is None else mask.detach(), *cfg)
-        wp = weight.detach().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
         npad = (co + 15) // 16 * 16
-        if npad != co:
-            wp = torch.cat([wp, wp.new_zeros(npad - co, wp.shape[1])], 0)
+
+        def pack_fwd(t):
+            p = t.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
+            if npad != co:
+                p = torch.cat([p, p.new_zeros(npad - co, p.shape[1])], 0)
+            return p.contiguous()
+        wp = G.cached_pack(weight, 'dcn_fwd', pack_fwd)
         b = None
         if bias is not None:
-            b = torch.zeros(npad, device=x.device, dtype=torch.float32)
-            b[:co] = bias.detach().float()
-        out = G.gemm(col, wp.contiguous(), b, False, torch.float32 if out_fp32 else torch.bfloat16)
+            b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
+        out = G.gemm(col, wp, b, False, torch.float32 if out_fp32 else torch.bfloat16)
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias = cfg, bias is not None
         return out.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
@@ -106,10 +109,13 @@ class _DCN(Function):
         gx = goff = gmask = gw = gb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
             # B operand [N = taps*ci, K = co]: W^T, K-major
-            wt = weight.detach().permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
-            if cop != co:
-                wt = torch.cat([wt, wt.new_zeros(wt.shape[0], cop - co)], 1)
-            gcol = G.gemm(gy2, wt.contiguous(), None, False, torch.bfloat16)
+            def pack_bwd(t):
+                p = t.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
+                if cop != co:
+                    p = torch.cat([p, p.new_zeros(p.shape[0], cop - co)], 1)
+                return p.contiguous()
+            wt = G.cached_pack(weight, 'dcn_bwd%d' % cop, pack_bwd)
+            gcol = G.gemm(gy2, wt, None, False, torch.bfloat16)
             gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
                                          need_dx=ctx.needs_input_grad[0])
             if gx is not None:

@@ -56,6 +56,21 @@ def as_nhwc(x, dtype=None):
     return x if ok else x.contiguous(memory_format=torch.channels_last)
 
 
+_PACK_CACHE = {}
+
+
+def cached_pack(w, kind, fn):
+    """Packed bf16 copies of a parameter are reused until the parameter changes in place (optimizer step bumps
+    ``_version``): the towers share weights across the 5 pyramid levels, so each weight is packed once per step."""
+    key = (id(w), kind)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == w._version and hit[2] == w.data_ptr():
+        return hit[1]
+    p = fn(w.detach())
+    _PACK_CACHE[key] = (w._version, p, w.data_ptr())
+    return p
+
+
 def pack_conv_weight(w, flip_transpose=False, n_pad=16):
     """(Cout, Cin, kh, kw) fp32 -> bf16 [Npad, kh*kw*Cpad] tap-major / channel-minor, Cin padded to 64 and rows to
     n_pad.  flip_transpose=True packs the weight of the input-gradient convolution: [Cin_pad16, taps(flipped), Cout_pad64]."""

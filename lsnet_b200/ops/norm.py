@@ -1,11 +1,52 @@
-"""GroupNorm (+ optional ReLU) over pixel-major bf16 maps.  Round-1 implementation: torch's native group_norm in fp32
-(library call) followed by a cast back to bf16 channels_last; SURVEY.md §8 row f1 replaces it with a fused kernel."""
+"""GroupNorm (+ optional residual add, + optional ReLU) over pixel-major bf16 maps on liblsnet_sm100.so
+(lsnet_groupnorm_fwd/bwd): fp32 statistics, bf16 in/out, one pass for statistics and one to apply, both directions."""
 import torch
-import torch.nn.functional as F
+from torch.autograd import Function
+
+from .. import lib as L
+from . import gemm_ops as G
 
 
-def group_norm_nhwc(x, num_groups, weight, bias, eps=1e-5, relu=False):
-    y = F.group_norm(x.float(), num_groups, weight, bias, eps)
-    if relu:
-        y = F.relu(y)
-    return y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+class _GroupNorm(Function):
+
+    @staticmethod
+    def forward(ctx, x, x2, weight, bias, num_groups, eps, relu):
+        x = G.as_nhwc(x, torch.bfloat16)
+        B, H, W, C, ldx = G.nhwc_geom(x)
+        ldx2 = 0
+        if x2 is not None:
+            x2 = G.as_nhwc(x2, torch.bfloat16)
+            ldx2 = G.nhwc_geom(x2)[4]
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        stats = torch.empty((B, num_groups, 2), device=x.device, dtype=torch.float64)
+        y = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+        L.call('lsnet_groupnorm_fwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.c_int(B), L.c_int(H * W),
+               L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats),
+               L.ptr(y), L.c_ll(C), L.stream())
+        ctx.save_for_backward(x, x2, w, b, stats)
+        ctx.cfg = (num_groups, eps, relu)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, x2, w, b, stats = ctx.saved_tensors
+        num_groups, eps, relu = ctx.cfg
+        B, H, W, C, ldx = G.nhwc_geom(x)
+        ldx2 = G.nhwc_geom(x2)[4] if x2 is not None else 0
+        gy = G.as_nhwc(gy, torch.bfloat16)
+        lddy = G.nhwc_geom(gy)[4]
+        bstats = torch.empty((B, num_groups, 2), device=x.device, dtype=torch.float64)
+        dx = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
+        L.call('lsnet_groupnorm_bwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.ptr(gy), L.c_ll(lddy),
+               L.c_int(B), L.c_int(H * W), L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps),
+               L.c_int(int(relu)), L.ptr(stats), L.ptr(bstats), L.ptr(dx), L.c_ll(C), L.ptr(dgamma), L.ptr(dbeta),
+               L.stream())
+        dxv = dx.permute(0, 3, 1, 2)
+        return dxv, (dxv if x2 is not None else None), dgamma, dbeta, None, None, None
+
+
+def group_norm_nhwc(x, num_groups, weight, bias, eps=1e-5, relu=False, residual=None):
+    """relu?(GroupNorm(x (+ residual))) -> (B,C,H,W) channels_last bf16."""
+    return _GroupNorm.apply(x, residual, weight, bias, int(num_groups), float(eps), bool(relu))

@@ -6,6 +6,7 @@ import torch
 import torch.distributed as dist
 from torch.nn.parallel import DistributedDataParallel as DDP
 
+from .modules.detector import parse_losses
 from .registry import build_detector
 
 
@@ -19,14 +20,16 @@ def warmup_lr(base_lr, it, warmup_iters=500, warmup_ratio=0.001):
 
 class Trainer:
 
-    def __init__(self, cfg, device='cuda', distributed=False, bucket_cap_mb=64):
+    def __init__(self, cfg, device='cuda', distributed=False, bucket_cap_mb=64, model=None):
         self.device = torch.device(device)
-        self.model = build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'), test_cfg=cfg.get('test_cfg'))
+        self.model = model if model is not None else build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'),
+                                                                    test_cfg=cfg.get('test_cfg'))
         self.model.to(self.device).train()
         self.core = self.model
         if distributed:
-            self.model = DDP(self.core, device_ids=[self.device.index], broadcast_buffers=False,
-                             bucket_cap_mb=bucket_cap_mb, gradient_as_bucket_view=True)
+            ids = [self.device.index] if self.device.type == 'cuda' else None
+            self.model = DDP(self.core, device_ids=ids, broadcast_buffers=False, bucket_cap_mb=bucket_cap_mb,
+                             gradient_as_bucket_view=True)
         opt = cfg.get('optimizer', dict(lr=0.01, momentum=0.9, weight_decay=1e-4))
         self.base_lr = opt['lr']
         params = [p for p in self.core.parameters() if p.requires_grad]
@@ -44,7 +47,7 @@ class Trainer:
             g['lr'] = warmup_lr(self.base_lr, self.iter)
         self.optimizer.zero_grad(set_to_none=True)
         losses = self.model(**batch)
-        loss, log_vars = self.core._parse_losses(losses, sync_log)
+        loss, log_vars = parse_losses(losses, sync_log)
         loss.backward()
         if self.max_norm is not None:
             torch.nn.utils.clip_grad_norm_(self.params, self.max_norm, foreach=True)

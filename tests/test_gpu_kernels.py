@@ -301,3 +301,36 @@ def test_pred_boxes_vs_oracle():
         ref = torch.cat([pts[:, :2], pts[:, :2]], 1)[None] + (O.extreme_points2bbox(p) * s).permute(0, 2, 3, 1).reshape(2, -1, 4)
         assert torch.equal(boxes[:, off:off + h * w], ref)
         off += h * w
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize('B,C,H,W,relu,res', [(2, 256, 13, 21, True, False), (1, 256, 50, 84, True, True),
+                                               (3, 256, 7, 11, False, False), (2, 64, 9, 10, False, True)])
+def test_groupnorm_forward_backward(B, C, H, W, relu, res):
+    """GN(32 groups) (+residual, +ReLU) vs torch's fp32 group_norm on the same bf16-rounded inputs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B * C + H)
+    G = 32 if C >= 256 else 8
+    x = _bf(torch.randn(B, C, H, W, generator=g) * 2 + 0.3)
+    x2 = _bf(torch.randn(B, C, H, W, generator=g)) if res else None
+    w = torch.randn(C, generator=g) * 0.5 + 1
+    b = torch.randn(C, generator=g) * 0.2
+    gy = _bf(torch.randn(B, C, H, W, generator=g))
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    x2r = x2.clone().requires_grad_(True) if res else None
+    s = _bf(xr + x2r) if res else xr
+    if res:   # keep autograd through the rounding as identity
+        s = (xr + x2r) + (_bf(xr + x2r) - (xr + x2r)).detach()
+    ref = F.group_norm(s, G, wr, br, 1e-5)
+    ref = F.relu(ref) if relu else ref
+    ins_r = [xr, wr, br] + ([x2r] if res else [])
+    rg = torch.autograd.grad(ref, ins_r, gy)
+    xd, wd, bd = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    x2d = x2.to(DEV).requires_grad_(True) if res else None
+    out = ops.group_norm_nhwc(xd, G, wd, bd, 1e-5, relu=relu, residual=x2d)
+    assert _rel(out.float(), ref) < 1.5e-2
+    gg = torch.autograd.grad(out, [xd, wd, bd] + ([x2d] if res else []), gy.to(DEV))
+    assert _rel(gg[0].float(), rg[0]) < 2e-2
+    assert _rel(gg[1], rg[1]) < 1e-2 and _rel(gg[2], rg[2]) < 1e-2
+    if res:
+        assert _rel(gg[3].float(), rg[3]) < 2e-2
