@@ -187,10 +187,16 @@ def run_gpu(args, rank, world, local_rank):
     if distributed:
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
-    tr = Trainer(MODEL_CFG['bbox_r50'], device=dev, distributed=distributed)
     nb = 4
     host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True) for s in range(nb)]
     resident = [to_device(b, dev) for b in host]
+    mode = 'cuda-graph (fwd+loss+bwd captured; flat all-reduce + clip + SGD eager)'
+    if args.eager:
+        tr = Trainer(MODEL_CFG['bbox_r50'], device=dev, distributed=distributed)
+        mode = 'eager (torch DDP)'
+    else:
+        from lsnet_b200.train import GraphTrainer
+        tr = GraphTrainer(MODEL_CFG['bbox_r50'], host[0], device=dev, distributed=distributed)
     torch.cuda.synchronize()
 
     def barrier():
@@ -288,7 +294,7 @@ def run_gpu(args, rank, world, local_rank):
                 data='synthetic',
                 config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
                             l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
-                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights'),
+                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights', step_mode=mode),
                 e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clk)
@@ -304,6 +310,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='per-op eager step with torch DDP instead of the CUDA graph')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

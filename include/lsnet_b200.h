@@ -84,7 +84,8 @@ int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, long long l
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float scale_h,
                           float scale_w, int deformable_groups, void* col, long long ldcol, void* stream);
 
-/* Adjoint: gcol bf16 [B*Ho*Wo, kh*kw*C] (= dY . W) -> dx fp32 NHWC (ACCUMULATED: caller zero-fills; may be NULL),
+/* Adjoint: gcol bf16 [B*Ho*Wo, kh*kw*C] (= dY . W) -> dx NHWC, ACCUMULATED (caller zero-fills; may be NULL): bf16 with
+ * 16-byte packed-bf16 vector reds (dx_fp32 = 0, the training default) or fp32 with v4.f32 reds (dx_fp32 = 1),
  * doffset fp32 [B*Ho*Wo, lddo], dmask fp32 [B*Ho*Wo, lddm] (NULL without mask).  Replaces *_col2im and
  * *_col2im_coord (deform_conv_cuda_kernel.cu:333-448, 486-615, 912-1044), the sampling half of
  * deform_conv_backward_input / pyramid_deform_conv_backward_input / modulated_deform_conv_backward
@@ -92,8 +93,8 @@ int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, long long l
 int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const void* x, int B, int H, int W, int C, long long ldx,
                           const float* offset, long long ldo, const float* mask, long long ldm, int Ho, int Wo,
                           int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                          float scale_h, float scale_w, int deformable_groups, float* dx, long long lddx,
-                          float* doffset, long long lddo, float* dmask, long long lddm, void* stream);
+                          float scale_h, float scale_w, int deformable_groups, void* dx, long long lddx,
+                          int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm, void* stream);
 
 /* ---- cross-IOU loss ----------------------------------------------------------------------------------------------
  * loss_type: 0 bbox, 1 polygon, 2 keypoint.  Dense form = CrossIOULoss.forward / cross_iou_loss

@@ -80,7 +80,9 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
   }
 }
 
-// grid: (patches_w, patches_h, B).  Each warp walks (pixel, tap) items of the patch; lanes own 8 channels each.
+// grid: (patches_w, patches_h, B).  One warp per output pixel: lane k (< taps) derives the sampling position, the four
+// (mask-folded) bilinear weights and the four corner pixel indices of tap k ONCE; the tap loop broadcasts them with
+// shuffles, and every lane gathers/interpolates/stores the 8 channels it owns (16-byte accesses, coalesced per corner).
 __global__ void __launch_bounds__(GATHER_THREADS)
 dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ offset,
                   const float* __restrict__ mask, __nv_bfloat16* __restrict__ col, const DcnGeom g) {
@@ -90,174 +92,175 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   const int h_base = blockIdx.y * PATCH_H, w_base = blockIdx.x * PATCH_W;
   const int taps = g.kh * g.kw;
   const int cpg = g.C / g.dg;
-  const int items = PATCH_H * PATCH_W * taps;
-  for (int item = warp; item < items; item += nwarps) {
-    const int pix = item / taps, k = item % taps;
+  for (int pix = warp; pix < PATCH_H * PATCH_W; pix += nwarps) {
     const int ho = h_base + pix / PATCH_W, wo = w_base + pix % PATCH_W;
     if (ho >= g.Ho || wo >= g.Wo) continue;
     const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
     const float* off_px = offset + p * g.ldo;
-    __nv_bfloat16* dst = col + p * g.ldcol + static_cast<long long>(k) * g.C;
-    for (int c0 = lane * 8; c0 < g.C; c0 += 256) {
-      const int grp = c0 / cpg;
-      float h, w;
-      sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
-      const Corner cn = make_corner(g, b, h, w);
-      float m = 1.f;
-      if (mask) m = __ldg(mask + p * g.ldm + grp * taps + k);
-      uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-      if (cn.inside) {
-        uint4 u[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(x + cn.o[q] + c0));
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-          bf16x8_to_float(u[q], f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(cn.w[q], f[e], acc[e]);
+    __nv_bfloat16* dst = col + p * g.ldcol;
+    for (int grp = 0; grp < g.dg; ++grp) {
+      for (int t0 = 0; t0 < taps; t0 += 32) {
+        // ---- lane k: tap t0 + k ----
+        float cw0 = 0.f, cw1 = 0.f, cw2 = 0.f, cw3 = 0.f;
+        int co0 = 0, co1 = 0, co2 = 0, co3 = 0;
+        if (t0 + lane < taps) {
+          const int k = t0 + lane;
+          float h, w;
+          sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
+          const Corner cn = make_corner(g, b, h, w);
+          float m = 1.f;
+          if (mask) m = __ldg(mask + p * g.ldm + grp * taps + k);
+          cw0 = cn.w[0] * m; cw1 = cn.w[1] * m; cw2 = cn.w[2] * m; cw3 = cn.w[3] * m;
+          co0 = static_cast<int>(cn.o[0] / g.ldx); co1 = static_cast<int>(cn.o[1] / g.ldx);
+          co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
         }
-        outv = make_uint4(pack_bf16x2(acc[0] * m, acc[1] * m), pack_bf16x2(acc[2] * m, acc[3] * m),
-                          pack_bf16x2(acc[4] * m, acc[5] * m), pack_bf16x2(acc[6] * m, acc[7] * m));
+        const int nt = min(32, taps - t0);
+        for (int kk = 0; kk < nt; ++kk) {
+          const float w0 = __shfl_sync(0xffffffffu, cw0, kk), w1 = __shfl_sync(0xffffffffu, cw1, kk);
+          const float w2 = __shfl_sync(0xffffffffu, cw2, kk), w3 = __shfl_sync(0xffffffffu, cw3, kk);
+          const long long o0 = static_cast<long long>(__shfl_sync(0xffffffffu, co0, kk)) * g.ldx;
+          const long long o1 = static_cast<long long>(__shfl_sync(0xffffffffu, co1, kk)) * g.ldx;
+          const long long o2 = static_cast<long long>(__shfl_sync(0xffffffffu, co2, kk)) * g.ldx;
+          const long long o3 = static_cast<long long>(__shfl_sync(0xffffffffu, co3, kk)) * g.ldx;
+          const bool any = (w0 != 0.f) || (w1 != 0.f) || (w2 != 0.f) || (w3 != 0.f);
+          __nv_bfloat16* d = dst + static_cast<long long>(t0 + kk) * g.C;
+          for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
+            uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+            if (any) {
+              const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(x + o0 + c0));
+              const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(x + o1 + c0));
+              const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(x + o2 + c0));
+              const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(x + o3 + c0));
+              float f0[8], f1[8], f2[8], f3[8], acc[8];
+              bf16x8_to_float(u0, f0); bf16x8_to_float(u1, f1); bf16x8_to_float(u2, f2); bf16x8_to_float(u3, f3);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] = fmaf(w3, f3[e], fmaf(w2, f2[e], fmaf(w1, f1[e], w0 * f0[e])));
+              outv = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                                pack_bf16x2(acc[6], acc[7]));
+            }
+            *reinterpret_cast<uint4*>(d + c0) = outv;
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(dst + c0) = outv;
     }
   }
 }
 
-// Adjoint.  gcol: [pixels, taps*C] bf16 (= dY . W).  dOffset / dMask are channel reductions done with warp shuffles
-// (one warp owns a whole (pixel, tap) item, so no atomics there).  dX (fp32 NHWC) is accumulated in two tiers: a
-// shared-memory window of WIN_H x WIN_W input pixels around the CTA's output patch absorbs every contribution that
-// lands near the patch (all of them while |offset| < 1 at scale 1: ~36 contributions per input pixel collapse into
-// one), and is flushed once with vector reds; contributions outside the window go straight to global reds.  This cuts
-// L2 atomic traffic (the reference's col2im is atomics-only: deform_conv_cuda_kernel.cu:346-388) by up to ~12x.
-constexpr int WIN_H = 8, WIN_W = 12;
+// Adjoint.  gcol: [pixels, taps*C] bf16 (= dY . W).  One warp per output pixel; lane k derives tap k's sampling
+// geometry once and the tap loop broadcasts it (as in the gather).  dOffset / dMask are channel reductions done with
+// warp shuffles (no atomics).  dX is accumulated with 16-byte vector reds of packed bf16x2 (8 channels per lane per
+// instruction): the kernel is bound by the SM-side RED issue rate (~1 cycle per lane), so halving the instruction count
+// against fp32 v4 reds halves the time, and dX lands directly in the bf16 NHWC layout the upstream kernels consume.
+// Corners whose bilinear weight is exactly zero (integer-aligned samples, e.g. zero-initialised conv_offset) are skipped.
+// (Reference: atomics-only fp32 col2im, deform_conv_cuda_kernel.cu:346-388.)
+__device__ __forceinline__ void red_bf16x8(__nv_bfloat16* dst, const float (&v)[8]) {
+  const uint32_t a = pack_bf16x2(v[0], v[1]), b = pack_bf16x2(v[2], v[3]), c = pack_bf16x2(v[4], v[5]),
+                 d = pack_bf16x2(v[6], v[7]);
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
 
-template <bool USE_WIN>
+__device__ __forceinline__ void red_f32x8(float* dst, const float (&v)[8]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+template <bool DX_FP32>
 __global__ void __launch_bounds__(GATHER_THREADS)
 dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* __restrict__ x,
-                  const float* __restrict__ offset, const float* __restrict__ mask, float* __restrict__ dx,
+                  const float* __restrict__ offset, const float* __restrict__ mask, void* __restrict__ dx,
                   float* __restrict__ doffset, float* __restrict__ dmask, const DcnGeom g, long long lddx,
                   long long lddo, long long lddm) {
-  extern __shared__ float win[];   // [WIN_H*WIN_W][C], channel c stored at (c%8)*(C/8) + c/8 (bank-conflict free)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = GATHER_THREADS / 32;
   const int b = blockIdx.z;
   const int h_base = blockIdx.y * PATCH_H, w_base = blockIdx.x * PATCH_W;
   const int taps = g.kh * g.kw;
   const int cpg = g.C / g.dg;
-  const int c8 = g.C / 8;
-  // window origin: one pixel before the smallest un-offset sampling position of the patch
-  const int wy0 = static_cast<int>(floorf(static_cast<float>(h_base * g.sh - g.ph) * g.scale_h)) - 1;
-  const int wx0 = static_cast<int>(floorf(static_cast<float>(w_base * g.sw - g.pw) * g.scale_w)) - 1;
-  if (USE_WIN && dx) {
-    for (int i = threadIdx.x; i < WIN_H * WIN_W * g.C; i += GATHER_THREADS) win[i] = 0.f;
-    __syncthreads();
-  }
-  const int items = PATCH_H * PATCH_W * taps * g.dg;
-  for (int item = warp; item < items; item += nwarps) {
-    const int grp = item % g.dg;
-    const int k = (item / g.dg) % taps;
-    const int pix = item / (g.dg * taps);
+  for (int pix = warp; pix < PATCH_H * PATCH_W; pix += nwarps) {
     const int ho = h_base + pix / PATCH_W, wo = w_base + pix % PATCH_W;
     if (ho >= g.Ho || wo >= g.Wo) continue;
     const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
     const float* off_px = offset + p * g.ldo;
-    float h, w;
-    sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
-    const Corner cn = make_corner(g, b, h, w);
-    float m = 1.f;
-    if (mask) m = __ldg(mask + p * g.ldm + grp * taps + k);
-    float gh = 0.f, gw = 0.f, gm = 0.f;
-    if (cn.inside) {
-      const __nv_bfloat16* src = gcol + p * g.ldcol + static_cast<long long>(k) * g.C;
-      const float hh = 1.f - cn.lh, hw = 1.f - cn.lw;
-      // window slot of each corner (-1: outside the window -> global red)
-      int wslot[4];
-      {
-        const int h0 = static_cast<int>(floorf(h)), w0 = static_cast<int>(floorf(w));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int yy = h0 + (q >> 1) - wy0, xx = w0 + (q & 1) - wx0;
-          wslot[q] = (USE_WIN && yy >= 0 && yy < WIN_H && xx >= 0 && xx < WIN_W) ? yy * WIN_W + xx : -1;
+    for (int grp = 0; grp < g.dg; ++grp) {
+      for (int t0 = 0; t0 < taps; t0 += 32) {
+        // ---- lane k: geometry of tap t0 + k ----
+        float lh_ = 0.f, lw_ = 0.f, m_ = 1.f;
+        int vbits = 0, co0 = 0, co1 = 0, co2 = 0, co3 = 0;
+        if (t0 + lane < taps) {
+          const int k = t0 + lane;
+          float h, w;
+          sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
+          const Corner cn = make_corner(g, b, h, w);
+          if (mask) m_ = __ldg(mask + p * g.ldm + grp * taps + k);
+          lh_ = cn.lh; lw_ = cn.lw;
+          vbits = (cn.v[0] ? 1 : 0) | (cn.v[1] ? 2 : 0) | (cn.v[2] ? 4 : 0) | (cn.v[3] ? 8 : 0) | (cn.inside ? 16 : 0);
+          co0 = static_cast<int>(cn.o[0] / g.ldx); co1 = static_cast<int>(cn.o[1] / g.ldx);
+          co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
         }
-      }
-      for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
-        float gc[8];
-        bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(src + c0)), gc);
-        float xv[4][8];
+        const int nt = min(32, taps - t0);
+        float my_gh = 0.f, my_gw = 0.f, my_gm = 0.f;   // results of tap (t0 + lane), filled by the reductions below
+        for (int kk = 0; kk < nt; ++kk) {
+          const float lh = __shfl_sync(0xffffffffu, lh_, kk), lw = __shfl_sync(0xffffffffu, lw_, kk);
+          const float m = __shfl_sync(0xffffffffu, m_, kk);
+          const int vb = __shfl_sync(0xffffffffu, vbits, kk);
+          const int oi[4] = {__shfl_sync(0xffffffffu, co0, kk), __shfl_sync(0xffffffffu, co1, kk),
+                             __shfl_sync(0xffffffffu, co2, kk), __shfl_sync(0xffffffffu, co3, kk)};
+          float gh = 0.f, gw = 0.f, gm = 0.f;
+          if (vb & 16) {
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float wq[4] = {(vb & 1) ? hh * hw : 0.f, (vb & 2) ? hh * lw : 0.f, (vb & 4) ? lh * hw : 0.f,
+                                 (vb & 8) ? lh * lw : 0.f};
+            const __nv_bfloat16* src = gcol + p * g.ldcol + static_cast<long long>(t0 + kk) * g.C;
+            for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
+              float gc[8];
+              bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(src + c0)), gc);
+              float xv[4][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (cn.v[q]) {
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + cn.o[q] + c0)), xv[q]);
-          } else {
+              for (int q = 0; q < 4; ++q) {
+                if (vb & (1 << q)) {
+                  bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[q]) * g.ldx + c0)), xv[q]);
+                } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xv[q][e] = 0.f;
-          }
-        }
+                  for (int e = 0; e < 8; ++e) xv[q][e] = 0.f;
+                }
+              }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float val = cn.w[0] * xv[0][e] + cn.w[1] * xv[1][e] + cn.w[2] * xv[2][e] + cn.w[3] * xv[3][e];
-          // d(val)/dh and d(val)/dw: get_coordinate_weight (…kernel.cu:145-188), out-of-range corners dropped
-          const float dvh = -hw * xv[0][e] - cn.lw * xv[1][e] + hw * xv[2][e] + cn.lw * xv[3][e];
-          const float dvw = -hh * xv[0][e] + hh * xv[1][e] - cn.lh * xv[2][e] + cn.lh * xv[3][e];
-          gm = fmaf(gc[e], val, gm);
-          gh = fmaf(gc[e] * m, dvh, gh);
-          gw = fmaf(gc[e] * m, dvw, gw);
-        }
-        if (dx) {
+              for (int e = 0; e < 8; ++e) {
+                const float val = wq[0] * xv[0][e] + wq[1] * xv[1][e] + wq[2] * xv[2][e] + wq[3] * xv[3][e];
+                // d(val)/dh, d(val)/dw: get_coordinate_weight (…kernel.cu:145-188), out-of-range corners dropped
+                const float dvh = -hw * xv[0][e] - lw * xv[1][e] + hw * xv[2][e] + lw * xv[3][e];
+                const float dvw = -hh * xv[0][e] + hh * xv[1][e] - lh * xv[2][e] + lh * xv[3][e];
+                gm = fmaf(gc[e], val, gm);
+                gh = fmaf(gc[e] * m, dvh, gh);
+                gw = fmaf(gc[e] * m, dvw, gw);
+              }
+              if (dx) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (!cn.v[q]) continue;
-            const float s = cn.w[q] * m;
-            if (wslot[q] >= 0) {
-              float* d = win + static_cast<long long>(wslot[q]) * g.C + (c0 >> 3);
+                for (int q = 0; q < 4; ++q) {
+                  const float sc = wq[q] * m;
+                  if (sc == 0.f) continue;
+                  float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) atomicAdd(d + e * c8, s * gc[e]);
-            } else {
-              float* d = dx + (cn.o[q] / g.ldx) * lddx + c0;
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(s * gc[0]), "f"(s * gc[1]),
-                           "f"(s * gc[2]), "f"(s * gc[3])
-                           : "memory");
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(s * gc[4]),
-                           "f"(s * gc[5]), "f"(s * gc[6]), "f"(s * gc[7])
-                           : "memory");
+                  for (int e = 0; e < 8; ++e) v[e] = sc * gc[e];
+                  if (DX_FP32) red_f32x8(static_cast<float*>(dx) + static_cast<long long>(oi[q]) * lddx + c0, v);
+                  else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + static_cast<long long>(oi[q]) * lddx + c0, v);
+                }
+              }
             }
           }
+          gh = warp_sum(gh); gw = warp_sum(gw); gm = warp_sum(gm);
+          if (lane == kk) { my_gh = gh; my_gw = gw; my_gm = gm; }
+        }
+        if (t0 + lane < taps) {
+          const int k = t0 + lane;
+          doffset[p * lddo + grp * 2 * taps + 2 * k] = my_gh;
+          doffset[p * lddo + grp * 2 * taps + 2 * k + 1] = my_gw;
+          if (dmask) dmask[p * lddm + grp * taps + k] = my_gm;
         }
       }
-    }
-    gh = warp_sum(gh);
-    gw = warp_sum(gw);
-    gm = warp_sum(gm);
-    if (lane == 0) {
-      doffset[p * lddo + grp * 2 * taps + 2 * k] = gh;
-      doffset[p * lddo + grp * 2 * taps + 2 * k + 1] = gw;
-      if (dmask) dmask[p * lddm + grp * taps + k] = gm;
-    }
-  }
-  if (USE_WIN && dx) {
-    __syncthreads();
-    // flush: one thread per (window pixel, 8-channel vector); untouched vectors are skipped
-    for (int i = threadIdx.x; i < WIN_H * WIN_W * c8; i += GATHER_THREADS) {
-      const int slot = i / c8, v = i % c8;
-      const int yy = wy0 + slot / WIN_W, xx = wx0 + slot % WIN_W;
-      if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
-      const float* s = win + static_cast<long long>(slot) * g.C + v;
-      float f[8];
-      bool any = false;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { f[e] = s[e * c8]; any |= (f[e] != 0.f); }
-      if (!any) continue;
-      float* d = dx + ((static_cast<long long>(b) * g.H + yy) * g.W + xx) * lddx + v * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3])
-                   : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]),
-                   "f"(f[7])
-                   : "memory");
     }
   }
 }
@@ -296,36 +299,27 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
                                      long long ldx, const float* offset, long long ldo, const float* mask,
                                      long long ldm, int Ho, int Wo, int kh, int kw, int stride_h, int stride_w,
                                      int pad_h, int pad_w, int dil_h, int dil_w, float scale_h, float scale_w,
-                                     int deformable_groups, float* dx, long long lddx, float* doffset, long long lddo,
-                                     float* dmask, long long lddm, void* stream) {
+                                     int deformable_groups, void* dx, long long lddx, int dx_fp32, float* doffset,
+                                     long long lddo, float* dmask, long long lddm, void* stream) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
   if (int rc = check_geom("lsnet_dcn_col2im_bf16", C, deformable_groups, ldx, ldcol)) return rc;
-  if (dx && (lddx % 4)) return set_error("lsnet_dcn_col2im_bf16: dx pitch must be a multiple of 4 floats");
+  if (dx && (lddx % 8)) return set_error("lsnet_dcn_col2im_bf16: dx pitch must be a multiple of 8 bf16");
   DcnGeom g{B, H, W, C, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, scale_h, scale_w,
             deformable_groups, ldx, ldo, ldm, ldcol};
   dim3 grid((Wo + PATCH_W - 1) / PATCH_W, (Ho + PATCH_H - 1) / PATCH_H, B);
   const double taps = kh * kw, px = static_cast<double>(B) * Ho * Wo;
-  // algorithmic bytes: dCol read (2*taps*C per px) + x read + offsets/mask read + dX written (fp32) + dOffset/dMask
-  const double bytes = px * 2.0 * taps * C + static_cast<double>(B) * H * W * (2.0 * C + (dx ? 4.0 * C : 0.0)) +
+  // algorithmic bytes: dCol read (2*taps*C per px) + x read + offsets/mask read + dX written (bf16) + dOffset/dMask
+  const double bytes = px * 2.0 * taps * C + static_cast<double>(B) * H * W * (2.0 * C + (dx ? (dx_fp32 ? 4.0 : 2.0) * C : 0.0)) +
                        px * 4.0 * taps * (mask ? 3 : 2) * 2.0;
   const int th = timing_begin(TC_COL2IM, bytes, static_cast<cudaStream_t>(stream));
-  const size_t win_bytes = sizeof(float) * WIN_H * WIN_W * C;
-  if (dx && C <= 256) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(dcn_col2im_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(sizeof(float) * WIN_H * WIN_W * 256));
-      if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(dcn_col2im): %s", cudaGetErrorString(e));
-      attr_done = true;
-    }
-    dcn_col2im_kernel<true><<<grid, GATHER_THREADS, win_bytes, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
-        dmask, g, lddx, lddo, lddm);
-  } else {
+  if (dx_fp32)
+    dcn_col2im_kernel<true><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
+        g, lddx, lddo, lddm);
+  else
     dcn_col2im_kernel<false><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
-        dmask, g, lddx, lddo, lddm);
-  }
+        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
+        g, lddx, lddo, lddm);
   timing_end(th, static_cast<cudaStream_t>(stream));
   return check_launch("dcn_col2im");
 }

@@ -73,6 +73,29 @@ class NormConvModule(nn.Module):
         return ops.group_norm_nhwc(self.conv(x), self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps, relu=True)
 
 
+class PackedGT:
+    """Per-batch ground truth already packed into fixed-capacity device tensors (the form LSHead.loss computes on).
+    Passing one of these as ``gt_bboxes`` skips the per-step host packing, which is what makes the whole step
+    capturable in a CUDA graph (static buffers refreshed with copy_ between replays).
+
+    bbox [B,G,4] f32, count [B] i32, labels [B,G] i32, tables {'bbox': [B,G,10], 'segm': [B,G,74], 'pose': [B,G,36]},
+    vs [B,G,17] or None, valid_hw [B,L,2] i32 (valid extent of every pyramid level for every image)."""
+
+    def __init__(self, bbox, count, labels, tables, vs=None, valid_hw=None):
+        self.bbox, self.count, self.labels, self.tables, self.vs, self.valid_hw = bbox, count, labels, tables, vs, valid_hw
+
+    def copy_from(self, other):
+        self.bbox.copy_(other.bbox, non_blocking=True)
+        self.count.copy_(other.count, non_blocking=True)
+        self.labels.copy_(other.labels, non_blocking=True)
+        for k in self.tables:
+            self.tables[k].copy_(other.tables[k], non_blocking=True)
+        if self.vs is not None:
+            self.vs.copy_(other.vs, non_blocking=True)
+        if self.valid_hw is not None:
+            self.valid_hw.copy_(other.valid_hw, non_blocking=True)
+
+
 BRANCHES = {'bbox': ['bbox'], 'segm': ['segm'], 'pose_bbox': ['bbox', 'pose'], 'pose_kbox': ['pose']}
 LOSS_KIND = {'bbox': 'bbox', 'segm': 'polygon', 'pose': 'keypoint'}
 
@@ -210,6 +233,18 @@ class LSHead(nn.Module):
         val, ind = offs.max(dim=2)
         return torch.where(ind == 0, -val, val)
 
+    _SCALE_CACHE = {}
+
+    def _scale_vec(self, sh, sw, device):
+        """(1, 2*points, 1, 1) vector [sh, sw, sh, sw, ...]; cached on the device so that no host->device copy happens
+        inside a captured step."""
+        key = (float(sh), float(sw), self.num_kernel_points, str(device))
+        v = LSHead._SCALE_CACHE.get(key)
+        if v is None:
+            v = torch.tensor([sh, sw] * self.num_kernel_points, dtype=torch.float32).view(1, -1, 1, 1).to(device)
+            LSHead._SCALE_CACHE[key] = v
+        return v
+
     def forward_single1(self, x):
         """lsnet_head.py:502-598 for one level: towers + init regression -> (cls_feat, {br: (feat, init_sp, dcn_off)})."""
         cls_feat = x
@@ -250,7 +285,7 @@ class LSHead(nn.Module):
             cls_raws = []
             for lv in lvls:
                 sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
-                sc = offs[brs[0]].new_tensor([sh, sw] * self.num_kernel_points).view(1, -1, 1, 1)
+                sc = self._scale_vec(sh, sw, offs[brs[0]].device)
                 for br in brs:
                     # the reference scales views of the offset tensor in place, so the factors accumulate over the
                     # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
@@ -345,6 +380,8 @@ class LSHead(nn.Module):
         task, brs = self.task, BRANCHES[self.task]
         preds = {'bbox': (bbox_pts_preds_init, bbox_pts_preds_refine), 'segm': (segm_pts_preds_init, segm_pts_preds_refine),
                  'pose': (pose_pts_preds_init, pose_pts_preds_refine)}
+        if isinstance(gt_bboxes, PackedGT):
+            return self._loss_packed(cls_scores, preds, gt_bboxes, img_metas, return_aux)
         tables, gt_vs = {}, None
         if task in ('bbox', 'pose_bbox'):
             if gt_extremes is None:
@@ -365,8 +402,49 @@ class LSHead(nn.Module):
         if gt_labels is not None:
             gt_lab = self._pack([l.view(-1, 1) for l in gt_labels], 1, dev, torch.int32).squeeze(-1).contiguous()
 
+        packed = PackedGT(gt_bb, gt_cnt, gt_lab, tables, gt_vs, None)
+        return self._loss_packed(cls_scores, preds, packed, img_metas, return_aux)
+
+    def pack_gt(self, gt_bboxes, gt_labels, img_metas, sizes, device, gt_extremes=None, gt_keypoints_vs=None,
+                gt_masks=None, capacity=None, pin=False):
+        """Host-side packing of one batch into a PackedGT on ``device`` (capacity = fixed Gmax, e.g. for CUDA graphs)."""
+        task = self.task
+        tables, gt_vs = {}, None
+
+        def pack(rows, width, dtype=torch.float32):
+            B = len(rows)
+            G = capacity or max(1, max(int(r.shape[0]) for r in rows))
+            out = torch.zeros((B, G, width), dtype=dtype)
+            for i, r in enumerate(rows):
+                if r.shape[0] > G:
+                    raise ValueError(f'{r.shape[0]} ground-truth instances exceed the packed capacity {G}')
+                out[i, :r.shape[0]] = r.reshape(r.shape[0], width).to(dtype)
+            return out.pin_memory() if pin else out
+        if task in ('bbox', 'pose_bbox'):
+            ext = gt_extremes if gt_extremes is not None else self.get_border_center(gt_bboxes)
+            tables['bbox'] = pack(ext, 10)
+        if task == 'segm':
+            polys, gt_bboxes = self.process_polygons(gt_masks)
+            tables['segm'] = pack(polys, polys[0].shape[1])
+        if task == 'pose_bbox':
+            kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
+            tables['pose'] = pack(kps, kps[0].shape[1])
+            gt_vs = pack(vss, vss[0].shape[1])
+        bb = pack(gt_bboxes, 4)
+        cnt = torch.tensor([int(b.shape[0]) for b in gt_bboxes], dtype=torch.int32)
+        lab = pack([l.view(-1, 1) for l in gt_labels], 1, torch.int32).squeeze(-1).contiguous()
+        valid = torch.tensor([[[min(int(np.ceil(m['pad_shape'][0] / s)), h), min(int(np.ceil(m['pad_shape'][1] / s)), w)]
+                               for (h, w), s in zip(sizes, self.point_strides)] for m in img_metas], dtype=torch.int32)
+        to = lambda t: None if t is None else t.to(device, non_blocking=True)
+        return PackedGT(to(bb), to(cnt), to(lab), {k: to(v) for k, v in tables.items()}, to(gt_vs), to(valid))
+
+    def _loss_packed(self, cls_scores, preds, gt, img_metas, return_aux=False):
+        dev = cls_scores[0].device
+        brs = BRANCHES[self.task]
+        tables, gt_vs, gt_bb, gt_cnt, gt_lab = gt.tables, gt.vs, gt.bbox, gt.count, gt.labels
         sizes = [tuple(c.shape[-2:]) for c in cls_scores]
-        pyr = ops.Pyramid(sizes, self.point_strides, [m['pad_shape'][:2] for m in img_metas], dev)
+        pyr = ops.Pyramid(sizes, self.point_strides, None if gt.valid_hw is not None else
+                          [m['pad_shape'][:2] for m in img_metas], dev, valid_hw=gt.valid_hw)
         init_acfg = _cfg_get(_cfg_get(self.train_cfg, 'init'), 'assigner')
         ref_acfg = _cfg_get(_cfg_get(self.train_cfg, 'refine'), 'assigner')
         # ---- init stage: nearest centre point of the GT's scale level (get_targets(stage='init')) ----

@@ -9,7 +9,7 @@ class Pyramid:
     """Host description of the point pyramid (PointGenerator grids, core/anchor/point_generator.py:17-37) plus the
     per-image valid extents derived from pad_shape (LSHead.get_points, lsnet_head.py:781-792)."""
 
-    def __init__(self, sizes, strides, pad_shapes, device):
+    def __init__(self, sizes, strides, pad_shapes, device, valid_hw=None):
         self.sizes = [(int(h), int(w)) for h, w in sizes]
         self.strides = [float(s) for s in strides]
         self.n = len(self.sizes)
@@ -19,6 +19,9 @@ class Pyramid:
         self.h_arr = L.host_int_array([h for h, _ in self.sizes])
         self.w_arr = L.host_int_array([w for _, w in self.sizes])
         self.s_arr = L.host_float_array(self.strides)
+        if valid_hw is not None:           # already on the device (static buffer of a captured step)
+            self.valid_hw, self.B = valid_hw, valid_hw.shape[0]
+            return
         valid = []
         for ph, pw in pad_shapes:
             valid.append([[min(int(np.ceil(ph / s)), h), min(int(np.ceil(pw / s)), w)]

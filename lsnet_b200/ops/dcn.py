@@ -42,21 +42,25 @@ def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg):
     return col
 
 
-def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True):
+DX_FP32 = False   # accumulate dX in fp32 (v4.f32 reds) instead of packed bf16 (half the red instructions)
+
+
+def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True, dx_fp32=None):
     B, H, W, C, ldx = G.nhwc_geom(x)
     offset, ldo = _pix_major(offset)
     ldm = 0
     if mask is not None:
         mask, ldm = _pix_major(mask)
     taps = kh * kw
-    dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32) if need_dx else None
+    dx_fp32 = DX_FP32 if dx_fp32 is None else dx_fp32
+    dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32 if dx_fp32 else torch.bfloat16) if need_dx else None
     doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
     dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
     L.call('lsnet_dcn_col2im_bf16', L.ptr(gcol), L.c_ll(gcol.stride(0)), L.ptr(x), L.c_int(B), L.c_int(H), L.c_int(W),
            L.c_int(C), L.c_ll(ldx), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.c_int(Ho), L.c_int(Wo),
            L.c_int(kh), L.c_int(kw), L.c_int(stride[0]), L.c_int(stride[1]), L.c_int(pad[0]), L.c_int(pad[1]),
            L.c_int(dil[0]), L.c_int(dil[1]), L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(dx), L.c_ll(C),
-           L.ptr(doff), L.c_ll(dg * 2 * taps), L.ptr(dmask), L.c_ll(dg * taps), L.stream())
+           L.c_int(int(bool(dx_fp32))), L.ptr(doff), L.c_ll(dg * 2 * taps), L.ptr(dmask), L.c_ll(dg * taps), L.stream())
     return (dx.permute(0, 3, 1, 2) if dx is not None else None, doff.permute(0, 3, 1, 2),
             dmask.permute(0, 3, 1, 2) if dmask is not None else None)
 
@@ -118,7 +122,7 @@ class _DCN(Function):
             gcol = G.gemm(gy2, wt, None, False, torch.bfloat16)
             gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
                                          need_dx=ctx.needs_input_grad[0])
-            if gx is not None:
+            if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
         if ctx.needs_input_grad[3]:
             dw = G.gemm_tn(gy2, col)                                   # [cop, taps*ci] fp32

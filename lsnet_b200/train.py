@@ -54,3 +54,119 @@ class Trainer:
         self.optimizer.step()
         self.iter += 1
         return loss, log_vars
+
+
+class GraphTrainer:
+    """The same training step with (almost) no host work per iteration, B200-first:
+
+      * forward + loss + backward are captured ONCE into a CUDA graph over static input buffers (image, PackedGT);
+        each step = refresh the static buffers (async copies) + one graph replay;
+      * every trainable parameter / gradient / momentum lives in ONE flat fp32 buffer, so data parallelism is a single
+        NCCL all-reduce of the flat gradient (154 MB; ~0.4 ms over NVLink 5 / NVSwitch — no bucketing or overlap
+        machinery needed at this bandwidth) and clip + SGD(momentum, wd) are a handful of flat element-wise kernels.
+
+    Semantics are those of ``Trainer`` / the reference's OptimizerHook: grads averaged over ranks, L2 clip at
+    ``max_norm`` on the averaged gradient, torch.optim.SGD update (dampening 0, no nesterov)."""
+
+    def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=16, model=None):
+        self.device = torch.device(device)
+        self.distributed = distributed
+        self.model = model if model is not None else build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'),
+                                                                    test_cfg=cfg.get('test_cfg'))
+        self.model.to(self.device).train()
+        self.core = self.model
+        opt = cfg.get('optimizer', dict(lr=0.01, momentum=0.9, weight_decay=1e-4))
+        self.base_lr, self.momentum, self.wd = opt['lr'], opt.get('momentum', 0.9), opt.get('weight_decay', 1e-4)
+        self.max_norm = (cfg.get('grad_clip') or {}).get('max_norm')
+        self.capacity = capacity
+        self.iter = 0
+        if distributed:     # identical replicas: broadcast rank 0's initial parameters/buffers once
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, 0)
+        # ---- flat parameter / gradient / momentum storage ----
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        al = 64                                  # every parameter starts on a 256-byte boundary of the flat buffers
+        n = sum((p.numel() + al - 1) // al * al for p in self.params)
+        self.flat_p = torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=self.device, dtype=torch.float32)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + k].view_as(p)
+            p.grad = self.flat_g[o:o + k].view_as(p)
+            o += (k + al - 1) // al * al
+        # ---- static inputs ----
+        self.img = torch.empty_like(sample_batch['img'], device=self.device).contiguous(memory_format=torch.channels_last)
+        self.metas = sample_batch['img_metas']
+        self.sizes = None
+        self.gt = None
+        self.graph = None
+        self.loss = None
+        self.log_vars = None
+        self._capture(sample_batch)
+
+    def _pack(self, batch, pin=False):
+        return self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes,
+                                           self.device, gt_extremes=batch.get('gt_extremes'),
+                                           gt_keypoints_vs=batch.get('gt_keypoints'), gt_masks=batch.get('gt_masks'),
+                                           capacity=self.capacity, pin=pin)
+
+    def _fwd_bwd(self):
+        self.flat_g.zero_()
+        losses = self.model(img=self.img, img_metas=self.metas, gt_bboxes=self.gt, gt_labels=None)
+        loss, log_vars = parse_losses(losses)
+        loss.backward()
+        return loss, log_vars
+
+    def _capture(self, batch):
+        from .ops import gemm_ops
+        with torch.no_grad():          # pyramid geometry of this input size
+            feats = self.core.extract_feat(batch['img'][:1].to(self.device))
+        self.sizes = [tuple(f.shape[-2:]) for f in feats]
+        del feats
+        self.img.copy_(batch['img'].to(self.device))
+        self.gt = self._pack(batch)
+        # warm-up on a side stream (allocator / cuDNN autotune / cudaFuncSetAttribute happen outside the capture)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        gemm_ops._PACK_CACHE.clear()           # the packs must be re-done INSIDE the captured region
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.log_vars = self._fwd_bwd()
+        gemm_ops._PACK_CACHE.clear()
+
+    def load_batch(self, batch):
+        """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host)."""
+        self.img.copy_(batch['img'], non_blocking=True)
+        self.gt.copy_from(self._pack(batch, pin=True))
+
+    def step(self, batch=None, sync_log=False):
+        if batch is not None:
+            self.load_batch(batch)
+        self.graph.replay()
+        g = self.flat_g
+        if self.distributed:
+            dist.all_reduce(g)
+            g.div_(dist.get_world_size())
+        lr = warmup_lr(self.base_lr, self.iter)
+        if self.max_norm is not None:
+            norm = torch.linalg.vector_norm(g)
+            g.mul_((self.max_norm / (norm + 1e-6)).clamp(max=1.0))
+        g.add_(self.flat_p, alpha=self.wd)
+        self.flat_m.mul_(self.momentum).add_(g)
+        self.flat_p.add_(self.flat_m, alpha=-lr)
+        self.iter += 1
+        log = self.log_vars
+        if sync_log:
+            flat = torch.stack([v.detach().float() for v in log.values()])
+            if self.distributed:
+                dist.all_reduce(flat.div_(dist.get_world_size()))
+            log = dict(zip(log.keys(), flat.tolist()))
+        return self.loss, log

@@ -99,9 +99,15 @@ def _dcn_case(seed, B, C, H, W, Ho, Wo, Co, mag):
     return x, off, mask, w, bias, gy
 
 
+@pytest.mark.parametrize('dx_fp32', [True, False])
 @pytest.mark.parametrize('variant', ['v2', 'v1', 'pyramid_up', 'pyramid_down', 'pyramid_same'])
-def test_dcn_forward_backward_vs_oracle(variant):
+def test_dcn_forward_backward_vs_oracle(variant, dx_fp32):
+    """dX accumulation: fp32 reds (2e-2 of the gradient scale, dominated by the bf16 dCol operand) or the training
+    default packed-bf16 reds, whose running sum is rounded to bf16 at every add: up to ~sqrt(n) * 2^-9 for n
+    contributions per input pixel (n ~ 36 at scale 1, ~144 when the offset grid is 2x finer than the input) -> 4e-2."""
     ops = _ops()
+    import lsnet_b200.ops.dcn as dcn_mod
+    dcn_mod.DX_FP32 = dx_fp32
     B, C, Co = 2, 64, 48
     if variant in ('v2', 'v1'):
         H, W, Ho, Wo = 13, 21, 13, 21
@@ -139,7 +145,9 @@ def test_dcn_forward_backward_vs_oracle(variant):
     gg = torch.autograd.grad(out, ins, gy.to(DEV))
     for name, a, r in zip(['x', 'offset', 'mask/w', 'w/b', 'b'], gg, rg):
         assert a.shape == r.shape, name
-        assert _rel(a.float(), r) < 2e-2, (variant, name, _rel(a.float(), r))
+        tol = 4e-2 if (name == 'x' and not dx_fp32) else 2e-2
+        assert _rel(a.float(), r) < tol, (variant, name, _rel(a.float(), r))
+    dcn_mod.DX_FP32 = False
 
 
 def test_dcn_out_of_range_and_zero_offsets():

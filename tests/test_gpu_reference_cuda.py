@@ -1,8 +1,11 @@
 """Pins the oracle's DCN restatement (oracle/dcn_ref.c, CPU) to the REFERENCE'S OWN CUDA kernels: the unmodified
 extension compiled into oracle/_ref (oracle/build_ref.py) is driven through its 8 pybind entry points
 (mmdet/ops/dcn/src/deform_conv_ext.cpp:227-250) exactly as the reference's autograd Functions call them
-(mmdet/ops/dcn/deform_conv.py:52-57,88-103,145-149,163-170,225-231,252-277), in fp64, and compared with the oracle on
-the same inputs.  Also times the reference kernel against ours on a head-sized shape ("kernel to beat")."""
+(mmdet/ops/dcn/deform_conv.py:52-57,88-103,145-149,163-170,225-231,252-277), in fp32, and compared with the oracle on
+the same inputs.  (fp64 is not usable: the reference launches 1024-thread blocks unconditionally, the fp64 col2im
+instantiation needs more registers than that allows on sm_100, and the reference only printf's launch errors
+(deform_conv_cuda_kernel.cu:326-330), leaving grad_input silently zero.)  Tolerance 2e-4 of the output scale: fp32
+atomics order + the FMA contraction nvcc applies to the sampling position.  Also times the reference kernel against ours on a head-sized shape ("kernel to beat")."""
 import pytest
 import torch
 
@@ -28,31 +31,31 @@ def _ref_modulated(ext, x, off, mask, w, b, gy):
     return out, gi, go, gm, gw, gb
 
 
-def test_oracle_dcnv2_equals_reference_cuda_fp64():
+def test_oracle_dcnv2_equals_reference_cuda():
     ext = _ext()
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(2, 8, 9, 11, generator=g, dtype=torch.float64)
-    off = torch.randn(2, 18, 9, 11, generator=g, dtype=torch.float64) * 2.5
-    mask = torch.rand(2, 9, 9, 11, generator=g, dtype=torch.float64)
-    w = torch.randn(6, 8, 3, 3, generator=g, dtype=torch.float64)
-    b = torch.randn(6, generator=g, dtype=torch.float64)
-    gy = torch.randn(2, 6, 9, 11, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 8, 9, 11, generator=g, dtype=torch.float32)
+    off = torch.randn(2, 18, 9, 11, generator=g, dtype=torch.float32) * 2.5
+    mask = torch.rand(2, 9, 9, 11, generator=g, dtype=torch.float32)
+    w = torch.randn(6, 8, 3, 3, generator=g, dtype=torch.float32)
+    b = torch.randn(6, generator=g, dtype=torch.float32)
+    gy = torch.randn(2, 6, 9, 11, generator=g, dtype=torch.float32)
     ref = _ref_modulated(ext, *(t.cuda() for t in (x, off, mask, w, b, gy)))
     xr, offr, mr, wr, br = (t.clone().requires_grad_(True) for t in (x, off, mask, w, b))
     y = OD.modulated_deform_conv(xr, offr, mr, wr, br, 1, 1, 1)
     grads = torch.autograd.grad(y, [xr, offr, mr, wr, br], gy)
     for name, a, r in zip(['out', 'dx', 'doff', 'dmask', 'dw', 'db'], (y,) + grads, ref):
-        assert (a.detach() - r.cpu()).abs().max() < 1e-10, name
+        assert (a.detach() - r.cpu()).abs().max() < 2e-4 * max(1.0, float(r.abs().max())), name
 
 
-def test_oracle_pyramid_equals_reference_cuda_fp64():
+def test_oracle_pyramid_equals_reference_cuda():
     ext = _ext()
     g = torch.Generator().manual_seed(1)
     H, W, Ho, Wo = 13, 21, 7, 11
-    x = torch.randn(2, 8, H, W, generator=g, dtype=torch.float64)
-    off = torch.randn(2, 18, Ho, Wo, generator=g, dtype=torch.float64) * 1.5
-    w = torch.randn(6, 8, 3, 3, generator=g, dtype=torch.float64)
-    gy = torch.randn(2, 6, Ho, Wo, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 8, H, W, generator=g, dtype=torch.float32)
+    off = torch.randn(2, 18, Ho, Wo, generator=g, dtype=torch.float32) * 1.5
+    w = torch.randn(6, 8, 3, 3, generator=g, dtype=torch.float32)
+    gy = torch.randn(2, 6, Ho, Wo, generator=g, dtype=torch.float32)
     sh, sw = H / Ho, W / Wo
     xc, oc, wc, gc = (t.cuda() for t in (x, off, w, gy))
     e = xc.new_empty(0)
@@ -66,7 +69,7 @@ def test_oracle_pyramid_equals_reference_cuda_fp64():
     grads = torch.autograd.grad(y, [xr, offr, wr], gy)
     # the scale is a C float in the reference; the oracle applies the same float product (dcn_ref.c sample_pos)
     for name, a, r in zip(['out', 'dx', 'doff', 'dw'], (y,) + grads, (out, gi, go, gw)):
-        assert (a.detach() - r.cpu()).abs().max() < 1e-9, name
+        assert (a.detach() - r.cpu()).abs().max() < 2e-4 * max(1.0, float(r.abs().max())), name
 
 
 def test_reference_kernel_vs_ours_timing():

@@ -1,0 +1,100 @@
+"""Per-kernel timing at the BASELINE cfg2 level-0 shapes (B=4, 256 ch, 100x168 -> 67 200 pixels): CUDA events on the
+launch stream after warm-up, L2 flushed between iterations (write of a 256 MB buffer), against MEASURED_PEAKS.json.
+Also the harness ncu attaches to (`--ncu KERNEL` runs that kernel 3 times only)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import lsnet_b200.ops as ops
+from lsnet_b200.ops import gemm_ops as G
+
+dev = 'cuda'
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json'))) \
+    if os.path.exists('MEASURED_PEAKS.json') else dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
+only = sys.argv[sys.argv.index('--ncu') + 1] if '--ncu' in sys.argv else None
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if only:
+        return 0.0
+    ts = []
+    for _ in range(n):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+B, C, H, W = 4, 256, 100, 168
+P = B * H * W
+g = torch.Generator().manual_seed(0)
+x = torch.randn(B, C, H, W, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+off = (torch.randn(B, 18, H, W, generator=g) * 1.5).to(dev).contiguous(memory_format=torch.channels_last)
+mask = torch.rand(B, 9, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+w = (torch.randn(256, 256, 3, 3, generator=g) / 48).to(dev)
+col = torch.randn(P, 2304, generator=g).to(dev, torch.bfloat16)
+wp = torch.randn(256, 2304, generator=g).to(dev, torch.bfloat16)
+wpT = torch.randn(2304, 256, generator=g).to(dev, torch.bfloat16)
+dy = torch.randn(P, 256, generator=g).to(dev, torch.bfloat16)
+out = torch.empty(P, 256, device=dev, dtype=torch.bfloat16)
+rows = []
+
+
+def add(name, ms, work, unit):
+    if only:
+        return
+    if unit == 'TFLOP/s':
+        ach = work / (ms * 1e-3) / 1e12
+        frac = ach / peaks['bf16_tflops']
+    else:
+        ach = work / (ms * 1e-3) / 1e9
+        frac = ach / peaks['hbm_gbs']
+    rows.append(dict(kernel=name, ms=ms, achieved=ach, unit=unit, frac_of_measured_peak=frac))
+    print(f'{name:46s} {ms:8.3f} ms  {ach:9.1f} {unit}  {100 * frac:5.1f}% of measured peak', flush=True)
+
+
+if only in (None, 'gemm'):
+    ms = timeit(lambda: G.gemm(col, wp, None, False, torch.bfloat16, out=out))
+    add('gemm_kmajor<256> DCN fwd  M67200 N256 K2304', ms, 2.0 * P * 256 * 2304, 'TFLOP/s')
+if only in (None, 'gemm_dcol'):
+    ms = timeit(lambda: G.gemm(dy, wpT, None, False, torch.bfloat16))
+    add('gemm_kmajor<256> dCol     M67200 N2304 K256', ms, 2.0 * P * 256 * 2304, 'TFLOP/s')
+if only in (None, 'conv'):
+    wc = G.pack_conv_weight(w)
+    ms = timeit(lambda: G.conv2d_nhwc(x, wc, 3, 3, 1))
+    add('gemm_kmajor<256> conv3x3  B4 100x168 256->256', ms, 2.0 * P * 256 * 2304, 'TFLOP/s')
+if only in (None, 'wgrad'):
+    ms = timeit(lambda: G.gemm_tn(dy, col))
+    add('gemm_mnmajor DCN dW       P67200 M256 N2304', ms, 2.0 * P * 256 * 2304, 'TFLOP/s')
+if only in (None, 'conv_wgrad'):
+    dyn = dy.view(B, H, W, 256).permute(0, 3, 1, 2)
+    ms = timeit(lambda: G.conv2d_wgrad_nhwc(dyn, x, 3, 3, 1))
+    add('gemm_mnmajor conv dW      B4 100x168 256x9x256', ms, 2.0 * P * 256 * 2304, 'TFLOP/s')
+if only in (None, 'im2col'):
+    ms = timeit(lambda: ops.dcn_im2col(x, off, mask, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1))
+    add('dcn_im2col DCNv2          B4 100x168 C256', ms, P * (2.0 * C + 4 * 27 + 2.0 * 9 * C), 'GB/s')
+if only in (None, 'col2im'):
+    gcol = torch.randn(P, 2304, generator=g).to(dev, torch.bfloat16)
+    ms = timeit(lambda: ops.dcn_col2im(gcol, x, off, mask, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1))
+    add('dcn_col2im DCNv2 bf16 reds B4 100x168 C256', ms, P * (2.0 * 9 * C + 2.0 * C + 2.0 * C + 8 * 27), 'GB/s')
+    ms = timeit(lambda: ops.dcn_col2im(gcol, x, off, mask, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1, dx_fp32=True))
+    add('dcn_col2im DCNv2 fp32 reds B4 100x168 C256', ms, P * (2.0 * 9 * C + 2.0 * C + 4.0 * C + 8 * 27), 'GB/s')
+    z = torch.zeros_like(off)
+    ms = timeit(lambda: ops.dcn_col2im(gcol, x, z, mask, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1))
+    add('dcn_col2im DCNv2 zero offsets (bench towers)', ms, P * (2.0 * 9 * C + 2.0 * C + 2.0 * C + 8 * 27), 'GB/s')
+if only in (None, 'gn'):
+    wgt, bias = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    ms = timeit(lambda: ops.group_norm_nhwc(x, 32, wgt, bias, 1e-5, relu=True))
+    add('groupnorm fwd (stats+apply) B4 100x168 C256', ms, P * 3.0 * 2 * C, 'GB/s')
+if not only:
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(rows, open('gpurun_out/kernels.json', 'w'), indent=1)

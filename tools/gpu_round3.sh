@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "dcn" -rA -p no:cacheprovider > gpurun_out/pytest_dcn.log 2>&1; echo "exit $?" >> gpurun_out/pytest_dcn.log
+grep -E "^(FAILED|ERROR)|^E  |passed|failed|exit" gpurun_out/pytest_dcn.log | head -20
+timeout 1200 python -m pytest tests/test_gpu_model.py tests/test_gpu_reference_cuda.py -q -m gpu -rA -s -p no:cacheprovider > gpurun_out/pytest_model.log 2>&1; echo "exit $?" >> gpurun_out/pytest_model.log
+grep -E "^(FAILED|ERROR)|^E  |passed|failed|exit|DCNv2 fwd" gpurun_out/pytest_model.log | head -30
+for mode in "--eager" ""; do
+timeout 900 python bench.py --steps 8 --warmup 3 --no-cpu-baseline $mode > gpurun_out/bench$mode.json 2> gpurun_out/bench$mode.err; echo "bench $mode exit $?"
+python - "$mode" <<'PY'
+import json,sys
+try:
+    d=json.loads(open('gpurun_out/bench%s.json'%sys.argv[1]).read().strip().splitlines()[-1])
+    print('value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'launches', d['gpu_launches'], d['config']['step_mode'])
+    for k,v in d['roofline']['classes'].items(): print(' ', k, v)
+except Exception as e: print('parse fail', e)
+PY
+tail -n 6 gpurun_out/bench$mode.err
+done
