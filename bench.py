@@ -196,7 +196,7 @@ def run_gpu(args, rank, world, local_rank):
         mode = 'eager (torch DDP)'
     else:
         from lsnet_b200.train import GraphTrainer
-        tr = GraphTrainer(MODEL_CFG['bbox_r50'], host[0], device=dev, distributed=distributed)
+        tr = GraphTrainer(MODEL_CFG['bbox_r50'], host[0], device=dev, distributed=distributed, kernel_timing=True)
     torch.cuda.synchronize()
 
     def barrier():
@@ -226,19 +226,28 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         clocks.start()
     # ---- value: inputs resident in HBM; kernel-class timing (CUDA events on the launch stream) enabled ----
-    lib.lsnet_timing_reset()
-    lib.lsnet_timing_enable(1)
+    graph_mode = not args.eager
+    if not graph_mode:
+        lib.lsnet_timing_reset()
+        lib.lsnet_timing_enable(1)
     l0 = L.launch_count()
     ms = timed(lambda s: tr.step(resident[s % nb]), args.steps)
-    launches = L.launch_count() - l0
+    launches = (tr.launches_per_step * args.steps) if graph_mode else (L.launch_count() - l0)
     lib.lsnet_timing_enable(0)
+    # eager: events of all K steps.  graph: one extra replay of the INSTRUMENTED capture of the same step right after
+    # the timed region (external event-record nodes; the timed graph itself carries no instrumentation)
+    timed_steps = 1 if graph_mode else args.steps
+    if graph_mode:
+        tr.replay_instrumented()
+        torch.cuda.synchronize()
     classes = {}
     for cls, name in enumerate(['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)',
                                 'dcn_im2col(gather)', 'dcn_col2im(scatter)']):
         tms, n, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
         lib.lsnet_timing_collect(cls, ctypes.byref(tms), ctypes.byref(n), ctypes.byref(work))
         classes[name] = dict(ms=tms.value, launches=n.value, work=work.value)
-    lib.lsnet_timing_reset()
+    if not graph_mode:
+        lib.lsnet_timing_reset()
     # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
     h2d = host[0]['img'].numel() * 4
 
@@ -268,8 +277,9 @@ def run_gpu(args, rank, world, local_rank):
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peaks['hbm'], unit='GB/s',
                     frac=achieved / peaks['hbm'], traffic=None)
     roof.update(peak_source=peaks['src'] + (' sustained' if 'gemm' in dom else ''),
-                share_of_step=c['ms'] / ms, avg_launch_ms=per_launch_ms, launches=c['launches'],
-                classes={k: dict(ms_per_step=v['ms'] / args.steps, launches_per_step=v['launches'] / args.steps,
+                share_of_step=c['ms'] / (ms * timed_steps / args.steps), avg_launch_ms=per_launch_ms,
+                launches_timed=c['launches'], timed_steps=timed_steps,
+                classes={k: dict(ms_per_step=v['ms'] / timed_steps, launches_per_step=v['launches'] / timed_steps,
                                  achieved=(v['work'] / (v['ms'] / 1e3) / (1e12 if 'gemm' in k else 1e9)) if v['ms'] > 0 else 0.0,
                                  unit='TFLOP/s' if 'gemm' in k else 'GB/s') for k, v in classes.items()})
     cpu = None

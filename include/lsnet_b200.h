@@ -71,6 +71,13 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
                         void* stream);
 
+/* Backward-pass gradient staging: dY (fp32 if gy_fp32 else bf16; P rows of C channels, pitch ldg) -> bf16 rows of Cpad
+ * channels (zero padded) in `out`, optionally masked by relu_out > 0 (bf16, the forward output of a conv+ReLU), and the
+ * per-channel sum of the staged values into colsum[C] (fp32; the bias gradient, replacing
+ * `grad_bias.addmv_(grad_output, ones)` of deform_conv_cuda.cpp:788-794).  relu_out / colsum may be NULL. */
+int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P, int C,
+                    int Cpad, void* out, long long ldout, float* colsum, void* stream);
+
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel

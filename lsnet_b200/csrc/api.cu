@@ -37,15 +37,23 @@ static cudaEvent_t get_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 bool timing_on() { return g_timing; }
+// Inside a stream capture the records become EXTERNAL event-record nodes of the graph: every replay re-stamps them, so
+// after a replay the elapsed time of each captured launch can be read like that of an eager launch.
+static void record(cudaEvent_t e, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, st, cudaEventRecordExternal);
+  else cudaEventRecord(e, st);
+}
 int timing_begin(int cls, double work, cudaStream_t st) {
   if (!g_timing) return -1;
   TimedLaunch t{cls, get_event(), get_event(), work};
-  cudaEventRecord(t.a, st);
+  record(t.a, st);
   g_timed.push_back(t);
   return static_cast<int>(g_timed.size()) - 1;
 }
 void timing_end(int h, cudaStream_t st) {
-  if (h >= 0) cudaEventRecord(g_timed[h].b, st);
+  if (h >= 0) record(g_timed[h].b, st);
 }
 }  // namespace lsn
 

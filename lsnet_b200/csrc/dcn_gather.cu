@@ -10,6 +10,8 @@
 // column matrix (tap-major, channel-minor) that the tcgen05 GEMM consumes K-major through TMA.
 // HBM-bound: algorithmic bytes per output pixel = 2C (x) + 4*3*taps (offset,mask) + 2*taps*C (columns).
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "lsnet_internal.h"
 
 namespace lsn {
@@ -70,6 +72,19 @@ __device__ __forceinline__ void sample_pos(const DcnGeom& g, const float* __rest
   *w = __fadd_rn(__fmul_rn(static_cast<float>(wo * g.sw - g.pw + j * g.dw), g.scale_w), ow);
 }
 
+// 16-byte streaming load that does not allocate in L1 (the column matrix is read exactly once; keep L1 for x)
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -83,6 +98,7 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
 // grid: (patches_w, patches_h, B).  One warp per output pixel: lane k (< taps) derives the sampling position, the four
 // (mask-folded) bilinear weights and the four corner pixel indices of tap k ONCE; the tap loop broadcasts them with
 // shuffles, and every lane gathers/interpolates/stores the 8 channels it owns (16-byte accesses, coalesced per corner).
+template <int U>   // taps in flight per lane: 4*U independent 16-byte gathers are issued before the first use
 __global__ void __launch_bounds__(GATHER_THREADS)
 dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ offset,
                   const float* __restrict__ mask, __nv_bfloat16* __restrict__ col, const DcnGeom g) {
@@ -115,30 +131,47 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
           co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
         }
         const int nt = min(32, taps - t0);
-        for (int kk = 0; kk < nt; ++kk) {
-          const float w0 = __shfl_sync(0xffffffffu, cw0, kk), w1 = __shfl_sync(0xffffffffu, cw1, kk);
-          const float w2 = __shfl_sync(0xffffffffu, cw2, kk), w3 = __shfl_sync(0xffffffffu, cw3, kk);
-          const long long o0 = static_cast<long long>(__shfl_sync(0xffffffffu, co0, kk)) * g.ldx;
-          const long long o1 = static_cast<long long>(__shfl_sync(0xffffffffu, co1, kk)) * g.ldx;
-          const long long o2 = static_cast<long long>(__shfl_sync(0xffffffffu, co2, kk)) * g.ldx;
-          const long long o3 = static_cast<long long>(__shfl_sync(0xffffffffu, co3, kk)) * g.ldx;
-          const bool any = (w0 != 0.f) || (w1 != 0.f) || (w2 != 0.f) || (w3 != 0.f);
-          __nv_bfloat16* d = dst + static_cast<long long>(t0 + kk) * g.C;
-          for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
-            uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-            if (any) {
-              const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(x + o0 + c0));
-              const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(x + o1 + c0));
-              const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(x + o2 + c0));
-              const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(x + o3 + c0));
-              float f0[8], f1[8], f2[8], f3[8], acc[8];
-              bf16x8_to_float(u0, f0); bf16x8_to_float(u1, f1); bf16x8_to_float(u2, f2); bf16x8_to_float(u3, f3);
+        for (int kk = 0; kk < nt; kk += U) {
+          float wq[U][4];
+          long long oq[U][4];
+          bool any[U];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] = fmaf(w3, f3[e], fmaf(w2, f2[e], fmaf(w1, f1[e], w0 * f0[e])));
-              outv = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                                pack_bf16x2(acc[6], acc[7]));
+          for (int u = 0; u < U; ++u) {
+            const int src = min(kk + u, nt - 1);
+            wq[u][0] = __shfl_sync(0xffffffffu, cw0, src); wq[u][1] = __shfl_sync(0xffffffffu, cw1, src);
+            wq[u][2] = __shfl_sync(0xffffffffu, cw2, src); wq[u][3] = __shfl_sync(0xffffffffu, cw3, src);
+            oq[u][0] = static_cast<long long>(__shfl_sync(0xffffffffu, co0, src)) * g.ldx;
+            oq[u][1] = static_cast<long long>(__shfl_sync(0xffffffffu, co1, src)) * g.ldx;
+            oq[u][2] = static_cast<long long>(__shfl_sync(0xffffffffu, co2, src)) * g.ldx;
+            oq[u][3] = static_cast<long long>(__shfl_sync(0xffffffffu, co3, src)) * g.ldx;
+            any[u] = (kk + u < nt) &&
+                     ((wq[u][0] != 0.f) || (wq[u][1] != 0.f) || (wq[u][2] != 0.f) || (wq[u][3] != 0.f));
+          }
+          for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
+            uint4 ld[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (any[u]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ld[u][q] = __ldg(reinterpret_cast<const uint4*>(x + oq[u][q] + c0));
+              }
             }
-            *reinterpret_cast<uint4*>(d + c0) = outv;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (kk + u >= nt) continue;
+              uint4 outv = make_uint4(0u, 0u, 0u, 0u);
+              if (any[u]) {
+                float f0[8], f1[8], f2[8], f3[8], acc[8];
+                bf16x8_to_float(ld[u][0], f0); bf16x8_to_float(ld[u][1], f1);
+                bf16x8_to_float(ld[u][2], f2); bf16x8_to_float(ld[u][3], f3);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  acc[e] = fmaf(wq[u][3], f3[e], fmaf(wq[u][2], f2[e], fmaf(wq[u][1], f1[e], wq[u][0] * f0[e])));
+                outv = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                                  pack_bf16x2(acc[6], acc[7]));
+              }
+              st_stream(dst + static_cast<long long>(t0 + kk + u) * g.C + c0, outv);
+            }
           }
         }
       }
@@ -168,7 +201,7 @@ __device__ __forceinline__ void red_f32x8(float* dst, const float (&v)[8]) {
 }
 
 template <bool DX_FP32>
-__global__ void __launch_bounds__(GATHER_THREADS)
+__global__ void __launch_bounds__(GATHER_THREADS, 3)
 dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* __restrict__ x,
                   const float* __restrict__ offset, const float* __restrict__ mask, void* __restrict__ dx,
                   float* __restrict__ doffset, float* __restrict__ dmask, const DcnGeom g, long long lddx,
@@ -216,7 +249,7 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
             const __nv_bfloat16* src = gcol + p * g.ldcol + static_cast<long long>(t0 + kk) * g.C;
             for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
               float gc[8];
-              bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(src + c0)), gc);
+              bf16x8_to_float(ld_stream(src + c0), gc);
               float xv[4][8];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -289,8 +322,18 @@ extern "C" int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, 
   // algorithmic bytes: x read once (B*H*W*2C) + offsets/mask (4*(2+[mask])*taps per px) + bf16 columns written
   const double bytes = static_cast<double>(B) * H * W * 2.0 * C + px * 4.0 * taps * (mask ? 3 : 2) + px * 2.0 * taps * C;
   const int th = timing_begin(TC_IM2COL, bytes, static_cast<cudaStream_t>(stream));
-  dcn_im2col_kernel<<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), offset, mask, static_cast<__nv_bfloat16*>(col), g);
+  static int unroll = 0;
+  if (!unroll) {
+    const char* e = getenv("LSNET_IM2COL_U");
+    unroll = e ? atoi(e) : 2;
+    if (unroll < 1 || unroll > 3) unroll = 2;
+  }
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* cp = static_cast<__nv_bfloat16*>(col);
+  if (unroll == 1) dcn_im2col_kernel<1><<<grid, GATHER_THREADS, 0, st_>>>(xp, offset, mask, cp, g);
+  else if (unroll == 2) dcn_im2col_kernel<2><<<grid, GATHER_THREADS, 0, st_>>>(xp, offset, mask, cp, g);
+  else dcn_im2col_kernel<3><<<grid, GATHER_THREADS, 0, st_>>>(xp, offset, mask, cp, g);
   timing_end(th, static_cast<cudaStream_t>(stream));
   return check_launch("dcn_im2col");
 }

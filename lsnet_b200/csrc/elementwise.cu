@@ -1,0 +1,71 @@
+// Small streaming helpers of the backward pass (sm_100a), fused so that every upstream gradient is read exactly once:
+//   grad_prep   dY (fp32 or bf16, any pixel pitch, C channels) -> bf16 pixel-major buffer with the channel count padded
+//               to the GEMM's alignment, optionally masked by the ReLU of the forward output (conv+ReLU epilogues),
+//               and -- in the same pass -- the per-channel column sum = bias gradient (replaces the reference's
+//               `grad_bias.addmv_(grad_output, ones)` GEMV, deform_conv_cuda.cpp:788-794, and torch's separate
+//               cast / mask / sum kernels).
+#include "common.cuh"
+#include "lsnet_internal.h"
+
+namespace lsn {
+
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_ROWS = 64;   // rows per CTA
+
+template <bool FP32_IN>
+__global__ void __launch_bounds__(PREP_THREADS)
+grad_prep_kernel(const void* __restrict__ gy, long long ldg, const __nv_bfloat16* __restrict__ relu_out, long long ldo,
+                 long long P, int C, int Cpad, __nv_bfloat16* __restrict__ out, long long ldout,
+                 float* __restrict__ colsum) {
+  extern __shared__ float sm[];   // [Cpad] partial column sums
+  for (int i = threadIdx.x; i < Cpad; i += PREP_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  const long long r0 = static_cast<long long>(blockIdx.x) * PREP_ROWS;
+  const long long r1 = min(P, r0 + PREP_ROWS);
+  // thread -> fixed column (stride PREP_THREADS over the row-major tile keeps columns fixed when Cpad | PREP_THREADS)
+  const long long total = (r1 - r0) * Cpad;
+  float acc = 0.f;
+  int my_c = -1;
+  for (long long i = threadIdx.x; i < total; i += PREP_THREADS) {
+    const int c = static_cast<int>(i % Cpad);
+    const long long r = r0 + i / Cpad;
+    if (colsum && my_c >= 0 && c != my_c) { atomicAdd(&sm[my_c], acc); acc = 0.f; }
+    my_c = c;
+    float v = 0.f;
+    if (c < C) {
+      v = FP32_IN ? static_cast<const float*>(gy)[r * ldg + c]
+                  : __bfloat162float(static_cast<const __nv_bfloat16*>(gy)[r * ldg + c]);
+      if (relu_out && !(__bfloat162float(relu_out[r * ldo + c]) > 0.f)) v = 0.f;
+    }
+    out[r * ldout + c] = __float2bfloat16(v);
+    acc += v;
+  }
+  if (colsum) {
+    if (my_c >= 0) atomicAdd(&sm[my_c], acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += PREP_THREADS)
+      if (sm[i] != 0.f) atomicAdd(&colsum[i], sm[i]);
+  }
+}
+
+}  // namespace lsn
+
+using namespace lsn;
+
+extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo,
+                               long long P, int C, int Cpad, void* out, long long ldout, float* colsum, void* stream) {
+  if (P <= 0) return 0;
+  if (Cpad < C || Cpad > 8192) return set_error("lsnet_grad_prep: bad channel counts C=%d Cpad=%d", C, Cpad);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
+  const int grid = static_cast<int>((P + PREP_ROWS - 1) / PREP_ROWS);
+  if (gy_fp32)
+    grad_prep_kernel<true><<<grid, PREP_THREADS, sizeof(float) * Cpad, st>>>(
+        gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, Cpad, static_cast<__nv_bfloat16*>(out), ldout,
+        colsum);
+  else
+    grad_prep_kernel<false><<<grid, PREP_THREADS, sizeof(float) * Cpad, st>>>(
+        gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, Cpad, static_cast<__nv_bfloat16*>(out), ldout,
+        colsum);
+  return check_launch("grad_prep");
+}

@@ -9,8 +9,8 @@
 //     split-K over pixel ranges with fp32 red.global.add.  Replaces the weight-gradient GEMMs
 //     (deform_conv_cuda.cpp:782-787, 1113-1124) and conv weight grads.
 //
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
-// warps2-5 = epilogue (each owns the TMEM lane quarter warp_idx%4).  Persistent over output tiles; smem ring of
+// Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
+// warps2-9 = epilogue (warp w owns TMEM lane quarter w%4; the two warps of a quarter split the tile's columns).  Persistent over output tiles; smem ring of
 // kStages {A,B} tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "lsnet_internal.h"
@@ -19,7 +19,7 @@ namespace lsn {
 
 constexpr int BM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int BK = 64;        // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps2-9 epilogue (two warps per TMEM lane quarter)
 
 struct GemmArgs {
   int M, N;            // logical output extent (N multiple of 16)
@@ -41,6 +41,8 @@ struct KCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;        // column halves only pay off from 64 columns up
+  static constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
 };
 
 template <int BN>
@@ -67,7 +69,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // one elected lane per epilogue warp
+      mbar_init(&tempty_bar[s], Cfg::kEpiWarps);   // one elected lane per epilogue warp
     }
     fence_barrier_init();
   }
@@ -147,10 +149,11 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else {
-    // ===================== epilogue (warps 2..5) =====================
+  } else if (warp - 2 < Cfg::kEpiWarps) {
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;     // accumulator row handled by this thread
+    const int col_begin = ((warp - 2) >> 2) * Cfg::kColsPerWarp;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -173,7 +176,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = col_begin; c < col_begin + Cfg::kColsPerWarp; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
@@ -267,7 +270,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -363,6 +366,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * (BNW / 2);
     int as = 0;
     uint32_t aphase = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -379,7 +383,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BNW);
 #pragma unroll 1
-      for (int c = 0; c < BNW; c += 32) {
+      for (int c = col_begin; c < col_begin + BNW / 2; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();

@@ -4,9 +4,81 @@ channels_last) in this round — SURVEY.md §8 row f4 ("next"); the DCNv2 ``conv
 through CONV_LAYERS and so land on the B200 deformable kernels (groups == 1 only for now)."""
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torch.utils.checkpoint as cp
+from torch.autograd import Function
 
 from ..registry import BACKBONES, build_conv_layer
+
+# ---------------------------------------------------------------------------------------------------------------
+# Frozen-statistics BN folded into the convolution (mmdet/models/backbones/resnet.py:636-646 keeps every BN in eval
+# mode; its affine parameters stay trainable).  With fixed (mean, var):  BN(conv(x, W)) = conv(x, W * s) + (beta - mean*s),
+# s = gamma / sqrt(var + eps) -- exactly the same function of (W, gamma, beta), so autograd through the tiny folding
+# ops yields the reference's gradients, while the three activation-sized BN passes (forward transform, backward
+# reduce, backward element-wise) and the separate ReLU / residual-add passes disappear into cuDNN's fused
+# conv+bias(+add)+ReLU epilogue.  Backward: one `grad_prep` pass (ReLU mask + bias column-sum) then cuDNN dgrad/wgrad.
+# ---------------------------------------------------------------------------------------------------------------
+_FUSED_OK = {'checked': False, 'ok': False}
+
+
+def _fused_available(x):
+    if not _FUSED_OK['checked']:
+        _FUSED_OK['checked'] = True
+        try:
+            xx = torch.randn(1, 8, 8, 8, device=x.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            ww = torch.randn(8, 8, 3, 3, device=x.device, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            bb = torch.zeros(8, device=x.device, dtype=torch.bfloat16)
+            y = torch.ops.aten.cudnn_convolution_relu(xx, ww, bb, [1, 1], [1, 1], [1, 1], 1)
+            z = torch.ops.aten.cudnn_convolution_add_relu(xx, ww, y, 1.0, bb, [1, 1], [1, 1], [1, 1], 1)
+            ref = F.relu(F.conv2d(xx.float(), ww.float(), None, 1, 1))
+            _FUSED_OK['ok'] = bool(torch.isfinite(z).all()) and float((y.float() - ref).abs().max()) < 0.1
+        except Exception:
+            _FUSED_OK['ok'] = False
+    return _FUSED_OK['ok']
+
+
+class _ConvBiasAct(Function):
+    """y = relu(conv(x, w) + bias (+ z)) on cuDNN's fused epilogue; bf16 channels_last."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, z, stride, padding, dilation, groups):
+        from ..ops import gemm_ops as G
+        x = G.as_nhwc(x, torch.bfloat16) if x.shape[1] >= 8 else x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wb = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        bb = bias.detach().to(torch.bfloat16)
+        if z is None:
+            y = torch.ops.aten.cudnn_convolution_relu(x, wb, bb, stride, padding, dilation, groups)
+        else:
+            zz = z.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            y = torch.ops.aten.cudnn_convolution_add_relu(x, wb, zz, 1.0, bb, stride, padding, dilation, groups)
+        y = G.as_nhwc(y)
+        ctx.save_for_backward(x, wb, y)
+        ctx.cfg = (stride, padding, dilation, groups, z is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from ..ops import gemm_ops as G
+        x, wb, y = ctx.saved_tensors
+        stride, padding, dilation, groups, has_z = ctx.cfg
+        g, colsum = G.grad_prep(gy, y, True, mult=1)          # ReLU mask + bias gradient in one pass
+        gx, gw, _ = torch.ops.aten.convolution_backward(g, x, wb, None, stride, padding, dilation, False, [0, 0], groups,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return gx, gw, colsum, (g if has_z else None), None, None, None, None
+
+
+def conv_bn_act(x, conv, bn, z=None):
+    """relu(BN_eval(conv(x)) (+ z)) with the BN folded into the conv (see above)."""
+    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * s
+    w = conv.weight * s.view(-1, 1, 1, 1)
+    return _ConvBiasAct.apply(x, w, shift, z, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups)
+
+
+def conv_bn_fold(conv, bn):
+    """(W*s, beta - mean*s): the folded weight and bias of a conv followed by an eval-mode BN, no activation."""
+    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    return conv.weight * s.view(-1, 1, 1, 1), bn.bias - bn.running_mean * s
 
 
 class Bottleneck(nn.Module):
@@ -39,6 +111,24 @@ class Bottleneck(nn.Module):
 
     norm3 = property(lambda self: self.bn3)
 
+    def _fusable(self, x):
+        return (x.is_cuda and not self.bn1.training and not self.bn2.training and not self.bn3.training
+                and isinstance(self.conv2, nn.Conv2d) and _fused_available(x))
+
+    def _inner_fused(self, x):
+        out = conv_bn_act(x, self.conv1, self.bn1)
+        out = conv_bn_act(out, self.conv2, self.bn2)
+        if self.downsample is None:
+            return conv_bn_act(out, self.conv3, self.bn3, z=x)
+        # identity branch: plain conv with the folded weight; its folded bias rides on conv3's bias
+        wd, bd = conv_bn_fold(self.downsample[0], self.downsample[1])
+        dc = self.downsample[0]
+        ident = F.conv2d(x.to(torch.bfloat16), wd.to(torch.bfloat16), None, dc.stride, dc.padding)
+        s = self.bn3.weight * torch.rsqrt(self.bn3.running_var + self.bn3.eps)
+        shift = self.bn3.bias - self.bn3.running_mean * s + bd
+        w3 = self.conv3.weight * s.view(-1, 1, 1, 1)
+        return _ConvBiasAct.apply(out, w3, shift, ident, [1, 1], [0, 0], [1, 1], 1)
+
     def _inner(self, x):
         out = self.relu(self.bn1(self.conv1(x)))
         out = self.relu(self.bn2(self.conv2(out)))
@@ -46,6 +136,10 @@ class Bottleneck(nn.Module):
         return out + (x if self.downsample is None else self.downsample(x))
 
     def forward(self, x):
+        if self._fusable(x):       # ReLU of the block output is inside the fused epilogue
+            if self.with_cp and x.requires_grad:
+                return cp.checkpoint(self._inner_fused, x, use_reentrant=False)
+            return self._inner_fused(x)
         out = cp.checkpoint(self._inner, x, use_reentrant=False) if self.with_cp and x.requires_grad else self._inner(x)
         return self.relu(out)
 
@@ -134,7 +228,10 @@ class ResNet(nn.Module):
                     nn.init.constant_(m.bn3.weight, 0)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        if x.is_cuda and not self.bn1.training and _fused_available(x):
+            x = self.maxpool(conv_bn_act(x, self.conv1, self.bn1))
+        else:
+            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
         for i, name in enumerate(self.res_layers):
             x = getattr(self, name)(x)

@@ -131,14 +131,17 @@ class PyramidDeformConv(_DeformBase):
         assert not bias
         super().__init__(*args, **kwargs)
 
-    def forward(self, x, offset, scale_h, scale_w):
+    def forward(self, x, offset, scale_h, scale_w, out_slice=None):
+        """``out_slice=(buffer [B,H,W,C_total] bf16, channel offset)`` makes the op write its result in place into a
+        wider pixel-major buffer (LSHead concatenates three of these along channels)."""
         ph = max(self.kernel_size[0] - x.size(2), 0)
         pw = max(self.kernel_size[1] - x.size(3), 0)
         if ph or pw:
             x = F.pad(x, (0, pw, 0, ph))
             offset = F.pad(offset, (0, pw, 0, ph))
+            out_slice = None
         out = ops.pyramid_deform_conv(x, offset, self.weight, (scale_h, scale_w), self.stride, self.padding,
-                                      self.dilation, self.groups, self.deformable_groups)
+                                      self.dilation, self.groups, self.deformable_groups, out_slice=out_slice)
         if ph or pw:
             out = out[:, :, :out.size(2) - ph, :out.size(3) - pw]
         return out

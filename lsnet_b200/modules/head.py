@@ -235,6 +235,14 @@ class LSHead(nn.Module):
 
     _SCALE_CACHE = {}
 
+    @staticmethod
+    def _join(buf, slices):
+        """The three pyramid-DCN results of a level: already adjacent in ``buf`` when they were written in place
+        (the reference does torch.cat, lsnet_head.py:701,707); otherwise concatenate."""
+        if all(s.data_ptr() == buf.data_ptr() + 2 * i * s.shape[1] for i, s in enumerate(slices)):
+            return ops.join_slices(buf.permute(0, 3, 1, 2), slices)
+        return torch.cat(slices, dim=1)
+
     def _scale_vec(self, sh, sw, device):
         """(1, 2*points, 1, 1) vector [sh, sw, sh, sw, ...]; cached on the device so that no host->device copy happens
         inside a captured step."""
@@ -283,23 +291,27 @@ class LSHead(nn.Module):
             offs = {br: lvl[l][1][br][2] for br in brs}
             raws = {br: [] for br in brs}
             cls_raws = []
-            for lv in lvls:
+            B_, pc = cls_feats[l].shape[0], self.point_feat_channels
+            bufs = {br: torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16) for br in brs}
+            cls_buf = torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16)
+            for j, lv in enumerate(lvls):
                 sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
                 sc = self._scale_vec(sh, sw, offs[brs[0]].device)
                 for br in brs:
                     # the reference scales views of the offset tensor in place, so the factors accumulate over the
                     # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
                     offs[br] = offs[br] * sc
-                    raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw))
-                cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw))
+                    raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw,
+                                                                          out_slice=(bufs[br], j * pc)))
+                cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw, out_slice=(cls_buf, j * pc)))
             for br in brs:
-                t = getattr(self, f'{br}_af_dcn_conv')(torch.cat(raws[br], dim=1))
+                t = getattr(self, f'{br}_af_dcn_conv')(self._join(bufs[br], raws[br]))
                 gn = getattr(self, f'{br}_GN')
                 t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
                                         residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
                 t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
                 outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
-            t = ops.group_norm_nhwc(self.cls_af_dcn_conv(torch.cat(cls_raws, dim=1)), self.cls_GN.num_groups,
+            t = ops.group_norm_nhwc(self.cls_af_dcn_conv(self._join(cls_buf, cls_raws)), self.cls_GN.num_groups,
                                     self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
                                     residual=self.cls_feat_conv(cls_feats[l]))
             outs['cls'].append(self.pts_cls_out(t, out_fp32=True))

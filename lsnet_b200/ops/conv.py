@@ -23,7 +23,8 @@ class _ConvSame(Function):
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
         out = G.conv2d_nhwc(x, wp, kh, kw, pad, dil, b, relu, torch.float32 if out_fp32 else torch.bfloat16,
                             n_valid=co)
-        ctx.save_for_backward(x, weight, out if relu else None)
+        ctx.save_for_backward(x, weight, out if (relu and not out_fp32) else None)
+        assert not (relu and out_fp32)
         ctx.cfg = (pad, dil, relu, bias is not None, ci)
         return out
 
@@ -32,9 +33,8 @@ class _ConvSame(Function):
         x, weight, out = ctx.saved_tensors
         pad, dil, relu, has_bias, ci = ctx.cfg
         co, _, kh, kw = weight.shape
-        if relu:
-            gy = gy * (out > 0).to(gy.dtype)
-        gyp = G.pad_channels_nhwc(gy, 8, torch.bfloat16)           # (B, co_pad8, H, W) pixel-major bf16
+        # one pass: cast to bf16, pad channels to 8, apply the ReLU mask, column-sum for the bias gradient
+        gyp, colsum = G.grad_prep(gy, out if relu else None, has_bias and ctx.needs_input_grad[2])
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             wt = G.cached_pack(weight, 'bwd', lambda t: G.pack_conv_weight(t, flip_transpose=True))
@@ -43,7 +43,7 @@ class _ConvSame(Function):
             dw = G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil)       # (co_pad, taps, C_pad8)
             gw = dw[:co, :, :ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
-            gb = gy.float().sum(dim=(0, 2, 3))
+            gb = colsum
         return gx, gw, gb, None, None, None, None
 
 

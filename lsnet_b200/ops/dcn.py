@@ -73,7 +73,8 @@ def _out_hw(H, W, kh, kw, stride, pad, dil):
 class _DCN(Function):
 
     @staticmethod
-    def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32):
+    def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
+                out_slice=None):
         if groups != 1:
             raise NotImplementedError('lsnet_b200 DCN: groups > 1 (X-101 backbone sites) is not built yet')
         co, ci, kh, kw = weight.shape
@@ -96,9 +97,17 @@ class _DCN(Function):
         b = None
         if bias is not None:
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
-        out = G.gemm(col, wp, b, False, torch.float32 if out_fp32 else torch.bfloat16)
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias = cfg, bias is not None
+        if out_slice is not None:
+            # write straight into channels [c0, c0+co) of a wider pixel-major buffer (replaces a later torch.cat)
+            buf, c0 = out_slice
+            assert npad == co and buf.dtype == torch.bfloat16 and buf.shape[:3] == (B, Ho, Wo) and c0 % 8 == 0
+            ld = buf.shape[3]
+            out2d = torch.as_strided(buf, (B * Ho * Wo, co), (ld, 1), buf.storage_offset() + c0)
+            G.gemm(col, wp, b, False, torch.bfloat16, out=out2d)
+            return torch.as_strided(buf, (B, co, Ho, Wo), (Ho * Wo * ld, 1, Wo * ld, ld), buf.storage_offset() + c0)
+        out = G.gemm(col, wp, b, False, torch.float32 if out_fp32 else torch.bfloat16)
         return out.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
 
     @staticmethod
@@ -107,7 +116,7 @@ class _DCN(Function):
         Ho, Wo, kh, kw = ctx.cfg[:4]
         co, ci = weight.shape[:2]
         B = x.shape[0]
-        gyp = G.pad_channels_nhwc(gy, 8, torch.bfloat16)
+        gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4])
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
         gx = goff = gmask = gw = gb = None
@@ -128,8 +137,8 @@ class _DCN(Function):
             dw = G.gemm_tn(gy2, col)                                   # [cop, taps*ci] fp32
             gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[4]:
-            gb = gy.float().sum(dim=(0, 2, 3))
-        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None
+            gb = colsum
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None
 
 
 def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
@@ -147,9 +156,31 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
 
 
 def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
-                        im2col_step=64, out_fp32=False):
+                        im2col_step=64, out_fp32=False, out_slice=None):
     """LSNet pyramid DCN — PyramidDeformConvFunction.apply (mmdet/ops/dcn/deform_conv.py:188-287); scales =
     (scale_h, scale_w); the output grid is the offset grid (:215-217)."""
     scales = _pair(scales)
     return _DCN.apply(x, offset, None, weight, None, _pair(stride), _pair(padding), _pair(dilation),
-                      (float(scales[0]), float(scales[1])), groups, deformable_groups, True, out_fp32)
+                      (float(scales[0]), float(scales[1])), groups, deformable_groups, True, out_fp32, out_slice)
+
+
+class _JoinSlices(Function):
+    """Autograd glue for outputs that several ops wrote into channel slices of ONE buffer: forward returns the buffer
+    (no copy — this is what torch.cat would have produced), backward hands each producer its slice of the gradient."""
+
+    @staticmethod
+    def forward(ctx, buf, *slices):
+        ctx.widths = [s.shape[1] for s in slices]
+        return buf.view_as(buf)
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, c = [], 0
+        for w in ctx.widths:
+            outs.append(g[:, c:c + w])
+            c += w
+        return (None,) + tuple(outs)
+
+
+def join_slices(buf_nchw, slices):
+    return _JoinSlices.apply(buf_nchw, *slices)

@@ -133,3 +133,29 @@ def pad_channels_nhwc(t, mult=8, dtype=torch.bfloat16):
     buf = torch.zeros((B, H, W, Cp), device=t.device, dtype=dtype)
     buf[..., :C] = t.permute(0, 2, 3, 1)
     return buf.permute(0, 3, 1, 2)
+
+
+def grad_prep(gy, relu_out=None, want_colsum=False, mult=8):
+    """Stage an upstream gradient (B,C,H,W) for the backward GEMMs in ONE pass: bf16 pixel-major with C padded to
+    ``mult``, ReLU-masked by ``relu_out`` (the forward output) if given, plus the per-channel sum (bias gradient).
+    Returns (gy_bf16 (B,Cpad,H,W) view, colsum or None).  A gradient that is already bf16 / pixel-major / aligned and
+    needs neither mask nor sum is passed through untouched."""
+    B, C, H, W = gy.shape
+    Cp = (C + mult - 1) // mult * mult
+    pix_major = gy.stride(1) == 1 and gy.stride(2) == W * gy.stride(3) and (B == 1 or gy.stride(0) == H * W * gy.stride(3))
+    if relu_out is None and not want_colsum and pix_major and gy.dtype == torch.bfloat16 and Cp == C \
+            and gy.stride(3) % 8 == 0:
+        return gy, None
+    if not pix_major or gy.dtype not in (torch.float32, torch.bfloat16):
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        if gy.dtype not in (torch.float32, torch.bfloat16):
+            gy = gy.float()
+    ldo = 0
+    if relu_out is not None:
+        assert relu_out.dtype == torch.bfloat16
+        ldo = nhwc_geom(relu_out)[4]
+    out = torch.empty((B, H, W, Cp), device=gy.device, dtype=torch.bfloat16)
+    colsum = torch.empty(C, device=gy.device, dtype=torch.float32) if want_colsum else None
+    L.call('lsnet_grad_prep', L.ptr(gy), L.c_int(int(gy.dtype == torch.float32)), L.c_ll(gy.stride(3)), L.ptr(relu_out),
+           L.c_ll(ldo), L.c_ll(B * H * W), L.c_int(C), L.c_int(Cp), L.ptr(out), L.c_ll(Cp), L.ptr(colsum), L.stream())
+    return out.permute(0, 3, 1, 2), colsum

@@ -68,7 +68,8 @@ class GraphTrainer:
     Semantics are those of ``Trainer`` / the reference's OptimizerHook: grads averaged over ranks, L2 clip at
     ``max_norm`` on the averaged gradient, torch.optim.SGD update (dampening 0, no nesterov)."""
 
-    def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=16, model=None):
+    def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=16, model=None,
+                 kernel_timing=False):
         self.device = torch.device(device)
         self.distributed = distributed
         self.model = model if model is not None else build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'),
@@ -79,6 +80,8 @@ class GraphTrainer:
         self.base_lr, self.momentum, self.wd = opt['lr'], opt.get('momentum', 0.9), opt.get('weight_decay', 1e-4)
         self.max_norm = (cfg.get('grad_clip') or {}).get('max_norm')
         self.capacity = capacity
+        self.kernel_timing = kernel_timing      # capture external event-record nodes around the library's kernels
+        self.launches_per_step = 0              # liblsnet_sm100 kernels inside one replay
         self.iter = 0
         if distributed:     # identical replicas: broadcast rank 0's initial parameters/buffers once
             for t in list(self.model.parameters()) + list(self.model.buffers()):
@@ -137,10 +140,29 @@ class GraphTrainer:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         gemm_ops._PACK_CACHE.clear()           # the packs must be re-done INSIDE the captured region
+        from . import lib as L
+        lib = L.load()
+        n0 = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.log_vars = self._fwd_bwd()
+        self.launches_per_step = L.launch_count() - n0
         gemm_ops._PACK_CACHE.clear()
+        self.graph_timed = None
+        if self.kernel_timing:
+            # a second, instrumented capture of the same step: external event-record nodes around every library
+            # kernel.  Kept apart from the graph that is timed end-to-end because ~500 event nodes perturb it.
+            lib.lsnet_timing_reset()
+            lib.lsnet_timing_enable(1)
+            self.graph_timed = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_timed):
+                self._fwd_bwd()
+            lib.lsnet_timing_enable(0)
+            gemm_ops._PACK_CACHE.clear()
+
+    def replay_instrumented(self):
+        """One forward+backward through the instrumented graph (gradients only; no optimizer step)."""
+        self.graph_timed.replay()
 
     def load_batch(self, batch):
         """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host)."""

@@ -106,3 +106,42 @@ def test_graph_trainer_matches_eager_trainer():
         l_g.append(float(graph.step(b)[0]))
     for a, c in zip(l_e, l_g):
         assert abs(a - c) < 2e-2 * abs(a), (l_e, l_g)
+
+
+def test_backbone_bn_fold_matches_unfused():
+    """ResNet-50 trunk with frozen-statistics BN folded into cuDNN's fused conv+bias(+add)+ReLU epilogue vs the plain
+    conv -> BN(eval) -> ReLU module path: same outputs and parameter gradients within bf16 tolerance."""
+    import lsnet_b200 as L
+    from lsnet_b200.modules import backbone as bb
+    torch.manual_seed(0)
+    net = L.build_backbone(dict(type='ResNet', depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                                norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True, style='pytorch'))
+    net.init_weights(None)
+    for m in net.modules():      # non-trivial statistics / affine so the fold is exercised
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+    net.cuda().train()
+    x = torch.randn(2, 3, 256, 320, device='cuda').contiguous(memory_format=torch.channels_last)
+
+    def run(fused):
+        bb._FUSED_OK.update(checked=True, ok=fused)
+        net.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            outs = net(x)
+        loss = sum((o.float() ** 2).mean() for o in outs)
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        return [o.float().detach() for o in outs], grads
+    bb._FUSED_OK.update(checked=False, ok=False)
+    assert bb._fused_available(x), 'cuDNN fused conv+bias+relu not available for bf16 NHWC'
+    o1, g1 = run(True)
+    o0, g0 = run(False)
+    bb._FUSED_OK.update(checked=False, ok=False)
+    for a, b in zip(o1, o0):
+        assert float((a - b).abs().max() / b.abs().max()) < 5e-2
+    assert set(g1) == set(g0)
+    for k in g0:
+        if g0[k].norm() > 0:
+            cos = float(torch.dot(g1[k].flatten().float(), g0[k].flatten().float()) / (g1[k].norm() * g0[k].norm()))
+            assert cos > 0.98, (k, cos)
