@@ -252,7 +252,8 @@ def run_gpu(args, rank, world, local_rank):
     h2d = host[0]['img'].numel() * 4
 
     def e2e_step(s):
-        b = to_device(host[s % nb], dev)
+        # graph mode: pinned host image -> static device buffer directly; eager: .to(device) then the step
+        b = host[s % nb] if graph_mode else to_device(host[s % nb], dev)
         loss, _ = tr.step(b)
         loss.item()
     ms_e2e = timed(e2e_step, args.steps)

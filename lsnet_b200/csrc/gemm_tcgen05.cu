@@ -40,7 +40,8 @@ struct KCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 32 * 80;   // per epilogue warp: 32 rows x (64 B + 16 B pad)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;        // column halves only pay off from 64 columns up
   static constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
 };
@@ -52,7 +53,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   using Cfg = KCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
@@ -159,56 +161,74 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int n0 = nt * BN;
-      long long row;
+      // output row (and validity) of accumulator row rr of this tile
+      auto row_of = [&](int rr, bool* ok) -> long long {
+        if (p.conv) {
+          const int per_img = p.tiles_h * p.tiles_w;
+          const int b = mt / per_img, t2 = mt % per_img;
+          const int h = (t2 / p.tiles_w) * p.TH + rr / p.TW;
+          const int w = (t2 % p.tiles_w) * p.TW + rr % p.TW;
+          *ok = (h < p.H) && (w < p.W);
+          return (static_cast<long long>(b) * p.H + h) * p.W + w;
+        }
+        const long long g = static_cast<long long>(mt) * BM + rr;
+        *ok = g < p.M;
+        return g;
+      };
       bool valid;
-      if (p.conv) {
-        const int per_img = p.tiles_h * p.tiles_w;
-        const int b = mt / per_img, rr = mt % per_img;
-        const int h = (rr / p.tiles_w) * p.TH + r / p.TW;
-        const int w = (rr % p.tiles_w) * p.TW + r % p.TW;
-        valid = (h < p.H) && (w < p.W);
-        row = (static_cast<long long>(b) * p.H + h) * p.W + w;
-      } else {
-        row = static_cast<long long>(mt) * BM + r;
-        valid = row < p.M;
-      }
+      const long long row = row_of(r, &valid);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      uint32_t* stg = staging + (warp - 2) * (32 * 20);
 #pragma unroll 1
       for (int c = col_begin; c < col_begin + Cfg::kColsPerWarp; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
         const int col0 = n0 + c;
-        if (valid && col0 < p.N) {
-          float f[32];
+        if (col0 >= p.N) continue;     // warp-uniform
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-          }
-          if (p.relu) {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_fp32) {
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.out_fp32) {
+          if (valid) {
             float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (col0 + j < p.N)
                 *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (col0 + j < p.N)
-                *reinterpret_cast<uint4*>(o + j) =
-                    make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                               pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
           }
+        } else {
+          // stage the 32x32 bf16 block in shared memory (row pitch 80 B: conflict-free 16-byte accesses), then store
+          // it with 8 rows x 64 contiguous bytes per warp instruction instead of 32 rows x 16 bytes
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 20 + j * 4) =
+                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          __syncwarp();
+          const int seg = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;
+            bool ok;
+            const long long grow = row_of(q * 32 + rr, &ok);
+            if (ok && col0 + seg * 8 < p.N) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + col0 + seg * 8) = val;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -243,20 +263,31 @@ struct WgradArgs {
 };
 
 constexpr int BNW = 256;
-constexpr int kWStages = 4;
-constexpr int kWABytes = BK * BM * 2;    // 64 pixels x 128 couts
-constexpr int kWBBytes = BK * BNW * 2;   // 64 pixels x 256 cins
-constexpr int kWStageBytes = kWABytes + kWBBytes;
-constexpr int kWSmemBytes = kWStages * kWStageBytes + 1024 + 256;
 
+// MT = number of 128-row output tiles (of C_out) one CTA accumulates at once.  MT = 2 keeps a 256 x 256 fp32
+// accumulator in all 512 TMEM columns and loads the B (pixel x C_in) tile ONCE for both halves: the kernel is
+// L2-bandwidth bound (every 64-pixel chunk is re-read by each output tile that needs it), so doubling the tile
+// height cuts the L2 traffic per FLOP by a third.  MT = 1 double-buffers the accumulator instead.
+template <int MT>
+struct WCfg {
+  static constexpr int kABytes = BK * BM * 2 * MT;    // 64 pixels x (MT*128) couts
+  static constexpr int kBBytes = BK * BNW * 2;        // 64 pixels x 256 cins
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = MT == 1 ? 4 : 3;
+  static constexpr int kAccStages = MT == 1 ? 2 : 1;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const WgradArgs p) {
+  using Cfg = WCfg<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes);
-  uint64_t* empty_bar = full_bar + kWStages;
-  uint64_t* tfull_bar = empty_bar + kWStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,7 +295,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kWStages; ++s) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -283,8 +314,9 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // work item = (tap, m_tile, n_tile, split)
-  const int items = p.taps * p.m_tiles * p.n_tiles * p.splits;
+  // work item = (tap, m_group, n_tile, split); m_group covers MT consecutive 128-row tiles
+  const int m_groups = (p.m_tiles + MT - 1) / MT;
+  const int items = p.taps * m_groups * p.n_tiles * p.splits;
   const int chunks_per_split = (p.k_chunks + p.splits - 1) / p.splits;
 
   if (warp == 0) {
@@ -295,36 +327,36 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int t = item;
         const int split = t % p.splits; t /= p.splits;
         const int nt = t % p.n_tiles; t /= p.n_tiles;
-        const int mt = t % p.m_tiles; t /= p.m_tiles;
+        const int mg = t % m_groups; t /= m_groups;
         const int tap = t;
         const int c_begin = split * chunks_per_split;
         const int c_end = min(p.k_chunks, c_begin + chunks_per_split);
         const int dy = p.conv ? tap / p.kw : 0, dx = p.conv ? tap % p.kw : 0;
         for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kWStageBytes;
-          uint8_t* sB = sA + kWABytes;
-          mbar_expect_tx(&full_bar[stage], kWStageBytes);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (p.conv) {
             const int per_img = p.tiles_h * p.tiles_w;
             const int b = ch / per_img, rr = ch % per_img;
             const int h0 = (rr / p.tiles_w) * p.TH, w0 = (rr % p.tiles_w) * p.TW;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_4d(sA + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, w0, h0, b);
+            for (int j = 0; j < MT * BM / 64; ++j)
+              tma_load_4d(sA + j * (BK * 128), &tmA, &full_bar[stage], mg * MT * BM + j * 64, w0, h0, b);
 #pragma unroll
             for (int j = 0; j < BNW / 64; ++j)
               tma_load_4d(sB + j * (BK * 128), &tmB, &full_bar[stage], nt * BNW + j * 64,
                           w0 - p.pad_w + dx * p.dil_w, h0 - p.pad_h + dy * p.dil_h, b);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], mt * BM + j * 64, ch * BK);
+            for (int j = 0; j < MT * BM / 64; ++j)
+              tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], mg * MT * BM + j * 64, ch * BK);
 #pragma unroll
             for (int j = 0; j < BNW / 64; ++j)
               tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], nt * BNW + j * 64, ch * BK);
           }
-          if (++stage == kWStages) { stage = 0; phase ^= 1; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -346,21 +378,24 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int ch = c_begin; ch < c_end; ++ch) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * kWStageBytes);
-          const uint32_t sB = sA + kWABytes;
+          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sB = sA + Cfg::kABytes;
           // MN-major: LBO = distance between 64-wide M/N chunks (one TMA box = 64 rows x 128 B), SBO = 8 K rows
-          const uint64_t adesc = umma_desc_sw128(sA, BK * 128, 1024);
           const uint64_t bdesc = umma_desc_sw128(sB, BK * 128, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // 16 K rows = 2 swizzle atoms of 8 rows = +2048 B -> +128 in the (addr>>4) field
-            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, ((ch - c_begin) | k) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = umma_desc_sw128(sA + mt * 2 * (BK * 128), BK * 128, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // 16 K rows = 2 swizzle atoms of 8 rows = +2048 B -> +128 in the (addr>>4) field
+              umma_bf16(tmem_d + mt * BNW, adesc + 128 * k, bdesc + 128 * k, idesc, ((ch - c_begin) | k) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (ch == c_end - 1) umma_commit(&tfull_bar[as]);
-          if (++stage == kWStages) { stage = 0; phase ^= 1; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
       }
     }
   } else {
@@ -373,30 +408,34 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int t = item;
       const int split = t % p.splits; t /= p.splits;
       const int nt = t % p.n_tiles; t /= p.n_tiles;
-      const int mt = t % p.m_tiles; t /= p.m_tiles;
+      const int mg = t % m_groups; t /= m_groups;
       const int tap = t;
       const int c_begin = split * chunks_per_split;
       const int c_end = min(p.k_chunks, c_begin + chunks_per_split);
       if (c_end <= c_begin) continue;
-      const int m = mt * BM + r;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BNW);
 #pragma unroll 1
-      for (int c = col_begin; c < col_begin + BNW / 2; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c, v);
-        tmem_ld_wait();
-        const int col0 = nt * BNW + c;
-        if (m < p.M && col0 < p.N) {
-          float* o = p.out + static_cast<long long>(m) * p.ldc + static_cast<long long>(tap) * p.N + col0;
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m = (mg * MT + mt) * BM + r;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(as * BNW + mt * BNW);
+#pragma unroll 1
+        for (int c = col_begin; c < col_begin + BNW / 2; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+          const int col0 = nt * BNW + c;
+          if (m < p.M && col0 < p.N) {
+            float* o = p.out + static_cast<long long>(m) * p.ldc + static_cast<long long>(tap) * p.N + col0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
-                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
-                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                           : "memory");
+            for (int j = 0; j < 32; j += 4) {
+              if (col0 + j < p.N) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                             "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                             "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+              }
             }
           }
         }
@@ -404,7 +443,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (++as == Cfg::kAccStages) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -566,15 +605,18 @@ extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C,
                          static_cast<cudaStream_t>(stream));
 }
 
-static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArgs& a, cudaStream_t st) {
+template <int MT>
+static int launch_wgrad_t(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArgs& a, cudaStream_t st) {
+  using Cfg = WCfg<MT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
-    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_mnmajor): %s", cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(gemm_mnmajor_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_mnmajor<%d>): %s", MT, cudaGetErrorString(e));
     attr_done = true;
   }
-  int base = a.taps * a.m_tiles * a.n_tiles;
+  const int m_groups = (a.m_tiles + MT - 1) / MT;
+  int base = a.taps * m_groups * a.n_tiles;
   int splits = (num_sms() + base - 1) / base;
   if (splits > a.k_chunks) splits = a.k_chunks;
   if (splits < 1) splits = 1;
@@ -582,12 +624,16 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArg
   int items = base * splits;
   int grid = items < num_sms() ? items : num_sms();
   const int th = timing_begin(TC_WGRAD, 2.0 * a.M * a.N * a.taps * a.k_chunks * BK, st);
-  gemm_mnmajor_kernel<<<grid, kThreads, kWSmemBytes, st>>>(tmA, tmB, a);
+  gemm_mnmajor_kernel<MT><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
   timing_end(th, st);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("gemm_mnmajor launch: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return set_error("gemm_mnmajor<%d> launch: %s", MT, cudaGetErrorString(e));
   count_launch();
   return 0;
+}
+
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArgs& a, cudaStream_t st) {
+  return a.m_tiles >= 2 ? launch_wgrad_t<2>(tmA, tmB, a, st) : launch_wgrad_t<1>(tmA, tmB, a, st);
 }
 
 // out[M,N] (fp32, pre-zeroed by the caller or accumulated into) += A[P,M]^T . B[P,N]

@@ -432,6 +432,9 @@ class LSHead(nn.Module):
                     raise ValueError(f'{r.shape[0]} ground-truth instances exceed the packed capacity {G}')
                 out[i, :r.shape[0]] = r.reshape(r.shape[0], width).to(dtype)
             return out.pin_memory() if pin else out
+
+        def fin(t):
+            return t.pin_memory() if (pin and t is not None) else t
         if task in ('bbox', 'pose_bbox'):
             ext = gt_extremes if gt_extremes is not None else self.get_border_center(gt_bboxes)
             tables['bbox'] = pack(ext, 10)
@@ -447,6 +450,8 @@ class LSHead(nn.Module):
         lab = pack([l.view(-1, 1) for l in gt_labels], 1, torch.int32).squeeze(-1).contiguous()
         valid = torch.tensor([[[min(int(np.ceil(m['pad_shape'][0] / s)), h), min(int(np.ceil(m['pad_shape'][1] / s)), w)]
                                for (h, w), s in zip(sizes, self.point_strides)] for m in img_metas], dtype=torch.int32)
+        if str(device) == 'cpu':
+            return PackedGT(bb, fin(cnt), fin(lab), tables, gt_vs, fin(valid))
         to = lambda t: None if t is None else t.to(device, non_blocking=True)
         return PackedGT(to(bb), to(cnt), to(lab), {k: to(v) for k, v in tables.items()}, to(gt_vs), to(valid))
 

@@ -42,7 +42,10 @@ def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg):
     return col
 
 
-DX_FP32 = False   # accumulate dX in fp32 (v4.f32 reds) instead of packed bf16 (half the red instructions)
+import os
+
+# accumulate dX in fp32 (v4.f32 reds) instead of packed bf16 (half the red instructions)
+DX_FP32 = os.environ.get('LSNET_DCN_DX_FP32', '0') == '1'
 
 
 def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True, dx_fp32=None):

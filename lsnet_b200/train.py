@@ -165,9 +165,29 @@ class GraphTrainer:
         self.graph_timed.replay()
 
     def load_batch(self, batch):
-        """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host)."""
+        """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host).  The packed GT goes
+        through two persistent pinned staging sets (no per-step cudaHostAlloc), guarded by an event each."""
         self.img.copy_(batch['img'], non_blocking=True)
-        self.gt.copy_from(self._pack(batch, pin=True))
+        if not hasattr(self, '_stage'):
+            self._stage, self._stage_ev, self._stage_i = [], [], 0
+            for _ in range(2):
+                host = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes,
+                                                   'cpu', gt_extremes=batch.get('gt_extremes'),
+                                                   gt_keypoints_vs=batch.get('gt_keypoints'),
+                                                   gt_masks=batch.get('gt_masks'), capacity=self.capacity, pin=True)
+                self._stage.append(host)
+                self._stage_ev.append(torch.cuda.Event())
+        i = self._stage_i
+        self._stage_i ^= 1
+        self._stage_ev[i].synchronize()          # the previous async copy out of this staging set has finished
+        fresh = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes, 'cpu',
+                                            gt_extremes=batch.get('gt_extremes'),
+                                            gt_keypoints_vs=batch.get('gt_keypoints'), gt_masks=batch.get('gt_masks'),
+                                            capacity=self.capacity, pin=False)
+        st = self._stage[i]
+        st.copy_from(fresh)                       # host -> pinned host (a few KB)
+        self.gt.copy_from(st)                     # pinned host -> static device buffers, async
+        self._stage_ev[i].record()
 
     def step(self, batch=None, sync_log=False):
         if batch is not None:
