@@ -325,8 +325,8 @@ extern "C" int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, 
   static int unroll = 0;
   if (!unroll) {
     const char* e = getenv("LSNET_IM2COL_U");
-    unroll = e ? atoi(e) : 2;
-    if (unroll < 1 || unroll > 3) unroll = 2;
+    unroll = e ? atoi(e) : 1;
+    if (unroll < 1 || unroll > 3) unroll = 1;
   }
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);

@@ -4,6 +4,8 @@
 //               and -- in the same pass -- the per-channel column sum = bias gradient (replaces the reference's
 //               `grad_bias.addmv_(grad_output, ones)` GEMV, deform_conv_cuda.cpp:788-794, and torch's separate
 //               cast / mask / sum kernels).
+#include <stdint.h>
+
 #include "common.cuh"
 #include "lsnet_internal.h"
 
@@ -48,6 +50,62 @@ grad_prep_kernel(const void* __restrict__ gy, long long ldg, const __nv_bfloat16
   }
 }
 
+// Vector path (C % 8 == 0, Cpad == C, 16-byte aligned pitches, (C/8) a power of two <= 256): one thread = one 16-byte
+// vector of 8 channels, walking rows with a fixed column, so the column sums live in registers until the end.
+constexpr int PREPV_ROWS = 128;
+template <bool FP32_IN>
+__global__ void __launch_bounds__(PREP_THREADS)
+grad_prep_vec_kernel(const void* __restrict__ gy, long long ldg, const __nv_bfloat16* __restrict__ relu_out,
+                     long long ldo, long long P, int C, __nv_bfloat16* __restrict__ out, long long ldout,
+                     float* __restrict__ colsum) {
+  extern __shared__ float sm[];   // [C]
+  const int vpp = C / 8;
+  if (colsum) {
+    for (int i = threadIdx.x; i < C; i += PREP_THREADS) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const int v = threadIdx.x % vpp, rstep = PREP_THREADS / vpp;
+  const long long r0 = static_cast<long long>(blockIdx.x) * PREPV_ROWS;
+  const long long r1 = min(P, r0 + PREPV_ROWS);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (long long r = r0 + threadIdx.x / vpp; r < r1; r += rstep) {
+    float f[8];
+    if (FP32_IN) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8 + 4));
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(gy) + r * ldg + v * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+    if (relu_out) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(relu_out + r * ldo + v * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        if (!(t.x > 0.f)) f[2 * i] = 0.f;
+        if (!(t.y > 0.f)) f[2 * i + 1] = 0.f;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + r * ldout + v * 8) =
+        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  if (colsum) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sm[v * 8 + e], acc[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += PREP_THREADS)
+      if (sm[i] != 0.f) atomicAdd(&colsum[i], sm[i]);
+  }
+}
+
 }  // namespace lsn
 
 using namespace lsn;
@@ -58,6 +116,23 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
   if (Cpad < C || Cpad > 8192) return set_error("lsnet_grad_prep: bad channel counts C=%d Cpad=%d", C, Cpad);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
+  const int vpp = C / 8;
+  const bool vec = (C % 8 == 0) && Cpad == C && vpp <= PREP_THREADS && (vpp & (vpp - 1)) == 0 &&
+                   (ldg % (gy_fp32 ? 4 : 8) == 0) && (ldout % 8 == 0) && (!relu_out || ldo % 8 == 0) &&
+                   (reinterpret_cast<uintptr_t>(gy) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                   (!relu_out || reinterpret_cast<uintptr_t>(relu_out) % 16 == 0);
+  if (vec) {
+    const int gridv = static_cast<int>((P + PREPV_ROWS - 1) / PREPV_ROWS);
+    if (gy_fp32)
+      grad_prep_vec_kernel<true><<<gridv, PREP_THREADS, sizeof(float) * C, st>>>(
+          gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, static_cast<__nv_bfloat16*>(out), ldout,
+          colsum);
+    else
+      grad_prep_vec_kernel<false><<<gridv, PREP_THREADS, sizeof(float) * C, st>>>(
+          gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, static_cast<__nv_bfloat16*>(out), ldout,
+          colsum);
+    return check_launch("grad_prep_vec");
+  }
   const int grid = static_cast<int>((P + PREP_ROWS - 1) / PREP_ROWS);
   if (gy_fp32)
     grad_prep_kernel<true><<<grid, PREP_THREADS, sizeof(float) * Cpad, st>>>(

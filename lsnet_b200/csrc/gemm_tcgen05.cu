@@ -12,6 +12,8 @@
 // Warp roles (320 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
 // warps2-9 = epilogue (warp w owns TMEM lane quarter w%4; the two warps of a quarter split the tile's columns).  Persistent over output tiles; smem ring of
 // kStages {A,B} tiles; two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lsnet_internal.h"
 
@@ -633,7 +635,11 @@ static int launch_wgrad_t(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradA
 }
 
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradArgs& a, cudaStream_t st) {
-  return a.m_tiles >= 2 ? launch_wgrad_t<2>(tmA, tmB, a, st) : launch_wgrad_t<1>(tmA, tmB, a, st);
+  // MT = 2 (256-row accumulator, B tile shared by both halves) measured no faster than MT = 1 with a double-buffered
+  // accumulator on the LSNet shapes (r01: DCN dW 0.130 vs 0.126 ms, whole step +0.4 ms), so it is opt-in.
+  static int mt2 = -1;
+  if (mt2 < 0) { const char* e = getenv("LSNET_WGRAD_MT2"); mt2 = (e && e[0] == '1') ? 1 : 0; }
+  return (mt2 && a.m_tiles >= 2) ? launch_wgrad_t<2>(tmA, tmB, a, st) : launch_wgrad_t<1>(tmA, tmB, a, st);
 }
 
 // out[M,N] (fp32, pre-zeroed by the caller or accumulated into) += A[P,M]^T . B[P,N]

@@ -1,4 +1,6 @@
 """Raw (non-autograd) wrappers of the tcgen05 GEMM / implicit-GEMM entry points of liblsnet_sm100.so."""
+import weakref
+
 import torch
 
 from .. import lib as L
@@ -61,13 +63,18 @@ _PACK_CACHE = {}
 
 def cached_pack(w, kind, fn):
     """Packed bf16 copies of a parameter are reused until the parameter changes in place (optimizer step bumps
-    ``_version``): the towers share weights across the 5 pyramid levels, so each weight is packed once per step."""
+    ``_version``): the towers share weights across the 5 pyramid levels, so each weight is packed once per step.
+    The entry holds a weak reference to the tensor object: ``id()`` values (and even data pointers) are recycled after
+    a tensor dies, so identity must be checked on the live object."""
     key = (id(w), kind)
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == w._version and hit[2] == w.data_ptr():
-        return hit[1]
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
     p = fn(w.detach())
-    _PACK_CACHE[key] = (w._version, p, w.data_ptr())
+    _PACK_CACHE[key] = (weakref.ref(w), w._version, p)
+    if len(_PACK_CACHE) > 4096:        # dead entries of short-lived tensors
+        for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
+            del _PACK_CACHE[k]
     return p
 
 

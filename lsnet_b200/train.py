@@ -144,7 +144,8 @@ class GraphTrainer:
         lib = L.load()
         n0 = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.loss, self.log_vars = self._fwd_bwd()
         self.launches_per_step = L.launch_count() - n0
         gemm_ops._PACK_CACHE.clear()
@@ -155,7 +156,7 @@ class GraphTrainer:
             lib.lsnet_timing_reset()
             lib.lsnet_timing_enable(1)
             self.graph_timed = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_timed):
+            with torch.cuda.graph(self.graph_timed, capture_error_mode='thread_local'):
                 self._fwd_bwd()
             lib.lsnet_timing_enable(0)
             gemm_ops._PACK_CACHE.clear()
