@@ -78,6 +78,16 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
 int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P, int C,
                     int Cpad, void* out, long long ldout, float* colsum, void* stream);
 
+/* Frozen-statistics BatchNorm folded into the preceding conv (ResNet trunk with norm_eval=True,
+ * mmdet/models/backbones/resnet.py:636-646): Wb[o] = W[o]*s[o] (bf16, OHWI order), bias[o] = beta[o] - mean[o]*s[o],
+ * s = gamma/sqrt(var+eps); W is OIHW fp32 with I input channels and KK = kh*kw taps.  bwd: gW (fp32 OIHW), ggamma, gbeta
+ * from gWb (bf16 OHWI) and gbias (fp32, may be NULL). */
+int lsnet_bn_fold_fwd(const float* W, const float* gamma, const float* beta, const float* mean, const float* var,
+                      float eps, int O, int I, int KK, void* Wb, float* bias, void* stream);
+int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const float* W, const float* gamma, const float* mean,
+                      const float* var, float eps, int O, int I, int KK, float* gW, float* ggamma, float* gbeta,
+                      void* stream);
+
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel

@@ -106,9 +106,85 @@ grad_prep_vec_kernel(const void* __restrict__ gy, long long ldg, const __nv_bflo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frozen-statistics BatchNorm folded into the preceding convolution's weights (ResNet trunk, norm_eval=True:
+// mmdet/models/backbones/resnet.py:636-646):  W'[o] = W[o] * s[o],  b'[o] = beta[o] - mean[o] * s[o],
+// s = gamma / sqrt(var + eps).  One block per output channel; W is OIHW fp32, W' is written bf16 in OHWI
+// (channels_last) order for cuDNN's NHWC kernels.  Backward: gW = gW' * s, ggamma = (sum gW'.W - gb'.mean)/sqrt(var+eps),
+// gbeta = gb'.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bn_fold_fwd_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ mean,
+                                   const float* __restrict__ var, float eps, int I, int KK,
+                                   __nv_bfloat16* __restrict__ Wb, float* __restrict__ bias) {
+  const int o = blockIdx.x;
+  const float s = gamma[o] * rsqrtf(var[o] + eps);
+  const int n = I * KK;
+  const float* w = W + static_cast<long long>(o) * n;
+  __nv_bfloat16* d = Wb + static_cast<long long>(o) * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {   // j indexes the OHWI destination
+    const int k = j / I, i = j % I;
+    d[j] = __float2bfloat16(w[i * KK + k] * s);
+  }
+  if (threadIdx.x == 0) bias[o] = beta[o] - mean[o] * s;
+}
+
+__global__ void bn_fold_bwd_kernel(const __nv_bfloat16* __restrict__ gWb, const float* __restrict__ gbias,
+                                   const float* __restrict__ W, const float* __restrict__ gamma,
+                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int I,
+                                   int KK, float* __restrict__ gW, float* __restrict__ ggamma,
+                                   float* __restrict__ gbeta) {
+  __shared__ float red[32];
+  const int o = blockIdx.x;
+  const float r = rsqrtf(var[o] + eps);
+  const float s = gamma[o] * r;
+  const int n = I * KK;
+  const float* w = W + static_cast<long long>(o) * n;
+  const __nv_bfloat16* g = gWb + static_cast<long long>(o) * n;
+  float* d = gW + static_cast<long long>(o) * n;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const int k = j / I, i = j % I;
+    const float gv = __bfloat162float(g[j]);
+    const float wv = w[i * KK + k];
+    d[i * KK + k] = gv * s;
+    acc += gv * wv;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const float gb = gbias ? gbias[o] : 0.f;
+      ggamma[o] = (v - gb * mean[o]) * r;
+      gbeta[o] = gb;
+    }
+  }
+}
+
 }  // namespace lsn
 
 using namespace lsn;
+
+extern "C" int lsnet_bn_fold_fwd(const float* W, const float* gamma, const float* beta, const float* mean,
+                                 const float* var, float eps, int O, int I, int KK, void* Wb, float* bias,
+                                 void* stream) {
+  if (O <= 0) return 0;
+  bn_fold_fwd_kernel<<<O, 128, 0, static_cast<cudaStream_t>(stream)>>>(W, gamma, beta, mean, var, eps, I, KK,
+                                                                      static_cast<__nv_bfloat16*>(Wb), bias);
+  return check_launch("bn_fold_fwd");
+}
+
+extern "C" int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const float* W, const float* gamma,
+                                 const float* mean, const float* var, float eps, int O, int I, int KK, float* gW,
+                                 float* ggamma, float* gbeta, void* stream) {
+  if (O <= 0) return 0;
+  bn_fold_bwd_kernel<<<O, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(gWb), gbias, W,
+                                                                      gamma, mean, var, eps, I, KK, gW, ggamma, gbeta);
+  return check_launch("bn_fold_bwd");
+}
 
 extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo,
                                long long P, int C, int Cpad, void* out, long long ldout, float* colsum, void* stream) {

@@ -44,7 +44,9 @@ class _ConvBiasAct(Function):
     def forward(ctx, x, w, bias, z, stride, padding, dilation, groups):
         from ..ops import gemm_ops as G
         x = G.as_nhwc(x, torch.bfloat16) if x.shape[1] >= 8 else x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        wb = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wb = w.detach()
+        if wb.dtype != torch.bfloat16 or not wb.is_contiguous(memory_format=torch.channels_last):
+            wb = wb.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         bb = bias.detach().to(torch.bfloat16)
         if z is None:
             y = torch.ops.aten.cudnn_convolution_relu(x, wb, bb, stride, padding, dilation, groups)
@@ -67,18 +69,47 @@ class _ConvBiasAct(Function):
         return gx, gw, colsum, (g if has_z else None), None, None, None, None
 
 
-def conv_bn_act(x, conv, bn, z=None):
-    """relu(BN_eval(conv(x)) (+ z)) with the BN folded into the conv (see above)."""
-    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-    shift = bn.bias - bn.running_mean * s
-    w = conv.weight * s.view(-1, 1, 1, 1)
-    return _ConvBiasAct.apply(x, w, shift, z, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups)
+class _BnFold(Function):
+    """(W, gamma, beta; frozen mean, var) -> (W' bf16 channels_last, b' fp32) in one kernel each way
+    (lsnet_bn_fold_fwd / lsnet_bn_fold_bwd)."""
+
+    @staticmethod
+    def forward(ctx, W, gamma, beta, mean, var, eps):
+        from .. import lib as L
+        O, I, kh, kw = W.shape
+        Wc = W.detach().contiguous()
+        wb = torch.empty((O, kh, kw, I), device=W.device, dtype=torch.bfloat16)
+        bias = torch.empty(O, device=W.device, dtype=torch.float32)
+        L.call('lsnet_bn_fold_fwd', L.ptr(Wc), L.ptr(gamma.detach()), L.ptr(beta.detach()), L.ptr(mean), L.ptr(var),
+               L.c_f(eps), L.c_int(O), L.c_int(I), L.c_int(kh * kw), L.ptr(wb), L.ptr(bias), L.stream())
+        ctx.save_for_backward(Wc, gamma, mean, var)
+        ctx.eps = eps
+        return wb.permute(0, 3, 1, 2), bias       # logical OIHW, channels_last memory
+
+    @staticmethod
+    def backward(ctx, gwb, gbias):
+        from .. import lib as L
+        Wc, gamma, mean, var = ctx.saved_tensors
+        O, I, kh, kw = Wc.shape
+        gwb = gwb.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gb = None if gbias is None else gbias.float().contiguous()
+        gW = torch.empty_like(Wc)
+        gg = torch.empty(O, device=Wc.device, dtype=torch.float32)
+        gbt = torch.empty(O, device=Wc.device, dtype=torch.float32)
+        L.call('lsnet_bn_fold_bwd', L.ptr(gwb), L.ptr(gb), L.ptr(Wc), L.ptr(gamma.detach()), L.ptr(mean), L.ptr(var),
+               L.c_f(ctx.eps), L.c_int(O), L.c_int(I), L.c_int(kh * kw), L.ptr(gW), L.ptr(gg), L.ptr(gbt), L.stream())
+        return gW, gg, gbt, None, None, None
 
 
 def conv_bn_fold(conv, bn):
-    """(W*s, beta - mean*s): the folded weight and bias of a conv followed by an eval-mode BN, no activation."""
-    s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-    return conv.weight * s.view(-1, 1, 1, 1), bn.bias - bn.running_mean * s
+    """(W*s bf16 channels_last, beta - mean*s): folded weight and bias of a conv followed by an eval-mode BN."""
+    return _BnFold.apply(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps))
+
+
+def conv_bn_act(x, conv, bn, z=None):
+    """relu(BN_eval(conv(x)) (+ z)) with the BN folded into the conv (see above)."""
+    w, shift = conv_bn_fold(conv, bn)
+    return _ConvBiasAct.apply(x, w, shift, z, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups)
 
 
 class Bottleneck(nn.Module):
@@ -123,11 +154,9 @@ class Bottleneck(nn.Module):
         # identity branch: plain conv with the folded weight; its folded bias rides on conv3's bias
         wd, bd = conv_bn_fold(self.downsample[0], self.downsample[1])
         dc = self.downsample[0]
-        ident = F.conv2d(x.to(torch.bfloat16), wd.to(torch.bfloat16), None, dc.stride, dc.padding)
-        s = self.bn3.weight * torch.rsqrt(self.bn3.running_var + self.bn3.eps)
-        shift = self.bn3.bias - self.bn3.running_mean * s + bd
-        w3 = self.conv3.weight * s.view(-1, 1, 1, 1)
-        return _ConvBiasAct.apply(out, w3, shift, ident, [1, 1], [0, 0], [1, 1], 1)
+        ident = F.conv2d(x.to(torch.bfloat16), wd, None, dc.stride, dc.padding)
+        w3, b3 = conv_bn_fold(self.conv3, self.bn3)
+        return _ConvBiasAct.apply(out, w3, b3 + bd, ident, [1, 1], [0, 0], [1, 1], 1)
 
     def _inner(self, x):
         out = self.relu(self.bn1(self.conv1(x)))
