@@ -76,22 +76,46 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
-__device__ __forceinline__ void mean_rstd(const double* stats, int b, int g, const GnArgs& a, float* mean, float* rstd) {
-  const double n = static_cast<double>(a.HW) * (a.C / a.G);
-  const double m = stats[(static_cast<long long>(b) * a.G + g) * 2] / n;
-  double var = stats[(static_cast<long long>(b) * a.G + g) * 2 + 1] / n - m * m;
+// (sum, sumsq) in fp64 -> (mean, rstd) in fp32, once per (sample, group); the streaming kernels then read two floats
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, int BG, double n, float eps,
+                                   float2* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  const double m = stats[2 * i] / n;
+  double var = stats[2 * i + 1] / n - m * m;
   var = var < 0.0 ? 0.0 : var;
-  *mean = static_cast<float>(m);
-  *rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps)));
+  mr[i] = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+__global__ void gn_finalize_bwd_kernel(const double* __restrict__ bstats, int BG, float2* __restrict__ s12) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  s12[i] = make_float2(static_cast<float>(bstats[2 * i]), static_cast<float>(bstats[2 * i + 1]));
+}
+__device__ __forceinline__ void mean_rstd(const float2* mr, int b, int g, const GnArgs& a, float* mean, float* rstd) {
+  const float2 v = __ldg(mr + static_cast<long long>(b) * a.G + g);
+  *mean = v.x;
+  *rstd = v.y;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // y = relu?((x (+x2) - mean) * rstd * gamma + beta)
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2, const GnArgs a,
-                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 __nv_bfloat16* __restrict__ y) {
   const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
   const long long total = static_cast<long long>(a.B) * a.HW * vpp;
+  // the launcher makes gridDim.x * GN_THREADS a multiple of vpp, so every thread keeps ONE vector column: its
+  // gamma / beta live in registers
+  float gm[8], bt[8];
+  {
+    const int v0 = static_cast<int>((static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x) % vpp);
+    load8f(gamma + v0 * 8, gm);
+    load8f(beta + v0 * 8, bt);
+  }
   for (long long i = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * GN_THREADS) {
     const int v = static_cast<int>(i % vpp);
@@ -107,10 +131,6 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
     }
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float o = (f[e] - mean) * rstd * gm[e] + bt[e];
@@ -125,7 +145,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2,
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
-                    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                     double* __restrict__ bstats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sm[];   // per channel: dgamma, dbeta [2*C]; per vector column: s1, s2 [2*vpp]
   const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
@@ -141,6 +161,8 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 #pragma unroll
   for (int e = 0; e < 8; ++e) dg[e] = db[e] = 0.f;
   int my_v = -1;
+  float gmr[8], btr[8];
+  int loaded_v = -1;
   auto flush = [&]() {
 #pragma unroll
     for (int e = 0; e < 8; ++e) { atomicAdd(&sm_dg[my_v * 8 + e], dg[e]); atomicAdd(&sm_db[my_v * 8 + e], db[e]); dg[e] = db[e] = 0.f; }
@@ -162,12 +184,13 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       for (int e = 0; e < 8; ++e) f[e] = __bfloat162float(__float2bfloat16(f[e] + f2[e]));
     }
     ld8(dy + px * lddy + v * 8, d);
+    if (loaded_v != v) { load8f(gamma + v * 8, gmr); load8f(beta + v * 8, btr); loaded_v = v; }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float gm = __ldg(gamma + v * 8 + e);
+      const float gm = gmr[e];
       const float xh = (f[e] - mean) * rstd;
       float dd = d[e];
-      if (a.relu && !(xh * gm + __ldg(beta + v * 8 + e) > 0.f)) dd = 0.f;
+      if (a.relu && !(xh * gm + btr[e] > 0.f)) dd = 0.f;
       dg[e] += dd * xh;
       db[e] += dd;
       s1 += dd * gm;
@@ -192,12 +215,18 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2,
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
-                    const double* __restrict__ stats, const double* __restrict__ bstats,
+                    const float2* __restrict__ stats, const float2* __restrict__ bstats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ dx,
                     long long lddx) {
   const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
   const float inv_n = 1.f / (static_cast<float>(a.HW) * (a.C / a.G));
   const long long total = static_cast<long long>(a.B) * a.HW * vpp;
+  float gmr[8], btr[8];
+  {
+    const int v0 = static_cast<int>((static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x) % vpp);
+    load8f(gamma + v0 * 8, gmr);
+    load8f(beta + v0 * 8, btr);
+  }
   for (long long i = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * GN_THREADS) {
     const int v = static_cast<int>(i % vpp);
@@ -205,8 +234,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     const int b = static_cast<int>(px / a.HW), g = v / cpg8;
     float mean, rstd;
     mean_rstd(stats, b, g, a, &mean, &rstd);
-    const float s1 = static_cast<float>(bstats[(static_cast<long long>(b) * a.G + g) * 2]);
-    const float s2 = static_cast<float>(bstats[(static_cast<long long>(b) * a.G + g) * 2 + 1]);
+    const float2 s12 = __ldg(bstats + static_cast<long long>(b) * a.G + g);
+    const float s1 = s12.x, s2 = s12.y;
     float f[8], d[8];
     ld8(x + px * a.ldx + v * 8, f);
     if (x2) {
@@ -218,10 +247,10 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     ld8(dy + px * lddy + v * 8, d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float gm = __ldg(gamma + v * 8 + e);
+      const float gm = gmr[e];
       const float xh = (f[e] - mean) * rstd;
       float dd = d[e];
-      if (a.relu && !(xh * gm + __ldg(beta + v * 8 + e) > 0.f)) dd = 0.f;
+      if (a.relu && !(xh * gm + btr[e] > 0.f)) dd = 0.f;
       f[e] = rstd * (dd * gm - (s1 + xh * s2) * inv_n);
     }
     st8(dx + px * lddx + v * 8, f);
@@ -233,9 +262,12 @@ static int gn_check(const char* who, int C, int G, long long ldx, long long ldy)
     return set_error("%s: needs (C/G) %% 8 == 0 and 16-byte aligned pitches (C=%d G=%d)", who, C, G);
   return 0;
 }
-static int gn_grid(long long total_vec) {
+// grid-stride launches: gridDim.x * GN_THREADS must be a multiple of vpp (= C/8) so that a thread keeps its column
+static int gn_grid(long long total_vec, int vpp) {
   long long blocks = (total_vec + GN_THREADS - 1) / GN_THREADS;
-  return static_cast<int>(blocks < 148 * 8 ? (blocks < 1 ? 1 : blocks) : 148 * 8);
+  long long g = blocks < 148 * 8 ? (blocks < 1 ? 1 : blocks) : 148 * 8;
+  while ((g * GN_THREADS) % vpp) ++g;
+  return static_cast<int>(g);
 }
 
 }  // namespace lsn
@@ -254,8 +286,11 @@ extern "C" int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2,
   gn_stats_kernel<<<grid, GN_THREADS, sizeof(float) * 2 * (C / 8), st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats);
   if (int rc = check_launch("gn_stats")) return rc;
-  gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8)), GN_THREADS, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats, gamma, beta,
+  float2* mr = reinterpret_cast<float2*>(stats + 2 * B * G);     // (mean, rstd) table behind the fp64 sums
+  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(stats, B * G, static_cast<double>(HW) * (C / G), eps, mr);
+  if (int rc = check_launch("gn_finalize")) return rc;
+  gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, mr, gamma, beta,
       static_cast<__nv_bfloat16*>(y));
   return check_launch("gn_apply");
 }
@@ -273,13 +308,17 @@ extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2,
   cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
   cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
   dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
+  const float2* mr = reinterpret_cast<const float2*>(stats + 2 * B * G);
   gn_bwd_stats_kernel<<<grid, GN_THREADS, sizeof(float) * (2 * C + 2 * (C / 8)), st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
-      static_cast<const __nv_bfloat16*>(dy), lddy, a, stats, gamma, beta, ws_bstats, dgamma, dbeta);
+      static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, gamma, beta, ws_bstats, dgamma, dbeta);
   if (int rc = check_launch("gn_bwd_stats")) return rc;
-  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8)), GN_THREADS, 0, st>>>(
+  float2* s12 = reinterpret_cast<float2*>(ws_bstats + 2 * B * G);
+  gn_finalize_bwd_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(ws_bstats, B * G, s12);
+  if (int rc = check_launch("gn_finalize_bwd")) return rc;
+  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
-      static_cast<const __nv_bfloat16*>(dy), lddy, a, stats, ws_bstats, gamma, beta, static_cast<__nv_bfloat16*>(dx),
+      static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, s12, gamma, beta, static_cast<__nv_bfloat16*>(dx),
       lddx);
   return check_launch("gn_bwd_apply");
 }

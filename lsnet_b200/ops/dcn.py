@@ -73,6 +73,17 @@ def _out_hw(H, W, kh, kw, stride, pad, dil):
             (W + 2 * pad[1] - (dil[1] * (kw - 1) + 1)) // stride[1] + 1)
 
 
+OVERLAP_WGRAD = os.environ.get('LSNET_OVERLAP_WGRAD', '1') == '1'
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class _DCN(Function):
 
     @staticmethod
@@ -123,6 +134,17 @@ class _DCN(Function):
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
         gx = goff = gmask = gw = gb = None
+        # The weight-gradient GEMM (tensor-pipe bound) only needs dY and the saved columns, the scatter (issue bound on
+        # the CUDA cores) only needs dCol: run the former on a side stream so the two overlap on the SMs.  Captured as a
+        # fork/join inside the step's CUDA graph.
+        side = None
+        if OVERLAP_WGRAD and ctx.needs_input_grad[3]:
+            cur = torch.cuda.current_stream()
+            side = _side_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dw = G.gemm_tn(gy2, col)
+                gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
             # B operand [N = taps*ci, K = co]: W^T, K-major
             def pack_bwd(t):
@@ -136,7 +158,9 @@ class _DCN(Function):
                                          need_dx=ctx.needs_input_grad[0])
             if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
-        if ctx.needs_input_grad[3]:
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif ctx.needs_input_grad[3]:
             dw = G.gemm_tn(gy2, col)                                   # [cop, taps*ci] fp32
             gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[4]:

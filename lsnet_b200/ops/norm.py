@@ -18,7 +18,7 @@ class _GroupNorm(Function):
             x2 = G.as_nhwc(x2, torch.bfloat16)
             ldx2 = G.nhwc_geom(x2)[4]
         w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
-        stats = torch.empty((B, num_groups, 2), device=x.device, dtype=torch.float64)
+        stats = torch.empty((B, num_groups, 3), device=x.device, dtype=torch.float64)
         y = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
         L.call('lsnet_groupnorm_fwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.c_int(B), L.c_int(H * W),
                L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats),
@@ -35,7 +35,7 @@ class _GroupNorm(Function):
         ldx2 = G.nhwc_geom(x2)[4] if x2 is not None else 0
         gy = G.as_nhwc(gy, torch.bfloat16)
         lddy = G.nhwc_geom(gy)[4]
-        bstats = torch.empty((B, num_groups, 2), device=x.device, dtype=torch.float64)
+        bstats = torch.empty((B, num_groups, 3), device=x.device, dtype=torch.float64)
         dx = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
         dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
         dbeta = torch.empty(C, device=x.device, dtype=torch.float32)

@@ -149,3 +149,61 @@ def test_backbone_bn_fold_matches_unfused():
         if g0[k].norm() > 0:
             cos = float(torch.dot(g1[k].flatten().float(), g0[k].flatten().float()) / (g1[k].norm() * g0[k].norm()))
             assert cos > 0.98, (k, cos)
+
+
+@pytest.mark.parametrize('task', ['segm', 'pose_bbox'])
+def test_head_targets_and_losses_other_tasks(task):
+    """BASELINE configs 4/5 (36 contour landmarks, 17 keypoints): LSHead forward on the B200 kernels, then target logic
+    and losses checked against the oracle on the head's own predictions (identical inputs): assignments bit-exact,
+    polygon / keypoint / bbox cross-IOU and focal terms within 1e-4."""
+    import lsnet_b200 as L
+    nv = {'segm': 36, 'pose_bbox': 17}[task]
+    gn = dict(type='GN', num_groups=32, requires_grad=True)
+    kw = dict(type='LSHead', task=task, num_vectors=nv, num_classes=80 if task == 'segm' else 1, in_channels=256,
+              feat_channels=256, point_feat_channels=256, stacked_convs=3, num_kernel_points=9, gradient_mul=0.1,
+              point_strides=[8, 16, 32, 64, 128], point_base_scale=4, norm_cfg=gn, conv_module_type='dcn',
+              loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+              train_cfg=dict(init=dict(assigner=dict(type='CentroidAssigner', scale=4, pos_num=1, iou_type='center')),
+                             refine=dict(assigner=dict(type='ATSSAssigner', topk=9))))
+    if task == 'segm':
+        kw.update(loss_segm_init=dict(type='CrossIOULoss', loss_weight=1.0, loss_type='polygon', stride=9),
+                  loss_segm_refine=dict(type='CrossIOULoss', loss_weight=2.0, loss_type='polygon', stride=9))
+    else:
+        kw.update(loss_bbox_init=dict(type='CrossIOULoss', loss_weight=0.1, loss_type='bbox'),
+                  loss_bbox_refine=dict(type='CrossIOULoss', loss_weight=0.2, loss_type='bbox'),
+                  loss_pose_init=dict(type='CrossIOULoss', loss_weight=1.0, loss_type='keypoint'),
+                  loss_pose_refine=dict(type='CrossIOULoss', loss_weight=2.0, loss_type='keypoint'))
+    torch.manual_seed(0)
+    head = L.build_head(kw)
+    sd = oinit.make_state_dict(task, seed=5, parts=('head',))
+    head.load_state_dict({k[len('bbox_head.'):]: v for k, v in sd.items()})
+    head.cuda().train()
+    d = synth.detector_batch(task, 303)
+    g = torch.Generator().manual_seed(7)
+    feats = [torch.randn(2, 256, 384 // s, 384 // s, generator=g).cuda().to(torch.bfloat16)
+             .contiguous(memory_format=torch.channels_last) for s in (8, 16, 32, 64, 128)]
+    outs = head(feats)
+    if task == 'segm':
+        losses, aux = head.loss(*outs, d['gt_bboxes'], None, None, d['gt_polygons'], d['gt_labels'], d['img_metas'],
+                                return_aux=True)
+        okw = dict(gt_polygons=d['gt_polygons'])
+        o_outs = {'cls': outs[0], 'segm_init': outs[3], 'segm_refine': outs[4]}
+    else:
+        losses, aux = head.loss(*outs, d['gt_bboxes'], None, d['gt_keypoints_vs'], None, d['gt_labels'], d['img_metas'],
+                                return_aux=True)
+        okw = dict(gt_keypoints_vs=[k.clone() for k in d['gt_keypoints_vs']])
+        o_outs = {'cls': outs[0], 'bbox_init': outs[1], 'bbox_refine': outs[2], 'pose_init': outs[5], 'pose_refine': outs[6]}
+    o_outs = {k: [t.detach().float().cpu().contiguous() for t in v] for k, v in o_outs.items()}
+    ol, oaux = O.head_loss(o_outs, d['gt_bboxes'], d['gt_labels'], d['img_metas'], task=task,
+                           num_classes=kw['num_classes'], return_aux=True, **okw)
+    for i in range(2):
+        assert torch.equal(aux['assign_init'][i].cpu().long() + 1, oaux['tg']['init'][i]['assign'])
+        assert torch.equal(aux['assign_refine'][i].cpu().long() + 1, oaux['tg']['refine'][i]['assign'])
+    assert set(losses) == set(ol)
+    for k in ol:
+        got = torch.stack([x.detach().float().cpu() for x in losses[k]])
+        ref = torch.stack([x.detach() for x in ol[k]])
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-6), (k, got, ref)
+    tot = sum(sum(v) for v in losses.values())
+    tot.backward()
+    assert all(torch.isfinite(p.grad).all() for p in head.parameters() if p.grad is not None)
