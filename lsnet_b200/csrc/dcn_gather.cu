@@ -298,128 +298,6 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Fast adjoint for the shape every LSHead site has: 3x3 taps, one deformable group.  Same outputs as
-// dcn_col2im_kernel, ~2x fewer issued instructions (the kernel is issue bound, profiles/r01_ncu_col2im.md):
-//   * per element the four corners are combined as  top = x00 + lw*(x01-x00), bot = x10 + lw*(x11-x10),
-//     val = top + lh*(bot-top), d(val)/dh = bot - top, d(val)/dw = (1-lh)*(x01-x00) + lh*(x11-x10)   (8 flops, was 12);
-//     the mask factor is applied once per tap after the channel reduction;
-//   * a warp-uniform "all four corners inside" path has no per-corner predication;
-//   * the 27 channel sums of a pixel (dy/dx/dmask for 9 taps) are reduced three taps at a time with a transposing
-//     butterfly (16 shuffles per 9 sums instead of 45).
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bfly9(float (&v)[16], int lane) {
-  // in: 16 per-lane partials (entries 9..15 zero); out: lane l (l & 15 < 9) returns the warp total of entry (l & 15)
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = (lane & s) ? v[i + s] : v[i];
-      const float send = (lane & s) ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-
-template <bool DX_FP32>
-__global__ void __launch_bounds__(GATHER_THREADS, 3)
-dcn_col2im9_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* __restrict__ x,
-                   const float* __restrict__ offset, const float* __restrict__ mask, void* __restrict__ dx,
-                   float* __restrict__ doffset, float* __restrict__ dmask, const DcnGeom g, long long lddx,
-                   long long lddo, long long lddm) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = GATHER_THREADS / 32;
-  const int b = blockIdx.z;
-  const int h_base = blockIdx.y * PATCH_H, w_base = blockIdx.x * PATCH_W;
-  for (int pix = warp; pix < PATCH_H * PATCH_W; pix += nwarps) {
-    const int ho = h_base + pix / PATCH_W, wo = w_base + pix % PATCH_W;
-    if (ho >= g.Ho || wo >= g.Wo) continue;
-    const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
-    // ---- lane k < 9: geometry of tap k ----
-    float lh_ = 0.f, lw_ = 0.f, m_ = 1.f;
-    int vbits = 0, co0 = 0, co1 = 0, co2 = 0, co3 = 0;
-    if (lane < 9) {
-      float h, w;
-      sample_pos(g, offset + p * g.ldo, 0, lane, ho, wo, &h, &w);
-      const Corner cn = make_corner(g, b, h, w);
-      if (mask) m_ = __ldg(mask + p * g.ldm + lane);
-      lh_ = cn.lh; lw_ = cn.lw;
-      vbits = (cn.v[0] ? 1 : 0) | (cn.v[1] ? 2 : 0) | (cn.v[2] ? 4 : 0) | (cn.v[3] ? 8 : 0) | (cn.inside ? 16 : 0);
-      co0 = static_cast<int>(cn.o[0] / g.ldx); co1 = static_cast<int>(cn.o[1] / g.ldx);
-      co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
-    }
-    const __nv_bfloat16* src0 = gcol + p * g.ldcol;
-#pragma unroll 1
-    for (int t3 = 0; t3 < 3; ++t3) {          // three taps per butterfly
-      float part[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) part[i] = 0.f;
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int kk = t3 * 3 + u;
-        const float lh = __shfl_sync(0xffffffffu, lh_, kk), lw = __shfl_sync(0xffffffffu, lw_, kk);
-        const float m = __shfl_sync(0xffffffffu, m_, kk);
-        const int vb = __shfl_sync(0xffffffffu, vbits, kk);
-        const int oi[4] = {__shfl_sync(0xffffffffu, co0, kk), __shfl_sync(0xffffffffu, co1, kk),
-                           __shfl_sync(0xffffffffu, co2, kk), __shfl_sync(0xffffffffu, co3, kk)};
-        if (!(vb & 16)) continue;              // warp-uniform: the sample is outside, nothing to add
-        const float hh = 1.f - lh, hw = 1.f - lw;
-        float gh = 0.f, gw = 0.f, gm = 0.f;
-        for (int c0 = lane * 8; c0 < g.C; c0 += 256) {
-          float gc[8];
-          bf16x8_to_float(ld_stream(src0 + static_cast<long long>(kk) * g.C + c0), gc);
-          float x0[8], x1[8], x2[8], x3[8];
-          if ((vb & 15) == 15) {
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[0]) * g.ldx + c0)), x0);
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[1]) * g.ldx + c0)), x1);
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[2]) * g.ldx + c0)), x2);
-            bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[3]) * g.ldx + c0)), x3);
-          } else {                             // border: out-of-range corners read as zero (…kernel.cu:98-109)
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            bf16x8_to_float((vb & 1) ? __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[0]) * g.ldx + c0)) : z, x0);
-            bf16x8_to_float((vb & 2) ? __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[1]) * g.ldx + c0)) : z, x1);
-            bf16x8_to_float((vb & 4) ? __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[2]) * g.ldx + c0)) : z, x2);
-            bf16x8_to_float((vb & 8) ? __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(oi[3]) * g.ldx + c0)) : z, x3);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float d10 = x1[e] - x0[e], d32 = x3[e] - x2[e];
-            const float top = fmaf(lw, d10, x0[e]), bot = fmaf(lw, d32, x2[e]);
-            const float dvh = bot - top;
-            gm = fmaf(gc[e], fmaf(lh, dvh, top), gm);
-            gh = fmaf(gc[e], dvh, gh);
-            gw = fmaf(gc[e], fmaf(lh, d32, hh * d10), gw);
-          }
-          if (dx) {
-            const float wq[4] = {hh * hw * m, hh * lw * m, lh * hw * m, lh * lw * m};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (!(vb & (1 << q)) || wq[q] == 0.f) continue;      // warp-uniform
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = wq[q] * gc[e];
-              if (DX_FP32) red_f32x8(static_cast<float*>(dx) + static_cast<long long>(oi[q]) * lddx + c0, v);
-              else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + static_cast<long long>(oi[q]) * lddx + c0, v);
-            }
-          }
-        }
-        part[3 * u] = gh * m;
-        part[3 * u + 1] = gw * m;
-        part[3 * u + 2] = gm;
-      }
-      const float tot = bfly9(part, lane);
-      const int j = lane & 15;
-      if (lane < 16 && j < 9) {
-        const int kk = t3 * 3 + j / 3, which = j % 3;
-        if (which == 0) doffset[p * lddo + 2 * kk] = tot;
-        else if (which == 1) doffset[p * lddo + 2 * kk + 1] = tot;
-        else if (dmask) dmask[p * lddm + kk] = tot;
-      }
-    }
-  }
-}
-
 static int check_geom(const char* who, int C, int dg, long long ldx, long long ldcol) {
   if (dg < 1 || C % dg || (C / dg) % 8 || (ldx % 8) || (ldcol % 8))
     return set_error("%s: need C/deformable_groups %% 8 == 0 and 16-byte aligned pitches (C=%d dg=%d)", who, C, dg);
@@ -477,16 +355,7 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
   const double bytes = px * 2.0 * taps * C + static_cast<double>(B) * H * W * (2.0 * C + (dx ? (dx_fp32 ? 4.0 : 2.0) * C : 0.0)) +
                        px * 4.0 * taps * (mask ? 3 : 2) * 2.0;
   const int th = timing_begin(TC_COL2IM, bytes, static_cast<cudaStream_t>(stream));
-  const bool fast9 = (kh * kw == 9) && deformable_groups == 1;
-  if (fast9 && dx_fp32)
-    dcn_col2im9_kernel<true><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
-        g, lddx, lddo, lddm);
-  else if (fast9)
-    dcn_col2im9_kernel<false><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
-        g, lddx, lddo, lddm);
-  else if (dx_fp32)
+  if (dx_fp32)
     dcn_col2im_kernel<true><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
         g, lddx, lddo, lddm);

@@ -10,6 +10,7 @@ levels on the device with no host synchronisation:
 Tensors between kernels are pixel-major (channels_last): bf16 feature maps, fp32 prediction maps.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -94,6 +95,17 @@ class PackedGT:
             self.vs.copy_(other.vs, non_blocking=True)
         if self.valid_hw is not None:
             self.valid_hw.copy_(other.valid_hw, non_blocking=True)
+
+
+TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
+_TOWER_STREAM = {}
+
+
+def _tower_stream(device):
+    key = str(device)
+    if key not in _TOWER_STREAM:
+        _TOWER_STREAM[key] = torch.cuda.Stream(device=device)
+    return _TOWER_STREAM[key]
 
 
 BRANCHES = {'bbox': ['bbox'], 'segm': ['segm'], 'pose_bbox': ['bbox', 'pose'], 'pose_kbox': ['pose']}
@@ -253,11 +265,12 @@ class LSHead(nn.Module):
             LSHead._SCALE_CACHE[key] = v
         return v
 
-    def forward_single1(self, x):
+    def forward_single1(self, x, with_cls=True):
         """lsnet_head.py:502-598 for one level: towers + init regression -> (cls_feat, {br: (feat, init_sp, dcn_off)})."""
-        cls_feat = x
-        for m in self.cls_convs:
-            cls_feat = m(cls_feat)
+        cls_feat = x if with_cls else None
+        if with_cls:
+            for m in self.cls_convs:
+                cls_feat = m(cls_feat)
         out = {}
         for br in BRANCHES[self.task]:
             feat = x
@@ -275,9 +288,33 @@ class LSHead(nn.Module):
             out[br] = (feat, sp, reg - self.dcn_base_offset)
         return cls_feat, out
 
+    def _towers_parallel(self, feats):
+        """forward_single1 for every level with the classification tower on a side stream: the two towers of a level
+        are independent chains, and the issue-bound gather / scatter / GroupNorm kernels of one overlap the tensor-bound
+        GEMMs of the other (autograd runs each backward node on its forward stream, so the backward overlaps too).
+        Inside the captured step this becomes two parallel branches of the CUDA graph."""
+        cur = torch.cuda.current_stream()
+        side = _tower_stream(feats[0].device)
+        side.wait_stream(cur)
+        cls_feats = []
+        with torch.cuda.stream(side):
+            for f in feats:
+                c = f
+                for m in self.cls_convs:
+                    c = m(c)
+                cls_feats.append(c)
+        outs = [self.forward_single1(f, with_cls=False)[1] for f in feats]
+        cur.wait_stream(side)
+        for c in cls_feats:
+            c.record_stream(cur)
+        return list(zip(cls_feats, outs))
+
     def forward(self, feats):
         L = len(feats)
-        lvl = [self.forward_single1(f) for f in feats]
+        if TOWER_STREAMS and feats[0].is_cuda:
+            lvl = self._towers_parallel(feats)
+        else:
+            lvl = [self.forward_single1(f) for f in feats]
         cls_feats = [c for c, _ in lvl]
         brs = BRANCHES[self.task]
         cls_driver = brs[-1]      # pts_cls_conv follows the pose offsets when both branches exist (:680-681)
