@@ -11,6 +11,7 @@
 // HBM-bound: algorithmic bytes per output pixel = 2C (x) + 4*3*taps (offset,mask) + 2*taps*C (columns).
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 #include "lsnet_internal.h"
 
@@ -298,10 +299,334 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Binned adjoint ("transposed gather") — the training default for deformable_groups == 1.
+//
+// The direct scatter above issues 4 vector REDs per (pixel, tap) and lane; REDG costs ~1.3 LSU cycles per lane, so it
+// is bound at ~1500 cycles per output pixel whatever the math costs.  Here a CTA owns a PH x PW patch of output pixels
+// and the window of the sampled map those pixels can reach with |offset| <= R:
+//   A   every (pixel, tap) derives its sampling geometry once (shared memory) and counts its non-zero corners per
+//       window cell; an exclusive scan turns the counts into a CSR of (column-row, weight) entries per cell;
+//   C   dOffset / dMask: one warp per pixel; per tap 4 dot products D_q = <dCol, x_q> over the channels, combined
+//       with the bilinear coefficients AFTER a 6-shuffle butterfly (get_coordinate_weight, ...kernel.cu:145-188);
+//   B   dX: one warp per window cell walks the cell's entries, accumulates its 8 channels per lane in fp32 registers
+//       and issues ONE vector RED per cell (cells overlap between neighbouring CTAs) instead of one per corner;
+//   F   corners outside the window (large offsets) fall back to the direct RED.
+// Same arithmetic as the reference col2im / col2im_coord kernels, different summation order.
+struct BinCfg {
+  int PH, PW, WH, WW, R, skip;
+};
+
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc = fmaf(__uint_as_float(pa[i] << 16), __uint_as_float(pb[i] << 16), acc);
+    acc = fmaf(__uint_as_float(pa[i] & 0xffff0000u), __uint_as_float(pb[i] & 0xffff0000u), acc);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void axpy8(float w, const uint4& a, float (&acc)[8]) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] = fmaf(w, __uint_as_float(pa[i] << 16), acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, __uint_as_float(pa[i] & 0xffff0000u), acc[2 * i + 1]);
+  }
+}
+
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_WARPS = BIN_THREADS / 32;
+constexpr int BU = 8;   // cell entries (independent 16-byte column loads) in flight per lane in phase B
+
+template <bool DX_FP32>
+__global__ void __launch_bounds__(BIN_THREADS, 2)
+dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* __restrict__ x,
+                         const float* __restrict__ offset, const float* __restrict__ mask, void* __restrict__ dx,
+                         float* __restrict__ doffset, float* __restrict__ dmask, const DcnGeom g, long long lddx,
+                         long long lddo, long long lddm, const BinCfg bc) {
+  extern __shared__ uint4 bin_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int taps = g.kh * g.kw;
+  const int npix = bc.PH * bc.PW, npt = npix * taps, ncell = bc.WH * bc.WW;
+  float4* geo = reinterpret_cast<float4*>(bin_smem);                 // {lh, lw, mask, bits}
+  uint2* ent = reinterpret_cast<uint2*>(geo + npt);                  // CSR payload: {column row, weight}
+  int* geo_hw = reinterpret_cast<int*>(ent + 4 * npt);               // (h0 << 16) | (w0 & 0xffff)
+  int* cnt = geo_hw + npt;                                           // [ncell + 1] -> CSR row starts
+  int* cur = cnt + ncell + 1;                                        // [ncell] fill cursors
+  int* wsum = cur + ncell;                                           // [BIN_WARPS + 1]
+  const int b = blockIdx.z;
+  const int h_base = blockIdx.y * bc.PH, w_base = blockIdx.x * bc.PW;
+  const int wh0 = static_cast<int>(floorf(__fmul_rn(static_cast<float>(h_base * g.sh - g.ph), g.scale_h))) - bc.R;
+  const int ww0 = static_cast<int>(floorf(__fmul_rn(static_cast<float>(w_base * g.sw - g.pw), g.scale_w))) - bc.R;
+  const bool want_dx = dx != nullptr;
+
+  for (int i = tid; i <= ncell; i += BIN_THREADS) cnt[i] = 0;
+  __syncthreads();
+  // ---- A: geometry + per-cell counts ----
+  for (int e = tid; e < npt; e += BIN_THREADS) {
+    const int pix = e / taps, tap = e - pix * taps;
+    const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
+    float lh = 0.f, lw = 0.f, m = 1.f;
+    int bits = 0, hw = 0;
+    if (ho < g.Ho && wo < g.Wo) {
+      const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
+      float h, w;
+      sample_pos(g, offset + p * g.ldo, 0, tap, ho, wo, &h, &w);
+      bits = 32;
+      if ((h > -1.f) && (w > -1.f) && (h < static_cast<float>(g.H)) && (w < static_cast<float>(g.W))) {
+        const float hf = floorf(h), wf = floorf(w);
+        const int h0 = static_cast<int>(hf), w0 = static_cast<int>(wf);
+        lh = h - hf; lw = w - wf;
+        if (mask) m = __ldg(mask + p * g.ldm + tap);
+        bits |= 16 | ((h0 >= 0 && w0 >= 0) ? 1 : 0) | ((h0 >= 0 && w0 + 1 <= g.W - 1) ? 2 : 0) |
+                ((h0 + 1 <= g.H - 1 && w0 >= 0) ? 4 : 0) | ((h0 + 1 <= g.H - 1 && w0 + 1 <= g.W - 1) ? 8 : 0);
+        hw = (h0 << 16) | (w0 & 0xffff);
+        if (want_dx) {
+          const float hh = 1.f - lh, hw_ = 1.f - lw;
+          const float wq[4] = {hh * hw_, hh * lw, lh * hw_, lh * lw};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (!((bits >> q) & 1) || wq[q] * m == 0.f) continue;
+            const int r = h0 + (q >> 1) - wh0, c = w0 + (q & 1) - ww0;
+            if (r >= 0 && r < bc.WH && c >= 0 && c < bc.WW) atomicAdd(&cnt[r * bc.WW + c], 1);
+            else bits |= 256 << q;
+          }
+        }
+      }
+    }
+    geo[e] = make_float4(lh, lw, m, __int_as_float(bits));
+    geo_hw[e] = hw;
+  }
+  __syncthreads();
+  if (want_dx) {
+    // ---- exclusive scan of the counts (block-wide) ----
+    const int per = (ncell + BIN_THREADS - 1) / BIN_THREADS;
+    const int lo = min(tid * per, ncell), hi = min(lo + per, ncell);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += cnt[i];
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = lane < BIN_WARPS ? wsum[lane] : 0, iv = v;
+#pragma unroll
+      for (int o = 1; o < BIN_WARPS; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += t;
+      }
+      if (lane < BIN_WARPS) wsum[lane] = iv - v;
+      if (lane == BIN_WARPS - 1) wsum[BIN_WARPS] = iv;
+    }
+    __syncthreads();
+    int base = wsum[warp] + incl - s;
+    for (int i = lo; i < hi; ++i) {
+      const int c = cnt[i];
+      cnt[i] = base; cur[i] = base;
+      base += c;
+    }
+    if (tid == 0) cnt[ncell] = wsum[BIN_WARPS];
+    __syncthreads();
+    // ---- A2: fill the CSR ----
+    for (int e = tid; e < npt; e += BIN_THREADS) {
+      const float4 gf = geo[e];
+      const int bits = __float_as_int(gf.w);
+      if (!(bits & 16)) continue;
+      const int pix = e / taps, tap = e - pix * taps;
+      const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
+      const int colrow = ((b * g.Ho + ho) * g.Wo + wo) * taps + tap;
+      const int hw = geo_hw[e];
+      const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
+      const float hh = 1.f - gf.x, hw_ = 1.f - gf.y;
+      const float wq[4] = {hh * hw_, hh * gf.y, gf.x * hw_, gf.x * gf.y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sc = wq[q] * gf.z;
+        if (!((bits >> q) & 1) || ((bits >> (8 + q)) & 1) || sc == 0.f) continue;
+        const int r = h0 + (q >> 1) - wh0, c = w0 + (q & 1) - ww0;
+        const int slot = atomicAdd(&cur[r * bc.WW + c], 1);
+        ent[slot] = make_uint2(static_cast<uint32_t>(colrow), __float_as_uint(sc));
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- C: dOffset / dMask, one warp per output pixel ----
+  // All 9 column loads of the pixel are issued up front (its 4.6 KB dCol row is the HBM stream of this kernel); the 27
+  // per-lane partials (gh, gw per tap, then gm per tap) are reduced together by ONE transposed butterfly (31 shuffles),
+  // which leaves value i in lane i == its position in the pixel's dOffset / dMask rows (coalesced stores).
+  for (int pix = warp; pix < npix && !(bc.skip & 1); pix += BIN_WARPS) {
+    const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
+    if (ho >= g.Ho || wo >= g.Wo) continue;
+    const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
+    const long long xb = static_cast<long long>(b) * g.H;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int cb = 0; cb < g.C; cb += 256) {
+      const int c0 = cb + lane * 8;
+      const bool act = c0 < g.C;
+      const __nv_bfloat16* src = gcol + p * g.ldcol + (act ? c0 : 0);
+      uint4 gc[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) gc[tap] = ld_stream(src + tap * g.C);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4 gf = geo[pix * 9 + tap];
+        const int bits = __float_as_int(gf.w);
+        if (!(bits & 16)) continue;
+        const int hw = geo_hw[pix * 9 + tap];
+        const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
+        const int ch0 = max(h0, 0), ch1 = min(h0 + 1, g.H - 1), cw0 = max(w0, 0), cw1 = min(w0 + 1, g.W - 1);
+        const __nv_bfloat16* xr0 = x + ((xb + ch0) * g.W) * g.ldx + (act ? c0 : 0);
+        const __nv_bfloat16* xr1 = x + ((xb + ch1) * g.W) * g.ldx + (act ? c0 : 0);
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 x0 = (bits & 1) ? __ldg(reinterpret_cast<const uint4*>(xr0 + cw0 * g.ldx)) : z4;
+        const uint4 x1 = (bits & 2) ? __ldg(reinterpret_cast<const uint4*>(xr0 + cw1 * g.ldx)) : z4;
+        const uint4 x2 = (bits & 4) ? __ldg(reinterpret_cast<const uint4*>(xr1 + cw0 * g.ldx)) : z4;
+        const uint4 x3 = (bits & 8) ? __ldg(reinterpret_cast<const uint4*>(xr1 + cw1 * g.ldx)) : z4;
+        if (!act) continue;
+        const float D0 = dot8(gc[tap], x0, 0.f), D1 = dot8(gc[tap], x1, 0.f);
+        const float D2 = dot8(gc[tap], x2, 0.f), D3 = dot8(gc[tap], x3, 0.f);
+        const float lh = gf.x, lw = gf.y, m = gf.z, hh = 1.f - lh, hw_ = 1.f - lw;
+        v[2 * tap] += m * (hw_ * (D2 - D0) + lw * (D3 - D1));
+        v[2 * tap + 1] += m * (hh * (D1 - D0) + lh * (D3 - D2));
+        v[18 + tap] += (hh * hw_) * D0 + (hh * lw) * D1 + (lh * hw_) * D2 + (lh * lw) * D3;
+      }
+    }
+#pragma unroll
+    for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+      const bool up = lane & o;
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        const float send = up ? v[i] : v[i + n / 2];
+        const float keep = up ? v[i + n / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    if (lane < 18) doffset[p * lddo + lane] = v[0];
+    else if (lane < 27 && dmask) dmask[p * lddm + lane - 18] = v[0];
+  }
+  if (!want_dx) return;
+
+  // ---- B: dX, one warp per window cell ----
+  for (int cell = warp; cell < ncell && !(bc.skip & 2); cell += BIN_WARPS) {
+    const int s = cnt[cell], n = cnt[cell + 1] - s;
+    if (n == 0) continue;
+    const int r = cell / bc.WW, c = cell - r * bc.WW;
+    const long long q = (static_cast<long long>(b) * g.H + (wh0 + r)) * g.W + (ww0 + c);
+    for (int cb = 0; cb < g.C; cb += 256) {
+      const int c0 = cb + lane * 8;
+      const bool act = c0 < g.C;
+      const __nv_bfloat16* src = gcol + (act ? c0 : 0);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int i = 0;
+      for (; i + BU <= n; i += BU) {
+        uint2 e[BU];
+        uint4 v[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) e[u] = ent[s + i + u];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(e[u].x) * g.C));
+#pragma unroll
+        for (int u = 0; u < BU; ++u) axpy8(__uint_as_float(e[u].y), v[u], acc);
+      }
+      for (; i < n; ++i) {
+        const uint2 e = ent[s + i];
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(e.x) * g.C));
+        axpy8(__uint_as_float(e.y), v, acc);
+      }
+      if (act) {
+        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + q * lddx + c0, acc);
+        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + q * lddx + c0, acc);
+      }
+    }
+  }
+
+  // ---- F: corners outside the window ----
+  for (int e = warp; e < npt; e += BIN_WARPS) {
+    const float4 gf = geo[e];
+    const int bits = __float_as_int(gf.w);
+    const int far = (bits >> 8) & 15;
+    if (!far) continue;
+    const int pix = e / taps, tap = e - pix * taps;
+    const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
+    const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
+    const int hw = geo_hw[e];
+    const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
+    const float hh = 1.f - gf.x, hw_ = 1.f - gf.y;
+    const float wq[4] = {hh * hw_, hh * gf.y, gf.x * hw_, gf.x * gf.y};
+    const __nv_bfloat16* src = gcol + p * g.ldcol + static_cast<long long>(tap) * g.C;
+    for (int c0 = lane * 8; c0 < g.C; c0 += 256) {
+      float gc[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(src + c0)), gc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!((far >> q) & 1)) continue;
+        const float sc = wq[q] * gf.z;
+        const long long qp = (static_cast<long long>(b) * g.H + (h0 + (q >> 1))) * g.W + (w0 + (q & 1));
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = sc * gc[t];
+        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + qp * lddx + c0, v);
+        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + qp * lddx + c0, v);
+      }
+    }
+  }
+}
+
 static int check_geom(const char* who, int C, int dg, long long ldx, long long ldcol) {
   if (dg < 1 || C % dg || (C / dg) % 8 || (ldx % 8) || (ldcol % 8))
     return set_error("%s: need C/deformable_groups %% 8 == 0 and 16-byte aligned pitches (C=%d dg=%d)", who, C, dg);
   return 0;
+}
+
+// Patch / window selection for the binned adjoint.  Returns false when the direct scatter must be used
+// (deformable groups, column pitch != taps*C, > 2^31 column rows, LSNET_COL2IM=direct, or a window that does not fit).
+static bool pick_binned(const DcnGeom& g, bool want_dx, BinCfg* bc, size_t* smem) {
+  static int mode = -1, max_smem = 0;
+  if (mode < 0) {
+    const char* e = getenv("LSNET_COL2IM");
+    mode = (e && !strcmp(e, "direct")) ? 0 : 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(dcn_col2im_binned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(dcn_col2im_binned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  }
+  const int taps = g.kh * g.kw;
+  if (!mode || g.dg != 1 || taps != 9 || g.ldcol != static_cast<long long>(taps) * g.C || g.scale_h <= 0.f || g.scale_w <= 0.f ||
+      static_cast<double>(g.B) * g.Ho * g.Wo * taps >= 2147483647.0 || g.H > 32767 || g.W > 32767)
+    return false;
+  static const int cand[3][2] = {{8, 16}, {8, 8}, {4, 8}};
+  const int R = 2;
+  static int first = -1;
+  if (first < 0) { const char* e = getenv("LSNET_BIN_PATCH"); first = e ? atoi(e) : 0; }
+  for (int i = first; i < 3; ++i) {
+    const int PH = cand[i][0], PW = cand[i][1];
+    const long long ctas = static_cast<long long>((g.Ho + PH - 1) / PH) * ((g.Wo + PW - 1) / PW) * g.B;
+    if (i < 2 && ctas < 2 * 148) continue;      // keep every SM busy: smaller patches on the small pyramid levels
+    const int WH = static_cast<int>(floorf(((PH - 1) * g.sh + (g.kh - 1) * g.dh) * g.scale_h)) + 3 + 2 * R;
+    const int WW = static_cast<int>(floorf(((PW - 1) * g.sw + (g.kw - 1) * g.dw) * g.scale_w)) + 3 + 2 * R;
+    const long long ncell = want_dx ? static_cast<long long>(WH) * WW : 1;
+    const long long npt = static_cast<long long>(PH) * PW * taps;
+    const long long bytes = npt * (16 + 32 + 4) + (2 * ncell + 1 + BIN_WARPS + 1) * 4 + 16;
+    if (bytes > 72 * 1024 || bytes > max_smem) continue;   // <= 72 KB keeps 3 CTAs per SM
+    static int skip = -1;
+    if (skip < 0) { const char* e = getenv("LSNET_BIN_SKIP"); skip = e ? atoi(e) : 0; }
+    *bc = BinCfg{PH, PW, want_dx ? WH : 1, want_dx ? WW : 1, R, skip};
+    *smem = static_cast<size_t>(bytes);
+    return true;
+  }
+  return false;
 }
 
 }  // namespace lsn
@@ -355,7 +680,19 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
   const double bytes = px * 2.0 * taps * C + static_cast<double>(B) * H * W * (2.0 * C + (dx ? (dx_fp32 ? 4.0 : 2.0) * C : 0.0)) +
                        px * 4.0 * taps * (mask ? 3 : 2) * 2.0;
   const int th = timing_begin(TC_COL2IM, bytes, static_cast<cudaStream_t>(stream));
-  if (dx_fp32)
+  BinCfg bc;
+  size_t bin_smem = 0;
+  if (pick_binned(g, dx != nullptr, &bc, &bin_smem)) {
+    dim3 bgrid((Wo + bc.PW - 1) / bc.PW, (Ho + bc.PH - 1) / bc.PH, B);
+    if (dx_fp32)
+      dcn_col2im_binned_kernel<true><<<bgrid, BIN_THREADS, bin_smem, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
+          dmask, g, lddx, lddo, lddm, bc);
+    else
+      dcn_col2im_binned_kernel<false><<<bgrid, BIN_THREADS, bin_smem, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
+          dmask, g, lddx, lddo, lddm, bc);
+  } else if (dx_fp32)
     dcn_col2im_kernel<true><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,
         g, lddx, lddo, lddm);

@@ -98,15 +98,20 @@ class PackedGT:
 
 
 TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
+# run pyramid levels 1.. (25 % of the pixels, launch-latency-bound kernels) on their own streams, beside level 0
+LEVEL_STREAMS = os.environ.get('LSNET_LEVEL_STREAMS', '0') == '1'   # measured: no gain (33.70 vs 33.63 ms)
 _TOWER_STREAM = {}
 
 
-def _tower_stream(device):
-    key = str(device)
+def _tower_stream(device, idx=0):
+    key = (str(device), idx)
     if key not in _TOWER_STREAM:
         _TOWER_STREAM[key] = torch.cuda.Stream(device=device)
     return _TOWER_STREAM[key]
 
+
+import contextlib
+_nullctx = contextlib.nullcontext
 
 BRANCHES = {'bbox': ['bbox'], 'segm': ['segm'], 'pose_bbox': ['bbox', 'pose'], 'pose_kbox': ['pose']}
 LOSS_KIND = {'bbox': 'bbox', 'segm': 'polygon', 'pose': 'keypoint'}
@@ -292,22 +297,71 @@ class LSHead(nn.Module):
         """forward_single1 for every level with the classification tower on a side stream: the two towers of a level
         are independent chains, and the issue-bound gather / scatter / GroupNorm kernels of one overlap the tensor-bound
         GEMMs of the other (autograd runs each backward node on its forward stream, so the backward overlaps too).
-        Inside the captured step this becomes two parallel branches of the CUDA graph."""
+        With LEVEL_STREAMS the small levels 1.. get their own pair of streams, so their short kernels run beside the
+        level-0 ones instead of after them.  Inside the captured step these become parallel branches of the CUDA graph."""
         cur = torch.cuda.current_stream()
-        side = _tower_stream(feats[0].device)
-        side.wait_stream(cur)
-        cls_feats = []
-        with torch.cuda.stream(side):
-            for f in feats:
-                c = f
-                for m in self.cls_convs:
-                    c = m(c)
-                cls_feats.append(c)
-        outs = [self.forward_single1(f, with_cls=False)[1] for f in feats]
-        cur.wait_stream(side)
-        for c in cls_feats:
-            c.record_stream(cur)
+        dev = feats[0].device
+        L = len(feats)
+        groups = [list(range(L))] if not (LEVEL_STREAMS and L > 1) else [[0], list(range(1, L))]
+        cls_feats, outs = [None] * L, [None] * L
+        used = []
+        for gi, lv in enumerate(groups):
+            s_cls = _tower_stream(dev, 2 * gi)
+            s_reg = cur if gi == 0 else _tower_stream(dev, 2 * gi + 1)
+            for st in (s_cls, s_reg):
+                if st is not cur:
+                    st.wait_stream(cur)
+                    used.append(st)
+            with torch.cuda.stream(s_cls):
+                for l in lv:
+                    c = feats[l]
+                    for m in self.cls_convs:
+                        c = m(c)
+                    cls_feats[l] = c
+            with torch.cuda.stream(s_reg):
+                for l in lv:
+                    outs[l] = self.forward_single1(feats[l], with_cls=False)[1]
+        for st in used:
+            cur.wait_stream(st)
+        for l in range(L):
+            cls_feats[l].record_stream(cur)
+            if l > 0 and len(groups) > 1:
+                for br in outs[l]:
+                    for t in outs[l][br]:
+                        t.record_stream(cur)
         return list(zip(cls_feats, outs))
+
+    def _refine_level(self, l, L, lvl, cls_feats, brs, cls_driver, outs):
+        """lsnet_head.py:600-755 for one level: the three pyramid DCNs per branch, fusion conv + GN, refine / cls heads."""
+        lvls = [l, l + 1, l + 2] if l == 0 else ([l, l - 1, l - 2] if l == L - 1 else [l, l - 1, l + 1])
+        bh, bw = cls_feats[l].shape[2:]
+        offs = {br: lvl[l][1][br][2] for br in brs}
+        raws = {br: [] for br in brs}
+        cls_raws = []
+        B_, pc = cls_feats[l].shape[0], self.point_feat_channels
+        bufs = {br: torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16) for br in brs}
+        cls_buf = torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16)
+        for j, lv in enumerate(lvls):
+            sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
+            sc = self._scale_vec(sh, sw, offs[brs[0]].device)
+            for br in brs:
+                # the reference scales views of the offset tensor in place, so the factors accumulate over the
+                # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
+                offs[br] = offs[br] * sc
+                raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw,
+                                                                      out_slice=(bufs[br], j * pc)))
+            cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw, out_slice=(cls_buf, j * pc)))
+        for br in brs:
+            t = getattr(self, f'{br}_af_dcn_conv')(self._join(bufs[br], raws[br]))
+            gn = getattr(self, f'{br}_GN')
+            t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
+                                    residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
+            t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
+            outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
+        t = ops.group_norm_nhwc(self.cls_af_dcn_conv(self._join(cls_buf, cls_raws)), self.cls_GN.num_groups,
+                                self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
+                                residual=self.cls_feat_conv(cls_feats[l]))
+        outs['cls'].append(self.pts_cls_out(t, out_fp32=True))
 
     def forward(self, feats):
         L = len(feats)
@@ -322,36 +376,25 @@ class LSHead(nn.Module):
         for br in brs:
             outs[br + '_init'] = [lvl[l][1][br][1] for l in range(L)]
             outs[br + '_refine'] = []
+        cur = torch.cuda.current_stream() if feats[0].is_cuda else None
+        side = None
+        if cur is not None and TOWER_STREAMS and LEVEL_STREAMS and L > 1:
+            side = _tower_stream(feats[0].device, 4)
+            side.wait_stream(cur)
+            for c, o in lvl:            # tower outputs are read by the refine stage of the neighbouring levels
+                c.record_stream(side)
+                for br in o:
+                    for t in o[br]:
+                        t.record_stream(side)
         for l in range(L):
-            lvls = [l, l + 1, l + 2] if l == 0 else ([l, l - 1, l - 2] if l == L - 1 else [l, l - 1, l + 1])
-            bh, bw = cls_feats[l].shape[2:]
-            offs = {br: lvl[l][1][br][2] for br in brs}
-            raws = {br: [] for br in brs}
-            cls_raws = []
-            B_, pc = cls_feats[l].shape[0], self.point_feat_channels
-            bufs = {br: torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16) for br in brs}
-            cls_buf = torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16)
-            for j, lv in enumerate(lvls):
-                sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
-                sc = self._scale_vec(sh, sw, offs[brs[0]].device)
-                for br in brs:
-                    # the reference scales views of the offset tensor in place, so the factors accumulate over the
-                    # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
-                    offs[br] = offs[br] * sc
-                    raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw,
-                                                                          out_slice=(bufs[br], j * pc)))
-                cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw, out_slice=(cls_buf, j * pc)))
-            for br in brs:
-                t = getattr(self, f'{br}_af_dcn_conv')(self._join(bufs[br], raws[br]))
-                gn = getattr(self, f'{br}_GN')
-                t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
-                                        residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
-                t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
-                outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
-            t = ops.group_norm_nhwc(self.cls_af_dcn_conv(self._join(cls_buf, cls_raws)), self.cls_GN.num_groups,
-                                    self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
-                                    residual=self.cls_feat_conv(cls_feats[l]))
-            outs['cls'].append(self.pts_cls_out(t, out_fp32=True))
+            with torch.cuda.stream(side if (side is not None and l > 0) else cur) if cur is not None else _nullctx():
+                self._refine_level(l, L, lvl, cls_feats, brs, cls_driver, outs)
+        if side is not None:
+            cur.wait_stream(side)
+            for k in outs:
+                for t in outs[k][1:]:
+                    if t is not None:
+                        t.record_stream(cur)
         none = [None] * L
         return (outs['cls'], outs.get('bbox_init', none), outs.get('bbox_refine', none), outs.get('segm_init', none),
                 outs.get('segm_refine', none), outs.get('pose_init', none), outs.get('pose_refine', none))

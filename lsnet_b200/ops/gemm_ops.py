@@ -69,9 +69,21 @@ def cached_pack(w, kind, fn):
     key = (id(w), kind)
     hit = _PACK_CACHE.get(key)
     if hit is not None and hit[0]() is w and hit[1] == w._version:
+        # Shared towers run their pyramid levels on different streams: a hit from another stream than the one that
+        # packed must wait for the packing kernels (inside a captured step this becomes a graph dependency).
+        if hit[3] is not None:
+            cur = torch.cuda.current_stream(w.device)
+            if cur != hit[4]:
+                cur.wait_event(hit[3])
+                hit[2].record_stream(cur)
         return hit[2]
     p = fn(w.detach())
-    _PACK_CACHE[key] = (weakref.ref(w), w._version, p)
+    ev = st = None
+    if w.is_cuda:
+        st = torch.cuda.current_stream(w.device)
+        ev = torch.cuda.Event()
+        ev.record(st)
+    _PACK_CACHE[key] = (weakref.ref(w), w._version, p, ev, st)
     if len(_PACK_CACHE) > 4096:        # dead entries of short-lived tensors
         for k in [k for k, v in _PACK_CACHE.items() if v[0]() is None]:
             del _PACK_CACHE[k]

@@ -13,7 +13,9 @@ from lsnet_b200.ops import gemm_ops as G
 dev = 'cuda'
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json'))) \
     if os.path.exists('MEASURED_PEAKS.json') else dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
-only = sys.argv[sys.argv.index('--ncu') + 1] if '--ncu' in sys.argv else None
+ncu_mode = '--ncu' in sys.argv
+only = sys.argv[sys.argv.index('--ncu') + 1] if ncu_mode else (
+    sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -21,7 +23,7 @@ def timeit(fn, n=10):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    if only:
+    if ncu_mode:
         return 0.0
     ts = []
     for _ in range(n):
@@ -50,7 +52,7 @@ rows = []
 
 
 def add(name, ms, work, unit):
-    if only:
+    if ncu_mode:
         return
     if unit == 'TFLOP/s':
         ach = work / (ms * 1e-3) / 1e12
@@ -91,6 +93,17 @@ if only in (None, 'col2im'):
     z = torch.zeros_like(off)
     ms = timeit(lambda: ops.dcn_col2im(gcol, x, z, mask, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1))
     add('dcn_col2im DCNv2 zero offsets (bench towers)', ms, P * (2.0 * 9 * C + 2.0 * C + 2.0 * C + 8 * 27), 'GB/s')
+if only in (None, 'col2im_pyr'):
+    # pyramid DCN adjoint on the level-0 grid: sampling level 1 (scale 1/2) and, on the level-1 grid, level 0 (scale 2)
+    gcol = torch.randn(P, 2304, generator=g).to(dev, torch.bfloat16)
+    x1 = torch.randn(B, C, 50, 84, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ms = timeit(lambda: ops.dcn_col2im(gcol, x1, off, None, H, W, 3, 3, (1, 1), (1, 1), (1, 1), (0.5, 0.5), 1))
+    add('dcn_col2im pyramid 100x168 <- 50x84 (s=0.5)', ms, P * (2.0 * 9 * C + 8 * 18) + B * 50 * 84 * 4.0 * C, 'GB/s')
+    P1 = B * 50 * 84
+    off1 = (torch.randn(B, 18, 50, 84, generator=g) * 1.5).to(dev).contiguous(memory_format=torch.channels_last)
+    gcol1 = torch.randn(P1, 2304, generator=g).to(dev, torch.bfloat16)
+    ms = timeit(lambda: ops.dcn_col2im(gcol1, x, off1, None, 50, 84, 3, 3, (1, 1), (1, 1), (1, 1), (2.0, 2.0), 1))
+    add('dcn_col2im pyramid 50x84 <- 100x168 (s=2)', ms, P1 * (2.0 * 9 * C + 8 * 18) + P * 4.0 * C, 'GB/s')
 if only in (None, 'gn'):
     wgt, bias = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     ms = timeit(lambda: ops.group_norm_nhwc(x, 32, wgt, bias, 1e-5, relu=True))
