@@ -318,44 +318,53 @@ struct BinCfg {
   int PH, PW, WH, WW, R, skip;
 };
 
-__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
-  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+// bf16x2 word -> (lo, hi) as a float2 register pair (one shift, one mask), the operand form of the packed fp32x2 FMA
+__device__ __forceinline__ float2 bf16x2_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// acc += <a, b> over 8 bf16 channels, accumulated pairwise with FFMA2 (sm_100 packed fp32x2; exact products)
+__device__ __forceinline__ float2 dot8(const float2 (&a)[4], const uint4& b, float2 acc) {
   const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc = fmaf(__uint_as_float(pa[i] << 16), __uint_as_float(pb[i] << 16), acc);
-    acc = fmaf(__uint_as_float(pa[i] & 0xffff0000u), __uint_as_float(pb[i] & 0xffff0000u), acc);
-  }
+  for (int i = 0; i < 4; ++i) acc = __ffma2_rn(a[i], bf16x2_f2(pb[i]), acc);
   return acc;
 }
 
-__device__ __forceinline__ void axpy8(float w, const uint4& a, float (&acc)[8]) {
+__device__ __forceinline__ void axpy8(float w, const uint4& a, float2 (&acc)[4]) {
   const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const float2 w2 = make_float2(w, w);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    acc[2 * i] = fmaf(w, __uint_as_float(pa[i] << 16), acc[2 * i]);
-    acc[2 * i + 1] = fmaf(w, __uint_as_float(pa[i] & 0xffff0000u), acc[2 * i + 1]);
-  }
+  for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(w2, bf16x2_f2(pa[i]), acc[i]);
 }
 
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_WARPS = BIN_THREADS / 32;
-constexpr int BU = 8;   // cell entries (independent 16-byte column loads) in flight per lane in phase B
+constexpr int BIN_PT_BYTES = 5 * 16 + 4 * 8;   // shared memory per (pixel, tap): 5 records + 4 CSR entries
 
-template <bool DX_FP32>
-__global__ void __launch_bounds__(BIN_THREADS, 2)
+// Per (pixel, tap) records in shared memory (all warp-uniform when read, i.e. broadcast LDS.128):
+//   ci  int4   pixel indices of the 4 corners, clamped into the map (always loadable; invalid corners get weight 0)
+//   ah  float4 d(sample)/dh coefficients per corner  = mask * (-hw, -lw, +hw, +lw), 0 for invalid corners / outside
+//   aw  float4 d(sample)/dw coefficients per corner  = mask * (-hh, +hh, -lh, +lh)
+//   am  float4 bilinear weights per corner (dMask coefficients; times mask = the dX scatter weights)
+//   gx  int4   {h0 << 16 | w0, validity / far bits, mask as float bits, 0}
+template <bool DX_FP32, int MINB, int BU>
+__global__ void __launch_bounds__(BIN_THREADS, MINB)
 dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* __restrict__ x,
                          const float* __restrict__ offset, const float* __restrict__ mask, void* __restrict__ dx,
                          float* __restrict__ doffset, float* __restrict__ dmask, const DcnGeom g, long long lddx,
                          long long lddo, long long lddm, const BinCfg bc) {
   extern __shared__ uint4 bin_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int taps = g.kh * g.kw;
+  constexpr int taps = 9;
   const int npix = bc.PH * bc.PW, npt = npix * taps, ncell = bc.WH * bc.WW;
-  float4* geo = reinterpret_cast<float4*>(bin_smem);                 // {lh, lw, mask, bits}
-  uint2* ent = reinterpret_cast<uint2*>(geo + npt);                  // CSR payload: {column row, weight}
-  int* geo_hw = reinterpret_cast<int*>(ent + 4 * npt);               // (h0 << 16) | (w0 & 0xffff)
-  int* cnt = geo_hw + npt;                                           // [ncell + 1] -> CSR row starts
+  int4* ci = reinterpret_cast<int4*>(bin_smem);
+  float4* ah = reinterpret_cast<float4*>(ci + npt);
+  float4* aw = ah + npt;
+  float4* am = aw + npt;
+  int4* gx = reinterpret_cast<int4*>(am + npt);
+  uint2* ent = reinterpret_cast<uint2*>(gx + npt);                   // CSR payload: {column row, weight}
+  int* cnt = reinterpret_cast<int*>(ent + 4 * npt);                  // [ncell + 1] -> CSR row starts
   int* cur = cnt + ncell + 1;                                        // [ncell] fill cursors
   int* wsum = cur + ncell;                                           // [BIN_WARPS + 1]
   const int b = blockIdx.z;
@@ -370,7 +379,9 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
   for (int e = tid; e < npt; e += BIN_THREADS) {
     const int pix = e / taps, tap = e - pix * taps;
     const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
-    float lh = 0.f, lw = 0.f, m = 1.f;
+    float4 rh = make_float4(0.f, 0.f, 0.f, 0.f), rw = rh, rm = rh;
+    int4 rc = make_int4(0, 0, 0, 0);
+    float m = 1.f;
     int bits = 0, hw = 0;
     if (ho < g.Ho && wo < g.Wo) {
       const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
@@ -380,17 +391,24 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
       if ((h > -1.f) && (w > -1.f) && (h < static_cast<float>(g.H)) && (w < static_cast<float>(g.W))) {
         const float hf = floorf(h), wf = floorf(w);
         const int h0 = static_cast<int>(hf), w0 = static_cast<int>(wf);
-        lh = h - hf; lw = w - wf;
+        const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw_ = 1.f - lw;
         if (mask) m = __ldg(mask + p * g.ldm + tap);
-        bits |= 16 | ((h0 >= 0 && w0 >= 0) ? 1 : 0) | ((h0 >= 0 && w0 + 1 <= g.W - 1) ? 2 : 0) |
-                ((h0 + 1 <= g.H - 1 && w0 >= 0) ? 4 : 0) | ((h0 + 1 <= g.H - 1 && w0 + 1 <= g.W - 1) ? 8 : 0);
+        const bool v0 = h0 >= 0 && w0 >= 0, v1 = h0 >= 0 && w0 + 1 <= g.W - 1;
+        const bool v2 = h0 + 1 <= g.H - 1 && w0 >= 0, v3 = h0 + 1 <= g.H - 1 && w0 + 1 <= g.W - 1;
+        bits |= 16 | (v0 ? 1 : 0) | (v1 ? 2 : 0) | (v2 ? 4 : 0) | (v3 ? 8 : 0);
         hw = (h0 << 16) | (w0 & 0xffff);
+        const int ch0 = max(h0, 0), ch1 = min(h0 + 1, g.H - 1), cw0 = max(w0, 0), cw1 = min(w0 + 1, g.W - 1);
+        const int r0 = (b * g.H + ch0) * g.W, r1 = (b * g.H + ch1) * g.W;
+        rc = make_int4(r0 + cw0, r0 + cw1, r1 + cw0, r1 + cw1);
+        // get_coordinate_weight (...kernel.cu:145-188): out-of-range corners dropped
+        rh = make_float4(v0 ? -m * hw_ : 0.f, v1 ? -m * lw : 0.f, v2 ? m * hw_ : 0.f, v3 ? m * lw : 0.f);
+        rw = make_float4(v0 ? -m * hh : 0.f, v1 ? m * hh : 0.f, v2 ? -m * lh : 0.f, v3 ? m * lh : 0.f);
+        rm = make_float4(v0 ? hh * hw_ : 0.f, v1 ? hh * lw : 0.f, v2 ? lh * hw_ : 0.f, v3 ? lh * lw : 0.f);
         if (want_dx) {
-          const float hh = 1.f - lh, hw_ = 1.f - lw;
-          const float wq[4] = {hh * hw_, hh * lw, lh * hw_, lh * lw};
+          const float wq[4] = {rm.x, rm.y, rm.z, rm.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (!((bits >> q) & 1) || wq[q] * m == 0.f) continue;
+            if (wq[q] * m == 0.f) continue;
             const int r = h0 + (q >> 1) - wh0, c = w0 + (q & 1) - ww0;
             if (r >= 0 && r < bc.WH && c >= 0 && c < bc.WW) atomicAdd(&cnt[r * bc.WW + c], 1);
             else bits |= 256 << q;
@@ -398,8 +416,8 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
         }
       }
     }
-    geo[e] = make_float4(lh, lw, m, __int_as_float(bits));
-    geo_hw[e] = hw;
+    ci[e] = rc; ah[e] = rh; aw[e] = rw; am[e] = rm;
+    gx[e] = make_int4(hw, bits, __float_as_int(m), 0);
   }
   __syncthreads();
   if (want_dx) {
@@ -437,20 +455,20 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
     __syncthreads();
     // ---- A2: fill the CSR ----
     for (int e = tid; e < npt; e += BIN_THREADS) {
-      const float4 gf = geo[e];
-      const int bits = __float_as_int(gf.w);
+      const int4 gg = gx[e];
+      const int bits = gg.y;
       if (!(bits & 16)) continue;
       const int pix = e / taps, tap = e - pix * taps;
       const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
       const int colrow = ((b * g.Ho + ho) * g.Wo + wo) * taps + tap;
-      const int hw = geo_hw[e];
-      const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
-      const float hh = 1.f - gf.x, hw_ = 1.f - gf.y;
-      const float wq[4] = {hh * hw_, hh * gf.y, gf.x * hw_, gf.x * gf.y};
+      const int h0 = gg.x >> 16, w0 = static_cast<int>(static_cast<short>(gg.x & 0xffff));
+      const float4 wm = am[e];
+      const float m = __int_as_float(gg.z);
+      const float wq[4] = {wm.x, wm.y, wm.z, wm.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float sc = wq[q] * gf.z;
-        if (!((bits >> q) & 1) || ((bits >> (8 + q)) & 1) || sc == 0.f) continue;
+        const float sc = wq[q] * m;
+        if (((bits >> (8 + q)) & 1) || sc == 0.f) continue;
         const int r = h0 + (q >> 1) - wh0, c = w0 + (q & 1) - ww0;
         const int slot = atomicAdd(&cur[r * bc.WW + c], 1);
         ent[slot] = make_uint2(static_cast<uint32_t>(colrow), __float_as_uint(sc));
@@ -460,14 +478,14 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
   }
 
   // ---- C: dOffset / dMask, one warp per output pixel ----
-  // All 9 column loads of the pixel are issued up front (its 4.6 KB dCol row is the HBM stream of this kernel); the 27
-  // per-lane partials (gh, gw per tap, then gm per tap) are reduced together by ONE transposed butterfly (31 shuffles),
-  // which leaves value i in lane i == its position in the pixel's dOffset / dMask rows (coalesced stores).
+  // Branch-free tap loop: 4 dot products <dCol, x_corner> per tap (packed fp32x2 FMAs), then the three linear
+  // combinations with the warp-uniform coefficient records.  The 27 per-lane partials (gh, gw per tap, then gm per tap)
+  // are reduced together by ONE transposed butterfly (31 shuffles), which leaves value i in lane i == its position in
+  // the pixel's dOffset / dMask rows (coalesced stores).
   for (int pix = warp; pix < npix && !(bc.skip & 1); pix += BIN_WARPS) {
     const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
     if (ho >= g.Ho || wo >= g.Wo) continue;
     const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
-    const long long xb = static_cast<long long>(b) * g.H;
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -475,31 +493,25 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
       const int c0 = cb + lane * 8;
       const bool act = c0 < g.C;
       const __nv_bfloat16* src = gcol + p * g.ldcol + (act ? c0 : 0);
-      uint4 gc[9];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) gc[tap] = ld_stream(src + tap * g.C);
+      const char* xc = reinterpret_cast<const char*>(x + (act ? c0 : 0));
+      const int ldxb = static_cast<int>(g.ldx) * 2;     // pixel pitch in bytes (checked < 2^31 on the host)
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float4 gf = geo[pix * 9 + tap];
-        const int bits = __float_as_int(gf.w);
-        if (!(bits & 16)) continue;
-        const int hw = geo_hw[pix * 9 + tap];
-        const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
-        const int ch0 = max(h0, 0), ch1 = min(h0 + 1, g.H - 1), cw0 = max(w0, 0), cw1 = min(w0 + 1, g.W - 1);
-        const __nv_bfloat16* xr0 = x + ((xb + ch0) * g.W) * g.ldx + (act ? c0 : 0);
-        const __nv_bfloat16* xr1 = x + ((xb + ch1) * g.W) * g.ldx + (act ? c0 : 0);
-        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-        const uint4 x0 = (bits & 1) ? __ldg(reinterpret_cast<const uint4*>(xr0 + cw0 * g.ldx)) : z4;
-        const uint4 x1 = (bits & 2) ? __ldg(reinterpret_cast<const uint4*>(xr0 + cw1 * g.ldx)) : z4;
-        const uint4 x2 = (bits & 4) ? __ldg(reinterpret_cast<const uint4*>(xr1 + cw0 * g.ldx)) : z4;
-        const uint4 x3 = (bits & 8) ? __ldg(reinterpret_cast<const uint4*>(xr1 + cw1 * g.ldx)) : z4;
-        if (!act) continue;
-        const float D0 = dot8(gc[tap], x0, 0.f), D1 = dot8(gc[tap], x1, 0.f);
-        const float D2 = dot8(gc[tap], x2, 0.f), D3 = dot8(gc[tap], x3, 0.f);
-        const float lh = gf.x, lw = gf.y, m = gf.z, hh = 1.f - lh, hw_ = 1.f - lw;
-        v[2 * tap] += m * (hw_ * (D2 - D0) + lw * (D3 - D1));
-        v[2 * tap + 1] += m * (hh * (D1 - D0) + lh * (D3 - D2));
-        v[18 + tap] += (hh * hw_) * D0 + (hh * lw) * D1 + (lh * hw_) * D2 + (lh * lw) * D3;
+        const int4 cq = ci[pix * 9 + tap];
+        const uint4 gc = ld_stream(src + tap * g.C);
+        const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.x) * ldxb));
+        const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.y) * ldxb));
+        const uint4 x2 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.z) * ldxb));
+        const uint4 x3 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.w) * ldxb));
+        const float2 ga[4] = {bf16x2_f2(gc.x), bf16x2_f2(gc.y), bf16x2_f2(gc.z), bf16x2_f2(gc.w)};
+        const float2 zz = make_float2(0.f, 0.f);
+        const float2 d0 = dot8(ga, x0, zz), d1 = dot8(ga, x1, zz), d2 = dot8(ga, x2, zz), d3 = dot8(ga, x3, zz);
+        const float D0 = act ? d0.x + d0.y : 0.f, D1 = act ? d1.x + d1.y : 0.f;
+        const float D2 = act ? d2.x + d2.y : 0.f, D3 = act ? d3.x + d3.y : 0.f;
+        const float4 kh = ah[pix * 9 + tap], kw = aw[pix * 9 + tap], km = am[pix * 9 + tap];
+        v[2 * tap] += kh.x * D0 + kh.y * D1 + kh.z * D2 + kh.w * D3;
+        v[2 * tap + 1] += kw.x * D0 + kw.y * D1 + kw.z * D2 + kw.w * D3;
+        v[18 + tap] += km.x * D0 + km.y * D1 + km.z * D2 + km.w * D3;
       }
     }
 #pragma unroll
@@ -518,16 +530,17 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
   if (!want_dx) return;
 
   // ---- B: dX, one warp per window cell ----
+  const float inv_ww = 1.f / static_cast<float>(bc.WW);
   for (int cell = warp; cell < ncell && !(bc.skip & 2); cell += BIN_WARPS) {
     const int s = cnt[cell], n = cnt[cell + 1] - s;
     if (n == 0) continue;
-    const int r = cell / bc.WW, c = cell - r * bc.WW;
-    const long long q = (static_cast<long long>(b) * g.H + (wh0 + r)) * g.W + (ww0 + c);
+    const int r = __float2int_rz((static_cast<float>(cell) + 0.5f) * inv_ww), c = cell - r * bc.WW;
+    const long long q = static_cast<long long>((b * g.H + (wh0 + r)) * g.W + (ww0 + c));
     for (int cb = 0; cb < g.C; cb += 256) {
       const int c0 = cb + lane * 8;
       const bool act = c0 < g.C;
       const __nv_bfloat16* src = gcol + (act ? c0 : 0);
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float2 acc[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       int i = 0;
       for (; i + BU <= n; i += BU) {
         uint2 e[BU];
@@ -545,25 +558,26 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
         axpy8(__uint_as_float(e.y), v, acc);
       }
       if (act) {
-        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + q * lddx + c0, acc);
-        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + q * lddx + c0, acc);
+        const float av[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y};
+        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + q * lddx + c0, av);
+        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + q * lddx + c0, av);
       }
     }
   }
 
   // ---- F: corners outside the window ----
   for (int e = warp; e < npt; e += BIN_WARPS) {
-    const float4 gf = geo[e];
-    const int bits = __float_as_int(gf.w);
-    const int far = (bits >> 8) & 15;
+    const int4 gg = gx[e];
+    const int far = (gg.y >> 8) & 15;
     if (!far) continue;
     const int pix = e / taps, tap = e - pix * taps;
     const int ho = h_base + pix / bc.PW, wo = w_base + pix % bc.PW;
     const long long p = (static_cast<long long>(b) * g.Ho + ho) * g.Wo + wo;
-    const int hw = geo_hw[e];
-    const int h0 = hw >> 16, w0 = static_cast<int>(static_cast<short>(hw & 0xffff));
-    const float hh = 1.f - gf.x, hw_ = 1.f - gf.y;
-    const float wq[4] = {hh * hw_, hh * gf.y, gf.x * hw_, gf.x * gf.y};
+    const int4 cq = ci[e];
+    const int qi[4] = {cq.x, cq.y, cq.z, cq.w};
+    const float4 wm = am[e];
+    const float wq[4] = {wm.x, wm.y, wm.z, wm.w};
+    const float m = __int_as_float(gg.z);
     const __nv_bfloat16* src = gcol + p * g.ldcol + static_cast<long long>(tap) * g.C;
     for (int c0 = lane * 8; c0 < g.C; c0 += 256) {
       float gc[8];
@@ -571,13 +585,12 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (!((far >> q) & 1)) continue;
-        const float sc = wq[q] * gf.z;
-        const long long qp = (static_cast<long long>(b) * g.H + (h0 + (q >> 1))) * g.W + (w0 + (q & 1));
+        const float sc = wq[q] * m;
         float v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) v[t] = sc * gc[t];
-        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + qp * lddx + c0, v);
-        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + qp * lddx + c0, v);
+        if (DX_FP32) red_f32x8(static_cast<float*>(dx) + static_cast<long long>(qi[q]) * lddx + c0, v);
+        else red_bf16x8(static_cast<__nv_bfloat16*>(dx) + static_cast<long long>(qi[q]) * lddx + c0, v);
       }
     }
   }
@@ -599,26 +612,32 @@ static bool pick_binned(const DcnGeom& g, bool want_dx, BinCfg* bc, size_t* smem
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(dcn_col2im_binned_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(dcn_col2im_binned_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+#define LSN_BIN_ATTR(MB, UN)                                                                                          \
+  cudaFuncSetAttribute(dcn_col2im_binned_kernel<true, MB, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); \
+  cudaFuncSetAttribute(dcn_col2im_binned_kernel<false, MB, UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+    LSN_BIN_ATTR(2, 8); LSN_BIN_ATTR(3, 8); LSN_BIN_ATTR(3, 4); LSN_BIN_ATTR(4, 4); LSN_BIN_ATTR(4, 8); LSN_BIN_ATTR(5, 4);
   }
   const int taps = g.kh * g.kw;
   if (!mode || g.dg != 1 || taps != 9 || g.ldcol != static_cast<long long>(taps) * g.C || g.scale_h <= 0.f || g.scale_w <= 0.f ||
-      static_cast<double>(g.B) * g.Ho * g.Wo * taps >= 2147483647.0 || g.H > 32767 || g.W > 32767)
+      static_cast<double>(g.B) * g.Ho * g.Wo * taps >= 2147483647.0 || g.H > 32767 || g.W > 32767 ||
+      g.ldx * 2 > 2147483647LL || static_cast<double>(g.B) * g.H * g.W >= 2147483647.0)
     return false;
-  static const int cand[3][2] = {{8, 16}, {8, 8}, {4, 8}};
+  // Patch candidates, largest first.  4x8 measured fastest on the large levels (8x16 / 8x8: LSNET_BIN_PATCH=0/1); the
+  // small pyramid levels take smaller patches so that the grid still covers the 148 SMs (their cost is the latency of
+  // one CTA's serial phases, which scales with the patch size).
+  static const int cand[6][2] = {{8, 16}, {8, 8}, {4, 8}, {2, 8}, {2, 4}, {1, 4}};
   const int R = 2;
   static int first = -1;
-  if (first < 0) { const char* e = getenv("LSNET_BIN_PATCH"); first = e ? atoi(e) : 0; }
-  for (int i = first; i < 3; ++i) {
+  if (first < 0) { const char* e = getenv("LSNET_BIN_PATCH"); first = e ? atoi(e) : 2; }
+  for (int i = first; i < 6; ++i) {
     const int PH = cand[i][0], PW = cand[i][1];
     const long long ctas = static_cast<long long>((g.Ho + PH - 1) / PH) * ((g.Wo + PW - 1) / PW) * g.B;
-    if (i < 2 && ctas < 2 * 148) continue;      // keep every SM busy: smaller patches on the small pyramid levels
+    if (i < 5 && ctas < 148) continue;
     const int WH = static_cast<int>(floorf(((PH - 1) * g.sh + (g.kh - 1) * g.dh) * g.scale_h)) + 3 + 2 * R;
     const int WW = static_cast<int>(floorf(((PW - 1) * g.sw + (g.kw - 1) * g.dw) * g.scale_w)) + 3 + 2 * R;
     const long long ncell = want_dx ? static_cast<long long>(WH) * WW : 1;
     const long long npt = static_cast<long long>(PH) * PW * taps;
-    const long long bytes = npt * (16 + 32 + 4) + (2 * ncell + 1 + BIN_WARPS + 1) * 4 + 16;
+    const long long bytes = npt * BIN_PT_BYTES + (2 * ncell + 1 + BIN_WARPS + 1) * 4 + 16;
     if (bytes > 72 * 1024 || bytes > max_smem) continue;   // <= 72 KB keeps 3 CTAs per SM
     static int skip = -1;
     if (skip < 0) { const char* e = getenv("LSNET_BIN_SKIP"); skip = e ? atoi(e) : 0; }
@@ -684,14 +703,18 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
   size_t bin_smem = 0;
   if (pick_binned(g, dx != nullptr, &bc, &bin_smem)) {
     dim3 bgrid((Wo + bc.PW - 1) / bc.PW, (Ho + bc.PH - 1) / bc.PH, B);
-    if (dx_fp32)
-      dcn_col2im_binned_kernel<true><<<bgrid, BIN_THREADS, bin_smem, static_cast<cudaStream_t>(stream)>>>(
-          static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
-          dmask, g, lddx, lddo, lddm, bc);
-    else
-      dcn_col2im_binned_kernel<false><<<bgrid, BIN_THREADS, bin_smem, static_cast<cudaStream_t>(stream)>>>(
-          static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset,
-          dmask, g, lddx, lddo, lddm, bc);
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("LSNET_BIN_VARIANT"); variant = e ? atoi(e) : 44; }
+#define LSN_BIN_LAUNCH(F32, MB, UN)                                                                                   \
+  dcn_col2im_binned_kernel<F32, MB, UN><<<bgrid, BIN_THREADS, bin_smem, static_cast<cudaStream_t>(stream)>>>(        \
+      static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask, g, \
+      lddx, lddo, lddm, bc)
+#define LSN_BIN_VARIANT(MB, UN)                                        \
+  if (variant == MB * 10 + UN) {                                       \
+    if (dx_fp32) LSN_BIN_LAUNCH(true, MB, UN); else LSN_BIN_LAUNCH(false, MB, UN); \
+  }
+    LSN_BIN_VARIANT(2, 8) else LSN_BIN_VARIANT(3, 8) else LSN_BIN_VARIANT(3, 4) else LSN_BIN_VARIANT(4, 4)
+    else LSN_BIN_VARIANT(4, 8) else LSN_BIN_VARIANT(5, 4) else return set_error("lsnet_dcn_col2im_bf16: unknown LSNET_BIN_VARIANT");
   } else if (dx_fp32)
     dcn_col2im_kernel<true><<<grid, GATHER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(gcol), static_cast<const __nv_bfloat16*>(x), offset, mask, dx, doffset, dmask,

@@ -7,7 +7,11 @@ backward : dCol = dY x W  (lsnet_gemm_bf16) -> scatter to dX / reduce to dOffset
            dW = dY^T x columns (lsnet_gemm_tn_bf16, MN-major split-K); the forward's column matrix is kept
            (HBM is plentiful on B200) instead of being re-gathered as the reference does
            (deform_conv_cuda.cpp:770-773).
-groups == 1 only (all LSHead sites); the grouped backbone sites (X-101, groups=64) are SURVEY §8 "next".
+groups > 1 (the X-101 backbone sites: groups=64, widths 512/1024/2048): v1 runs the SAME kernels on the block-diagonal
+expansion of the grouped weight (dense [Cout, taps*Cin] with zeros outside each group's channel block) and takes the
+block diagonal of the dense weight gradient.  That spends groups x redundant tensor-core FLOPs (0.3 ms per layer at
+~1 PFLOP/s) instead of a dedicated HBM-bound grouped kernel — SURVEY §8 "next" — but is exact: the extra products are
+all multiplications by zero.
 """
 import torch
 from torch.autograd import Function
@@ -73,7 +77,7 @@ def _out_hw(H, W, kh, kw, stride, pad, dil):
             (W + 2 * pad[1] - (dil[1] * (kw - 1) + 1)) // stride[1] + 1)
 
 
-OVERLAP_WGRAD = os.environ.get('LSNET_OVERLAP_WGRAD', '1') == '1'
+OVERLAP_WGRAD = os.environ.get('LSNET_OVERLAP_WGRAD', '0') == '1'   # measured with the binned adjoint: 34.5 ms with, 32.4 ms without
 _SIDE = {}
 
 
@@ -84,14 +88,26 @@ def _side_stream(device):
     return _SIDE[key]
 
 
+def _expand_groups(w, groups):
+    """(Cout, Cin/groups, kh, kw) grouped weight -> dense (Cout, Cin, kh, kw), zero outside each group's input block."""
+    if groups == 1:
+        return w
+    co, cig, kh, kw = w.shape
+    idx = torch.arange(groups, device=w.device)
+    d = w.new_zeros(groups, co // groups, groups, cig, kh, kw)
+    d[idx, :, idx] = w.view(groups, co // groups, cig, kh, kw)
+    return d.view(co, groups * cig, kh, kw)
+
+
 class _DCN(Function):
 
     @staticmethod
     def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
                 out_slice=None):
-        if groups != 1:
-            raise NotImplementedError('lsnet_b200 DCN: groups > 1 (X-101 backbone sites) is not built yet')
-        co, ci, kh, kw = weight.shape
+        co, cig, kh, kw = weight.shape
+        ci = cig * groups
+        if co % groups:
+            raise ValueError(f'out_channels {co} is not divisible by groups {groups}')
         x = G.as_nhwc(x, torch.bfloat16)
         B, _, H, W = x.shape
         src = offset if out_from_offset else x
@@ -103,16 +119,16 @@ class _DCN(Function):
         npad = (co + 15) // 16 * 16
 
         def pack_fwd(t):
-            p = t.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
+            p = _expand_groups(t, groups).permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
             if npad != co:
                 p = torch.cat([p, p.new_zeros(npad - co, p.shape[1])], 0)
             return p.contiguous()
-        wp = G.cached_pack(weight, 'dcn_fwd', pack_fwd)
+        wp = G.cached_pack(weight, 'dcn_fwd%d' % groups, pack_fwd)
         b = None
         if bias is not None:
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
         ctx.save_for_backward(x, offset, mask, weight, col)
-        ctx.cfg, ctx.has_bias = cfg, bias is not None
+        ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
         if out_slice is not None:
             # write straight into channels [c0, c0+co) of a wider pixel-major buffer (replaces a later torch.cat)
             buf, c0 = out_slice
@@ -128,8 +144,17 @@ class _DCN(Function):
     def backward(ctx, gy):
         x, offset, mask, weight, col = ctx.saved_tensors
         Ho, Wo, kh, kw = ctx.cfg[:4]
-        co, ci = weight.shape[:2]
+        groups = ctx.groups
+        co, ci = weight.shape[0], weight.shape[1] * groups
         B = x.shape[0]
+
+        def unpack_dw(dw):       # dense [cop, taps*ci] fp32 -> (co, ci/groups, kh, kw): block diagonal when grouped
+            d = dw[:co].view(co, kh, kw, ci)
+            if groups > 1:
+                idx = torch.arange(groups, device=d.device)
+                d = d.view(groups, co // groups, kh, kw, groups, ci // groups)[idx, :, :, :, idx]
+                d = d.reshape(co, kh, kw, ci // groups)
+            return d.permute(0, 3, 1, 2).to(weight.dtype)
         gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4])
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
@@ -143,16 +168,15 @@ class _DCN(Function):
             side = _side_stream(x.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                dw = G.gemm_tn(gy2, col)
-                gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
+                gw = unpack_dw(G.gemm_tn(gy2, col))
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
             # B operand [N = taps*ci, K = co]: W^T, K-major
             def pack_bwd(t):
-                p = t.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
+                p = _expand_groups(t, groups).permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
                 if cop != co:
                     p = torch.cat([p, p.new_zeros(p.shape[0], cop - co)], 1)
                 return p.contiguous()
-            wt = G.cached_pack(weight, 'dcn_bwd%d' % cop, pack_bwd)
+            wt = G.cached_pack(weight, 'dcn_bwd%d_%d' % (cop, groups), pack_bwd)
             gcol = G.gemm(gy2, wt, None, False, torch.bfloat16)
             gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
                                          need_dx=ctx.needs_input_grad[0])
@@ -161,8 +185,7 @@ class _DCN(Function):
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif ctx.needs_input_grad[3]:
-            dw = G.gemm_tn(gy2, col)                                   # [cop, taps*ci] fp32
-            gw = dw[:co].view(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
+            gw = unpack_dw(G.gemm_tn(gy2, col))                        # [cop, taps*ci] fp32
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
         return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None

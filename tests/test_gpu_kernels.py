@@ -150,6 +150,32 @@ def test_dcn_forward_backward_vs_oracle(variant, dx_fp32):
     dcn_mod.DX_FP32 = False
 
 
+@pytest.mark.parametrize('groups,stride', [(4, 1), (8, 2)])
+def test_dcn_grouped_vs_oracle(groups, stride):
+    """DCNv2 with conv groups > 1 (the X-101-64x4d backbone sites: groups=64, stride 2 in the first block of a stage,
+    deform_conv.py:488-534 called from resnext.py:114-118) against the grouped oracle."""
+    ops = _ops()
+    B, C, Co, H, W = 2, 64, 64, 12, 14
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    g = torch.Generator().manual_seed(77 + groups)
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    off = torch.randn(B, 18, Ho, Wo, generator=g) * 1.5
+    mask = torch.rand(B, 9, Ho, Wo, generator=g)
+    w = _bf(torch.randn(Co, C // groups, 3, 3, generator=g) / (C // groups * 9) ** 0.5)
+    gy = _bf(torch.randn(B, Co, Ho, Wo, generator=g))
+    ins_r = [t.clone().requires_grad_(True) for t in (x, off, mask, w)]
+    ref = OD.modulated_deform_conv(*ins_r, None, stride, 1, 1, groups)
+    rg = torch.autograd.grad(ref, ins_r, gy)
+    ins = [t.to(DEV).requires_grad_(True) for t in (x, off, mask, w)]
+    out = ops.modulated_deform_conv(*ins, None, stride, 1, 1, groups, out_fp32=True)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 4e-3
+    gg = torch.autograd.grad(out, ins, gy.to(DEV))
+    for name, a, r in zip(['x', 'offset', 'mask', 'w'], gg, rg):
+        assert a.shape == r.shape, name
+        assert _rel(a.float(), r) < (4e-2 if name == 'x' else 2e-2), (groups, name, _rel(a.float(), r))
+
+
 def test_dcn_out_of_range_and_zero_offsets():
     """P4 / P6: far-away samples contribute nothing; zero offsets + mask 0.5 reduce DCNv2 to 0.5 * conv."""
     ops = _ops()
