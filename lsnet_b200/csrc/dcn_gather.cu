@@ -96,9 +96,16 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float (&f)[8]) {
   }
 }
 
+// bf16x2 word -> (lo, hi) as a float2 register pair (one shift, one mask), the operand form of the packed fp32x2 FMA
+__device__ __forceinline__ float2 bf16x2_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
 // grid: (patches_w, patches_h, B).  One warp per output pixel: lane k (< taps) derives the sampling position, the four
 // (mask-folded) bilinear weights and the four corner pixel indices of tap k ONCE; the tap loop broadcasts them with
 // shuffles, and every lane gathers/interpolates/stores the 8 channels it owns (16-byte accesses, coalesced per corner).
+// Corner indices are clamped into the map (always loadable, weight 0 when outside), so the tap loop is branch-free;
+// the interpolation runs on packed fp32x2 FMAs (sm_100 FFMA2).
 template <int U>   // taps in flight per lane: 4*U independent 16-byte gathers are issued before the first use
 __global__ void __launch_bounds__(GATHER_THREADS)
 dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ offset,
@@ -109,6 +116,7 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   const int h_base = blockIdx.y * PATCH_H, w_base = blockIdx.x * PATCH_W;
   const int taps = g.kh * g.kw;
   const int cpg = g.C / g.dg;
+  const int ldxb = static_cast<int>(g.ldx) * 2;      // pixel pitch in bytes (checked < 2^31 on the host)
   for (int pix = warp; pix < PATCH_H * PATCH_W; pix += nwarps) {
     const int ho = h_base + pix / PATCH_W, wo = w_base + pix % PATCH_W;
     if (ho >= g.Ho || wo >= g.Wo) continue;
@@ -132,46 +140,44 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
           co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
         }
         const int nt = min(32, taps - t0);
-        for (int kk = 0; kk < nt; kk += U) {
-          float wq[U][4];
-          long long oq[U][4];
-          bool any[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int src = min(kk + u, nt - 1);
-            wq[u][0] = __shfl_sync(0xffffffffu, cw0, src); wq[u][1] = __shfl_sync(0xffffffffu, cw1, src);
-            wq[u][2] = __shfl_sync(0xffffffffu, cw2, src); wq[u][3] = __shfl_sync(0xffffffffu, cw3, src);
-            oq[u][0] = static_cast<long long>(__shfl_sync(0xffffffffu, co0, src)) * g.ldx;
-            oq[u][1] = static_cast<long long>(__shfl_sync(0xffffffffu, co1, src)) * g.ldx;
-            oq[u][2] = static_cast<long long>(__shfl_sync(0xffffffffu, co2, src)) * g.ldx;
-            oq[u][3] = static_cast<long long>(__shfl_sync(0xffffffffu, co3, src)) * g.ldx;
-            any[u] = (kk + u < nt) &&
-                     ((wq[u][0] != 0.f) || (wq[u][1] != 0.f) || (wq[u][2] != 0.f) || (wq[u][3] != 0.f));
-          }
-          for (int c0 = grp * cpg + lane * 8; c0 < (grp + 1) * cpg; c0 += 256) {
+        for (int cb = grp * cpg; cb < (grp + 1) * cpg; cb += 256) {     // warp-uniform trip count (shuffles inside)
+          const bool act = cb + lane * 8 < (grp + 1) * cpg;
+          const int c0 = act ? cb + lane * 8 : cb;
+          const char* xc = reinterpret_cast<const char*>(x + c0);
+          for (int kk = 0; kk < nt; kk += U) {
             uint4 ld[U][4];
+            float wq[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-              if (any[u]) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ld[u][q] = __ldg(reinterpret_cast<const uint4*>(x + oq[u][q] + c0));
-              }
+              const int src = min(kk + u, nt - 1);
+              wq[u][0] = __shfl_sync(0xffffffffu, cw0, src); wq[u][1] = __shfl_sync(0xffffffffu, cw1, src);
+              wq[u][2] = __shfl_sync(0xffffffffu, cw2, src); wq[u][3] = __shfl_sync(0xffffffffu, cw3, src);
+              const int o0 = __shfl_sync(0xffffffffu, co0, src), o1 = __shfl_sync(0xffffffffu, co1, src);
+              const int o2 = __shfl_sync(0xffffffffu, co2, src), o3 = __shfl_sync(0xffffffffu, co3, src);
+              ld[u][0] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(o0) * ldxb));
+              ld[u][1] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(o1) * ldxb));
+              ld[u][2] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(o2) * ldxb));
+              ld[u][3] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(o3) * ldxb));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (kk + u >= nt) continue;
-              uint4 outv = make_uint4(0u, 0u, 0u, 0u);
-              if (any[u]) {
-                float f0[8], f1[8], f2[8], f3[8], acc[8];
-                bf16x8_to_float(ld[u][0], f0); bf16x8_to_float(ld[u][1], f1);
-                bf16x8_to_float(ld[u][2], f2); bf16x8_to_float(ld[u][3], f3);
+              uint32_t outw[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  acc[e] = fmaf(wq[u][3], f3[e], fmaf(wq[u][2], f2[e], fmaf(wq[u][1], f1[e], wq[u][0] * f0[e])));
-                outv = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                                  pack_bf16x2(acc[6], acc[7]));
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t a0 = reinterpret_cast<const uint32_t*>(&ld[u][0])[i];
+                const uint32_t a1 = reinterpret_cast<const uint32_t*>(&ld[u][1])[i];
+                const uint32_t a2 = reinterpret_cast<const uint32_t*>(&ld[u][2])[i];
+                const uint32_t a3 = reinterpret_cast<const uint32_t*>(&ld[u][3])[i];
+                // same association as the scalar chain: ((w0*f0 + w1*f1) + w2*f2) + w3*f3, each step one fused FMA
+                float2 acc = __fmul2_rn(make_float2(wq[u][0], wq[u][0]), bf16x2_f2(a0));
+                acc = __ffma2_rn(make_float2(wq[u][1], wq[u][1]), bf16x2_f2(a1), acc);
+                acc = __ffma2_rn(make_float2(wq[u][2], wq[u][2]), bf16x2_f2(a2), acc);
+                acc = __ffma2_rn(make_float2(wq[u][3], wq[u][3]), bf16x2_f2(a3), acc);
+                outw[i] = pack_bf16x2(acc.x, acc.y);
               }
-              st_stream(dst + static_cast<long long>(t0 + kk + u) * g.C + c0, outv);
+              if (act)
+                st_stream(dst + static_cast<long long>(t0 + kk + u) * g.C + c0, make_uint4(outw[0], outw[1], outw[2], outw[3]));
             }
           }
         }
@@ -317,11 +323,6 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
 struct BinCfg {
   int PH, PW, WH, WW, R, skip;
 };
-
-// bf16x2 word -> (lo, hi) as a float2 register pair (one shift, one mask), the operand form of the packed fp32x2 FMA
-__device__ __forceinline__ float2 bf16x2_f2(uint32_t u) {
-  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-}
 
 // acc += <a, b> over 8 bf16 channels, accumulated pairwise with FFMA2 (sm_100 packed fp32x2; exact products)
 __device__ __forceinline__ float2 dot8(const float2 (&a)[4], const uint4& b, float2 acc) {
