@@ -93,6 +93,9 @@ int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const float* W, const
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel
  * g*2*kh*kw + 2*k + {0:dy, 1:dx}; mask: fp32 [B*Ho*Wo, ldm], channel g*kh*kw + k; col: bf16 [B*Ho*Wo, kh*kw*C].
+ * mask_logits = 1: `mask` holds the raw conv_offset outputs and the kernels apply the sigmoid of
+ * ModulatedDeformConvPack.forward (deform_conv.py:528-531) themselves (the adjoint then returns dmask w.r.t. the
+ * logits), so offset and mask can be two column ranges of ONE conv_offset output and no element-wise kernel runs.
  * Replaces deformable_im2col / pyramid_deformable_im2col / modulated_deformable_im2col_cuda
  * (mmdet/ops/dcn/src/cuda/deform_conv_cuda_kernel.cu:190-332, 647-680, 847-910, 1046-1076), i.e. the sampling half
  * of deform_conv_forward / pyramid_deform_conv_forward / modulated_deform_conv_forward
@@ -100,7 +103,8 @@ int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const float* W, const
 int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, long long ldx, const float* offset,
                           long long ldo, const float* mask, long long ldm, int Ho, int Wo, int kh, int kw,
                           int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, float scale_h,
-                          float scale_w, int deformable_groups, void* col, long long ldcol, void* stream);
+                          float scale_w, int deformable_groups, void* col, long long ldcol, int mask_logits,
+                          void* stream);
 
 /* Adjoint: gcol bf16 [B*Ho*Wo, kh*kw*C] (= dY . W) -> dx NHWC, ACCUMULATED (caller zero-fills; may be NULL): bf16 with
  * 16-byte packed-bf16 vector reds (dx_fp32 = 0, the training default) or fp32 with v4.f32 reds (dx_fp32 = 1),
@@ -112,7 +116,8 @@ int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const void* x, int 
                           const float* offset, long long ldo, const float* mask, long long ldm, int Ho, int Wo,
                           int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                           float scale_h, float scale_w, int deformable_groups, void* dx, long long lddx,
-                          int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm, void* stream);
+                          int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm, int mask_logits,
+                          void* stream);
 
 /* ---- cross-IOU loss ----------------------------------------------------------------------------------------------
  * loss_type: 0 bbox, 1 polygon, 2 keypoint.  Dense form = CrossIOULoss.forward / cross_iou_loss

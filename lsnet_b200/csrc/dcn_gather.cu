@@ -24,6 +24,7 @@ struct DcnGeom {
   float scale_h, scale_w;  // pyramid: base grid is scaled, the learned offset is not (…kernel.cu:281-282)
   int dg;                  // deformable groups
   long long ldx, ldo, ldm, ldcol;
+  int mask_logits;         // mask holds the raw conv_offset logits: m = sigmoid(raw), dMask is returned w.r.t. the logits
 };
 
 constexpr int PATCH_H = 4, PATCH_W = 8;   // 32 output pixels per CTA: keeps the sampled rows L1-resident
@@ -36,6 +37,11 @@ struct Corner {
   float lh, lw;
   bool v[4];
 };
+
+__device__ __forceinline__ float load_mask(const DcnGeom& g, const float* mp) {
+  const float r = __ldg(mp);
+  return g.mask_logits ? 1.f / (1.f + __expf(-r)) : r;
+}
 
 __device__ __forceinline__ Corner make_corner(const DcnGeom& g, int b, float h, float w) {
   Corner c;
@@ -134,7 +140,7 @@ dcn_im2col_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
           sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
           const Corner cn = make_corner(g, b, h, w);
           float m = 1.f;
-          if (mask) m = __ldg(mask + p * g.ldm + grp * taps + k);
+          if (mask) m = load_mask(g, mask + p * g.ldm + grp * taps + k);
           cw0 = cn.w[0] * m; cw1 = cn.w[1] * m; cw2 = cn.w[2] * m; cw3 = cn.w[3] * m;
           co0 = static_cast<int>(cn.o[0] / g.ldx); co1 = static_cast<int>(cn.o[1] / g.ldx);
           co2 = static_cast<int>(cn.o[2] / g.ldx); co3 = static_cast<int>(cn.o[3] / g.ldx);
@@ -234,7 +240,7 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
           float h, w;
           sample_pos(g, off_px, grp, k, ho, wo, &h, &w);
           const Corner cn = make_corner(g, b, h, w);
-          if (mask) m_ = __ldg(mask + p * g.ldm + grp * taps + k);
+          if (mask) m_ = load_mask(g, mask + p * g.ldm + grp * taps + k);
           lh_ = cn.lh; lw_ = cn.lw;
           vbits = (cn.v[0] ? 1 : 0) | (cn.v[1] ? 2 : 0) | (cn.v[2] ? 4 : 0) | (cn.v[3] ? 8 : 0) | (cn.inside ? 16 : 0);
           co0 = static_cast<int>(cn.o[0] / g.ldx); co1 = static_cast<int>(cn.o[1] / g.ldx);
@@ -292,7 +298,7 @@ dcn_col2im_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bfloat16* _
             }
           }
           gh = warp_sum(gh); gw = warp_sum(gw); gm = warp_sum(gm);
-          if (lane == kk) { my_gh = gh; my_gw = gw; my_gm = gm; }
+          if (lane == kk) { my_gh = gh; my_gw = gw; my_gm = g.mask_logits ? gm * m * (1.f - m) : gm; }
         }
         if (t0 + lane < taps) {
           const int k = t0 + lane;
@@ -393,7 +399,7 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
         const float hf = floorf(h), wf = floorf(w);
         const int h0 = static_cast<int>(hf), w0 = static_cast<int>(wf);
         const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw_ = 1.f - lw;
-        if (mask) m = __ldg(mask + p * g.ldm + tap);
+        if (mask) m = load_mask(g, mask + p * g.ldm + tap);
         const bool v0 = h0 >= 0 && w0 >= 0, v1 = h0 >= 0 && w0 + 1 <= g.W - 1;
         const bool v2 = h0 + 1 <= g.H - 1 && w0 >= 0, v3 = h0 + 1 <= g.H - 1 && w0 + 1 <= g.W - 1;
         bits |= 16 | (v0 ? 1 : 0) | (v1 ? 2 : 0) | (v2 ? 4 : 0) | (v3 ? 8 : 0);
@@ -526,7 +532,14 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
       }
     }
     if (lane < 18) doffset[p * lddo + lane] = v[0];
-    else if (lane < 27 && dmask) dmask[p * lddm + lane - 18] = v[0];
+    else if (lane < 27 && dmask) {
+      float r = v[0];
+      if (g.mask_logits) {
+        const float m = __int_as_float(gx[pix * 9 + lane - 18].z);
+        r *= m * (1.f - m);
+      }
+      dmask[p * lddm + lane - 18] = r;
+    }
   }
   if (!want_dx) return;
 
@@ -657,11 +670,11 @@ extern "C" int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, 
                                      long long ldo, const float* mask, long long ldm, int Ho, int Wo, int kh, int kw,
                                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                                      float scale_h, float scale_w, int deformable_groups, void* col, long long ldcol,
-                                     void* stream) {
+                                     int mask_logits, void* stream) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
   if (int rc = check_geom("lsnet_dcn_im2col_bf16", C, deformable_groups, ldx, ldcol)) return rc;
   DcnGeom g{B, H, W, C, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, scale_h, scale_w,
-            deformable_groups, ldx, ldo, ldm, ldcol};
+            deformable_groups, ldx, ldo, ldm, ldcol, (mask && mask_logits) ? 1 : 0};
   dim3 grid((Wo + PATCH_W - 1) / PATCH_W, (Ho + PATCH_H - 1) / PATCH_H, B);
   const double taps = kh * kw, px = static_cast<double>(B) * Ho * Wo;
   // algorithmic bytes: x read once (B*H*W*2C) + offsets/mask (4*(2+[mask])*taps per px) + bf16 columns written
@@ -688,12 +701,12 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
                                      long long ldm, int Ho, int Wo, int kh, int kw, int stride_h, int stride_w,
                                      int pad_h, int pad_w, int dil_h, int dil_w, float scale_h, float scale_w,
                                      int deformable_groups, void* dx, long long lddx, int dx_fp32, float* doffset,
-                                     long long lddo, float* dmask, long long lddm, void* stream) {
+                                     long long lddo, float* dmask, long long lddm, int mask_logits, void* stream) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
   if (int rc = check_geom("lsnet_dcn_col2im_bf16", C, deformable_groups, ldx, ldcol)) return rc;
   if (dx && (lddx % 8)) return set_error("lsnet_dcn_col2im_bf16: dx pitch must be a multiple of 8 bf16");
   DcnGeom g{B, H, W, C, Ho, Wo, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, scale_h, scale_w,
-            deformable_groups, ldx, ldo, ldm, ldcol};
+            deformable_groups, ldx, ldo, ldm, ldcol, (mask && mask_logits) ? 1 : 0};
   dim3 grid((Wo + PATCH_W - 1) / PATCH_W, (Ho + PATCH_H - 1) / PATCH_H, B);
   const double taps = kh * kw, px = static_cast<double>(B) * Ho * Wo;
   // algorithmic bytes: dCol read (2*taps*C per px) + x read + offsets/mask read + dX written (bf16) + dOffset/dMask

@@ -12,6 +12,11 @@ from .. import ops
 from ..registry import CONV_LAYERS
 
 
+import os
+
+PACKED_OFFSET_MASK = os.environ.get('LSNET_DCN_PACKED_OM', '1') == '1'
+
+
 class _DeformBase(nn.Module):
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
@@ -118,6 +123,10 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
     def forward(self, x):
         out = _offset_conv(self, x)
         n = self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
+        if PACKED_OFFSET_MASK and x.is_cuda:
+            # one op: the sampling kernels split offsets / mask logits and apply the sigmoid (and its derivative)
+            return ops.modulated_deform_conv_packed(x, out[:, :3 * n], self.weight, self.bias, self.stride, self.padding,
+                                                    self.dilation, self.groups, self.deformable_groups)
         # chunk(3) + cat(o1, o2) keeps the channel order (deform_conv.py:528-531): offsets = first 2n channels
         offset, mask = out[:, :2 * n], torch.sigmoid(out[:, 2 * n:3 * n])
         return ops.modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,

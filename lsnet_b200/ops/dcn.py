@@ -32,7 +32,7 @@ def _pix_major(t, min_ld_mult=1):
     return t, ld
 
 
-def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg):
+def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False):
     B, H, W, C, ldx = G.nhwc_geom(x)
     offset, ldo = _pix_major(offset)
     ldm = 0
@@ -42,7 +42,8 @@ def dcn_im2col(x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg):
     L.call('lsnet_dcn_im2col_bf16', L.ptr(x), L.c_int(B), L.c_int(H), L.c_int(W), L.c_int(C), L.c_ll(ldx),
            L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.c_int(Ho), L.c_int(Wo), L.c_int(kh), L.c_int(kw),
            L.c_int(stride[0]), L.c_int(stride[1]), L.c_int(pad[0]), L.c_int(pad[1]), L.c_int(dil[0]), L.c_int(dil[1]),
-           L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(col), L.c_ll(col.stride(0)), L.stream())
+           L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(col), L.c_ll(col.stride(0)), L.c_int(int(mask_logits)),
+           L.stream())
     return col
 
 
@@ -52,7 +53,8 @@ import os
 DX_FP32 = os.environ.get('LSNET_DCN_DX_FP32', '0') == '1'
 
 
-def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True, dx_fp32=None):
+def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True, dx_fp32=None,
+               mask_logits=False, packed_out=False):
     B, H, W, C, ldx = G.nhwc_geom(x)
     offset, ldo = _pix_major(offset)
     ldm = 0
@@ -61,13 +63,25 @@ def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, 
     taps = kh * kw
     dx_fp32 = DX_FP32 if dx_fp32 is None else dx_fp32
     dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32 if dx_fp32 else torch.bfloat16) if need_dx else None
-    doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
-    dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
+    if packed_out:
+        # ONE gradient tensor for the conv_offset output: dOffset in channels [0, 2*dg*taps), dMask (w.r.t. the
+        # logits) behind it — the layout of ModulatedDeformConvPack's conv_offset (deform_conv.py:528-531)
+        assert mask is not None
+        nom = dg * 3 * taps
+        dom = torch.empty((B, Ho, Wo, nom), device=x.device, dtype=torch.float32)
+        doff, dmask, lddo, lddm = dom, dom[..., dg * 2 * taps:], nom, nom
+    else:
+        doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
+        dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
+        lddo, lddm = dg * 2 * taps, dg * taps
     L.call('lsnet_dcn_col2im_bf16', L.ptr(gcol), L.c_ll(gcol.stride(0)), L.ptr(x), L.c_int(B), L.c_int(H), L.c_int(W),
            L.c_int(C), L.c_ll(ldx), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.c_int(Ho), L.c_int(Wo),
            L.c_int(kh), L.c_int(kw), L.c_int(stride[0]), L.c_int(stride[1]), L.c_int(pad[0]), L.c_int(pad[1]),
            L.c_int(dil[0]), L.c_int(dil[1]), L.c_f(scales[0]), L.c_f(scales[1]), L.c_int(dg), L.ptr(dx), L.c_ll(C),
-           L.c_int(int(bool(dx_fp32))), L.ptr(doff), L.c_ll(dg * 2 * taps), L.ptr(dmask), L.c_ll(dg * taps), L.stream())
+           L.c_int(int(bool(dx_fp32))), L.ptr(doff), L.c_ll(lddo), L.ptr(dmask), L.c_ll(lddm),
+           L.c_int(int(mask_logits)), L.stream())
+    if packed_out:
+        return dx.permute(0, 3, 1, 2) if dx is not None else None, dom.permute(0, 3, 1, 2), None
     return (dx.permute(0, 3, 1, 2) if dx is not None else None, doff.permute(0, 3, 1, 2),
             dmask.permute(0, 3, 1, 2) if dmask is not None else None)
 
@@ -103,7 +117,9 @@ class _DCN(Function):
 
     @staticmethod
     def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
-                out_slice=None):
+                out_slice=None, packed_om=False):
+        # packed_om: ``offset`` is the whole conv_offset output (B, 3*dg*taps, Ho, Wo) — offsets in the first 2/3 of the
+        # channels, mask LOGITS behind them; ``mask`` is None and the kernels apply the sigmoid.
         co, cig, kh, kw = weight.shape
         ci = cig * groups
         if co % groups:
@@ -115,7 +131,14 @@ class _DCN(Function):
         if offset.shape[2] != Ho or offset.shape[3] != Wo:
             raise ValueError(f'offset grid {tuple(offset.shape[2:])} != output grid {(Ho, Wo)}')
         cfg = (Ho, Wo, kh, kw, stride, pad, dil, scales, dg)
-        col = dcn_im2col(x, offset.detach(), None if mask is None else mask.detach(), *cfg)
+        ctx.packed_om = packed_om
+        if packed_om:
+            om, _ = _pix_major(offset.detach())
+            n2 = 2 * dg * kh * kw
+            col = dcn_im2col(x, om[:, :n2], om[:, n2:], *cfg, mask_logits=True)
+            offset = om
+        else:
+            col = dcn_im2col(x, offset.detach(), None if mask is None else mask.detach(), *cfg)
         npad = (co + 15) // 16 * 16
 
         def pack_fwd(t):
@@ -178,8 +201,13 @@ class _DCN(Function):
                 return p.contiguous()
             wt = G.cached_pack(weight, 'dcn_bwd%d_%d' % (cop, groups), pack_bwd)
             gcol = G.gemm(gy2, wt, None, False, torch.bfloat16)
-            gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
-                                         need_dx=ctx.needs_input_grad[0])
+            if ctx.packed_om:
+                n2 = 2 * ctx.cfg[8] * kh * kw
+                gx, goff, gmask = dcn_col2im(gcol, x, offset[:, :n2], offset[:, n2:], *ctx.cfg,
+                                             need_dx=ctx.needs_input_grad[0], mask_logits=True, packed_out=True)
+            else:
+                gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
+                                             need_dx=ctx.needs_input_grad[0])
             if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
         if side is not None:
@@ -188,7 +216,7 @@ class _DCN(Function):
             gw = unpack_dw(G.gemm_tn(gy2, col))                        # [cop, taps*ci] fp32
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
-        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None
 
 
 def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
@@ -203,6 +231,14 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
     """DCNv2 — ModulatedDeformConvFunction.apply (mmdet/ops/dcn/deform_conv.py:114-185)."""
     return _DCN.apply(x, offset, mask, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
                       groups, deformable_groups, False, out_fp32)
+
+
+def modulated_deform_conv_packed(x, offset_mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                                 deformable_groups=1, out_fp32=False):
+    """ModulatedDeformConvPack.forward after its conv_offset (deform_conv.py:528-533) as ONE op: ``offset_mask`` is the
+    raw conv_offset output; chunk / cat / sigmoid and their backward happen inside the sampling kernels."""
+    return _DCN.apply(x, offset_mask, None, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
+                      groups, deformable_groups, False, out_fp32, None, True)
 
 
 def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

@@ -176,6 +176,31 @@ def test_dcn_grouped_vs_oracle(groups, stride):
         assert _rel(a.float(), r) < (4e-2 if name == 'x' else 2e-2), (groups, name, _rel(a.float(), r))
 
 
+def test_dcnv2_pack_fused_sigmoid_matches_unfused():
+    """ModulatedDeformConvPack (deform_conv.py:488-534): the one-op path (sampling kernels read offsets and mask LOGITS
+    straight from the conv_offset output, sigmoid and its derivative inside) against chunk/cat/sigmoid in torch."""
+    import lsnet_b200.modules.dcn as mdcn
+    torch.manual_seed(4)
+    m = mdcn.ModulatedDeformConvPack(64, 48, 3, stride=1, padding=1, bias=True).to(DEV)
+    torch.nn.init.normal_(m.conv_offset.weight, std=0.05)
+    torch.nn.init.normal_(m.conv_offset.bias, std=0.5)
+    x = _bf(torch.randn(2, 64, 13, 21)).to(DEV)
+    gy = _bf(torch.randn(2, 48, 13, 21)).to(DEV)
+    res = []
+    for packed in (True, False):
+        mdcn.PACKED_OFFSET_MASK = packed
+        xi = x.clone().requires_grad_(True)
+        m.zero_grad()
+        y = m(xi)
+        y.backward(gy.to(y.dtype))
+        res.append((y.detach().float(), xi.grad.float(), m.conv_offset.weight.grad.clone(), m.conv_offset.bias.grad.clone(),
+                    m.weight.grad.clone()))
+    mdcn.PACKED_OFFSET_MASK = True
+    for name, a, b in zip(['y', 'dx', 'd conv_offset.weight', 'd conv_offset.bias', 'dw'], res[0], res[1]):
+        assert _rel(a, b) < 2e-2, (name, _rel(a, b))      # bf16 dX reds / column rounding order
+    assert _rel(res[0][0], res[1][0]) < 1e-3 and _rel(res[0][3], res[1][3]) < 1e-3
+
+
 def test_dcn_out_of_range_and_zero_offsets():
     """P4 / P6: far-away samples contribute nothing; zero offsets + mask 0.5 reduce DCNv2 to 0.5 * conv."""
     ops = _ops()
