@@ -92,8 +92,9 @@ grad_prep_vec_kernel(const void* __restrict__ gy, long long ldg, const __nv_bflo
         if (!(t.y > 0.f)) f[2 * i + 1] = 0.f;
       }
     }
-    *reinterpret_cast<uint4*>(out + r * ldout + v * 8) =
-        make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    if (out)     // out == nullptr: column sums only (the gradient is already in the layout the GEMMs consume)
+      *reinterpret_cast<uint4*>(out + r * ldout + v * 8) =
+          make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += f[e];
   }
@@ -194,7 +195,7 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
   if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
   const int vpp = C / 8;
   const bool vec = (C % 8 == 0) && Cpad == C && vpp <= PREP_THREADS && (vpp & (vpp - 1)) == 0 &&
-                   (ldg % (gy_fp32 ? 4 : 8) == 0) && (ldout % 8 == 0) && (!relu_out || ldo % 8 == 0) &&
+                   (ldg % (gy_fp32 ? 4 : 8) == 0) && (!out || ldout % 8 == 0) && (!relu_out || ldo % 8 == 0) &&
                    (reinterpret_cast<uintptr_t>(gy) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                    (!relu_out || reinterpret_cast<uintptr_t>(relu_out) % 16 == 0);
   if (vec) {
@@ -209,6 +210,7 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
           colsum);
     return check_launch("grad_prep_vec");
   }
+  if (!out) return set_error("lsnet_grad_prep: out == NULL (column sums only) needs the vector path");
   const int grid = static_cast<int>((P + PREP_ROWS - 1) / PREP_ROWS);
   if (gy_fp32)
     grad_prep_kernel<true><<<grid, PREP_THREADS, sizeof(float) * Cpad, st>>>(

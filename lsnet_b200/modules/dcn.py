@@ -30,6 +30,7 @@ class _DeformBase(nn.Module):
         self.groups, self.deformable_groups = groups, deformable_groups
         self.transposed, self.output_padding = False, _single(0)   # nn.Conv2d compatibility (ConvModule copies them)
         self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        self.weight._lsnet_tapmajor = groups == 1     # GraphTrainer may keep it tap-major (see train.py)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -114,6 +115,7 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
         self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 3 * self.kernel_size[0] *
                                      self.kernel_size[1], kernel_size=self.kernel_size, stride=self.stride,
                                      padding=self.padding, dilation=self.dilation, bias=True)
+        self.conv_offset.weight._lsnet_tapmajor = self.stride == (1, 1)
         self.init_offset()
 
     def init_offset(self):

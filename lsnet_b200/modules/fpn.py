@@ -18,6 +18,7 @@ class ConvNorm(nn.Module):
         self.with_norm = norm_cfg is not None
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=not self.with_norm)
         self.stride, self.padding, self.k, self.act = stride, padding, k, act
+        self.conv.weight._lsnet_tapmajor = stride == 1 and (k == 1 or padding == k // 2)   # see train.py
         if self.with_norm:
             kind = norm_cfg.get('type', 'GN')
             if kind == 'GN':

@@ -33,6 +33,10 @@ def _cfg_get(cfg, key, default=None):
 class B200Conv2d(nn.Conv2d):
     """nn.Conv2d whose stride-1 'same' forward runs on the tcgen05 implicit-GEMM kernel (parameter names unchanged)."""
 
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.weight._lsnet_tapmajor = True       # GraphTrainer may keep it tap-major (see train.py)
+
     def forward(self, x, relu=False, out_fp32=False):
         k, p, d = self.kernel_size, self.padding, self.dilation
         assert self.stride == (1, 1) and self.groups == 1 and 2 * p[0] == d[0] * (k[0] - 1) and k[0] == k[1]

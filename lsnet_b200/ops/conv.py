@@ -26,6 +26,7 @@ class _ConvSame(Function):
         ctx.save_for_backward(x, weight, out if (relu and not out_fp32) else None)
         assert not (relu and out_fp32)
         ctx.cfg = (pad, dil, relu, bias is not None, ci)
+        ctx.grad2d = G.direct_grad(weight)
         return out
 
     @staticmethod
@@ -40,8 +41,14 @@ class _ConvSame(Function):
             wt = G.cached_pack(weight, 'bwd', lambda t: G.pack_conv_weight(t, flip_transpose=True))
             gx = G.conv2d_nhwc(gyp, wt, kh, kw, pad, dil, None, False, torch.bfloat16, n_valid=ci)
         if ctx.needs_input_grad[1]:
-            dw = G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil)       # (co_pad, taps, C_pad8)
-            gw = dw[:co, :, :ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
+            direct = ctx.grad2d
+            if direct is not None and tuple(direct.shape) != (gyp.shape[1], kh * kw * x.shape[1]):
+                direct = None            # padded channel counts: go through the staging buffer
+            if direct is not None:       # accumulate straight into the parameter's (tap-major) gradient memory
+                G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil, out=direct)
+            else:
+                dw = G.conv2d_wgrad_nhwc(gyp, x, kh, kw, pad, dil)       # (co_pad, taps, C_pad8)
+                gw = dw[:co, :, :ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             gb = colsum
         return gx, gw, gb, None, None, None, None

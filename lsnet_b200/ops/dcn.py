@@ -109,7 +109,7 @@ def _expand_groups(w, groups):
     co, cig, kh, kw = w.shape
     idx = torch.arange(groups, device=w.device)
     d = w.new_zeros(groups, co // groups, groups, cig, kh, kw)
-    d[idx, :, idx] = w.view(groups, co // groups, cig, kh, kw)
+    d[idx, :, idx] = w.reshape(groups, co // groups, cig, kh, kw)
     return d.view(co, groups * cig, kh, kw)
 
 
@@ -152,6 +152,7 @@ class _DCN(Function):
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
+        ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
         if out_slice is not None:
             # write straight into channels [c0, c0+co) of a wider pixel-major buffer (replaces a later torch.cat)
             buf, c0 = out_slice
@@ -213,7 +214,13 @@ class _DCN(Function):
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif ctx.needs_input_grad[3]:
-            gw = unpack_dw(G.gemm_tn(gy2, col))                        # [cop, taps*ci] fp32
+            direct = ctx.grad2d
+            if direct is not None and tuple(direct.shape) != (cop, kh * kw * ci):
+                direct = None
+            if direct is not None:       # accumulate straight into the parameter's (tap-major) gradient memory
+                G.gemm_tn(gy2, col, out=direct)
+            else:
+                gw = unpack_dw(G.gemm_tn(gy2, col))                    # [cop, taps*ci] fp32
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
         return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None

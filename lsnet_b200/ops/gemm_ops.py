@@ -124,12 +124,22 @@ def conv2d_nhwc(x, wp, kh, kw, pad, dil=1, bias=None, relu=False, out_dtype=torc
     return buf.permute(0, 3, 1, 2)[:, :n_valid]
 
 
-def conv2d_wgrad_nhwc(dy, x, kh, kw, pad, dil=1):
-    """dW (N, kh*kw, C) fp32 of a stride-1 'same' conv; dy (B,N,H,W), x (B,C,H,W) channels_last bf16, N%8 == C%8 == 0."""
+def direct_grad(weight):
+    """The [Cout, taps*Cin] fp32 view of ``weight``'s gradient memory that a weight-gradient GEMM may accumulate into
+    directly (GraphTrainer lays such parameters out tap-major inside its flat gradient buffer), or None."""
+    g2 = getattr(weight, '_lsnet_grad2d', None)
+    if g2 is not None and weight.grad is not None and weight.grad.data_ptr() == g2.data_ptr():
+        return g2
+    return None
+
+
+def conv2d_wgrad_nhwc(dy, x, kh, kw, pad, dil=1, out=None):
+    """dW (N, kh*kw, C) fp32 of a stride-1 'same' conv; dy (B,N,H,W), x (B,C,H,W) channels_last bf16, N%8 == C%8 == 0.
+    ``out``: accumulate into this [N, kh*kw*C] fp32 buffer instead of a fresh zero-filled one."""
     B, H, W, C, ldx = nhwc_geom(x)
     _, _, _, N, ldy = nhwc_geom(dy)
     assert N % 8 == 0 and C % 8 == 0
-    dw = torch.zeros((N, kh * kw, C), device=x.device, dtype=torch.float32)
+    dw = torch.zeros((N, kh * kw, C), device=x.device, dtype=torch.float32) if out is None else out
     if kh == 1 and kw == 1:
         a = torch.as_strided(dy, (B * H * W, N), (ldy, 1))
         b = torch.as_strided(x, (B * H * W, C), (ldx, 1))
@@ -165,6 +175,13 @@ def grad_prep(gy, relu_out=None, want_colsum=False, mult=8):
     if relu_out is None and not want_colsum and pix_major and gy.dtype == torch.bfloat16 and Cp == C \
             and gy.stride(3) % 8 == 0:
         return gy, None
+    if relu_out is None and pix_major and gy.dtype == torch.bfloat16 and Cp == C and gy.stride(3) % 8 == 0 \
+            and (C // 8) & (C // 8 - 1) == 0 and C // 8 <= 256 and gy.data_ptr() % 16 == 0:
+        # already in the GEMM layout: only the bias gradient is missing -> read-only column-sum pass
+        colsum = torch.empty(C, device=gy.device, dtype=torch.float32)
+        L.call('lsnet_grad_prep', L.ptr(gy), L.c_int(0), L.c_ll(gy.stride(3)), L.ptr(None), L.c_ll(0), L.c_ll(B * H * W),
+               L.c_int(C), L.c_int(Cp), L.ptr(None), L.c_ll(0), L.ptr(colsum), L.stream())
+        return gy, colsum
     if not pix_major or gy.dtype not in (torch.float32, torch.bfloat16):
         gy = gy.contiguous(memory_format=torch.channels_last)
         if gy.dtype not in (torch.float32, torch.bfloat16):

@@ -2,6 +2,8 @@
 through torch DDP over NCCL (one process per GPU).  Mirrors what ``OptimizerHook.after_train_iter`` +
 ``EpochBasedRunner.train`` do per iteration (mmcv/mmcv/runner/hooks/optimizer.py:19-28,
 mmcv/mmcv/runner/epoch_based_runner.py:20-47) without the reference's per-scalar all-reduce + .item() every step."""
+import os
+
 import torch
 import torch.distributed as dist
 from torch.nn.parallel import DistributedDataParallel as DDP
@@ -56,6 +58,9 @@ class Trainer:
         return loss, log_vars
 
 
+DIRECT_WGRAD = os.environ.get('LSNET_DIRECT_WGRAD', '1') == '1'
+
+
 class GraphTrainer:
     """The same training step with (almost) no host work per iteration, B200-first:
 
@@ -96,9 +101,20 @@ class GraphTrainer:
         o = 0
         for p in self.params:
             k = p.numel()
-            self.flat_p[o:o + k].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[o:o + k].view_as(p)
-            p.grad = self.flat_g[o:o + k].view_as(p)
+            if DIRECT_WGRAD and p.dim() == 4 and getattr(p, '_lsnet_tapmajor', False):
+                # Weights of the tcgen05 conv / DCN kernels live tap-major ([Cout][kh][kw][Cin] memory, i.e.
+                # torch.channels_last strides on the OIHW parameter): the bf16 operand pack is then a plain cast and the
+                # weight-gradient GEMM's [Cout, taps*Cin] fp32 output IS the gradient's memory, so it accumulates
+                # there directly (no memset, no permute, no AccumulateGrad add per pyramid level).
+                co, ci, kh, kw = p.shape
+                self.flat_p[o:o + k].view(co, kh, kw, ci).copy_(p.data.permute(0, 2, 3, 1))
+                p.data = self.flat_p[o:o + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                p.grad = self.flat_g[o:o + k].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+                p._lsnet_grad2d = self.flat_g[o:o + k].view(co, kh * kw * ci)
+            else:
+                self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[o:o + k].view_as(p)
+                p.grad = self.flat_g[o:o + k].view_as(p)
             o += (k + al - 1) // al * al
         # ---- static inputs ----
         self.img = torch.empty_like(sample_batch['img'], device=self.device).contiguous(memory_format=torch.channels_last)
