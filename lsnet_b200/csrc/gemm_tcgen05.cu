@@ -554,6 +554,11 @@ static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
 static int dispatch_kmajor(const CUtensorMap& tmA, const void* Bw, int N, int K, long long ldb, GemmArgs& a,
                            cudaStream_t st) {
   int BN = N >= 256 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  // Small problems (the upper pyramid levels: 3..33 M tiles) leave most of the 148 SMs idle with 256-wide tiles, and
+  // one CTA streams its K loop at only ~80 GB/s: narrow the N tile until the grid covers the machine.
+  static int adapt = -1;
+  if (adapt < 0) { const char* e = getenv("LSNET_GEMM_ADAPT_BN"); adapt = e ? atoi(e) : 0; }   // measured in-step: 7.50 ms with, 7.36 ms without -> opt-in
+  while (adapt && BN > 32 && static_cast<long long>(a.m_tiles) * ((N + BN - 1) / BN) < num_sms()) BN /= 2;
   a.n_tiles = (N + BN - 1) / BN;
   CUtensorMap tmB;
   if (int rc = make_map_2d(&tmB, Bw, N, K, ldb, 64, BN)) return rc;

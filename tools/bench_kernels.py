@@ -104,6 +104,36 @@ if only in (None, 'col2im_pyr'):
     gcol1 = torch.randn(P1, 2304, generator=g).to(dev, torch.bfloat16)
     ms = timeit(lambda: ops.dcn_col2im(gcol1, x, off1, None, 50, 84, 3, 3, (1, 1), (1, 1), (1, 1), (2.0, 2.0), 1))
     add('dcn_col2im pyramid 50x84 <- 100x168 (s=2)', ms, P1 * (2.0 * 9 * C + 8 * 18) + P * 4.0 * C, 'GB/s')
+if only == 'gemm_shapes':
+    # every GEMM / implicit-conv shape of one LSHead level set: where does the gemm_kmajor class lose its efficiency?
+    lv = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    tot = 0.0
+    for (h, w_) in lv:
+        Pl = B * h * w_
+        xl = torch.randn(B, 256, h, w_, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x768 = torch.randn(Pl, 768, generator=g).to(dev, torch.bfloat16)
+        coll = torch.randn(Pl, 2304, generator=g).to(dev, torch.bfloat16)
+        dyl = torch.randn(Pl, 256, generator=g).to(dev, torch.bfloat16)
+        dy32 = torch.randn(B, 32, h, w_, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w256 = G.pack_conv_weight(w)
+        w27 = G.pack_conv_weight(torch.randn(27, 256, 3, 3, generator=g).to(dev))
+        w27t = G.pack_conv_weight(torch.randn(27, 256, 3, 3, generator=g).to(dev), flip_transpose=True)
+        w11 = torch.randn(256, 768, generator=g).to(dev, torch.bfloat16)
+        w80 = torch.randn(80, 256, generator=g).to(dev, torch.bfloat16)
+        cases = [
+            ('DCN fwd      N256  K2304 x12', 12, lambda: G.gemm(coll, wp, None, False, torch.bfloat16), 2.0 * Pl * 256 * 2304),
+            ('DCN dcol     N2304 K256  x12', 12, lambda: G.gemm(dyl, wpT, None, False, torch.bfloat16), 2.0 * Pl * 256 * 2304),
+            ('conv3x3 256->256 fwd+dgrad x6', 6, lambda: G.conv2d_nhwc(xl, w256, 3, 3, 1), 2.0 * Pl * 256 * 2304),
+            ('conv_offset 256->27 fwd   x8', 8, lambda: G.conv2d_nhwc(xl, w27, 3, 3, 1, out_dtype=torch.float32), 2.0 * Pl * 32 * 2304),
+            ('conv_offset dgrad 32->256 x8', 8, lambda: G.conv2d_nhwc(dy32, w27t, 3, 3, 1), 2.0 * Pl * 256 * 9 * 64),
+            ('1x1 768->256 fwd+dgrad    x4', 4, lambda: G.gemm(x768, w11, None, True, torch.bfloat16), 2.0 * Pl * 256 * 768),
+            ('1x1 256->80 out           x6', 6, lambda: G.gemm(dyl, w80, None, False, torch.float32), 2.0 * Pl * 80 * 256),
+        ]
+        for name, cnt, fn, fl in cases:
+            ms = timeit(fn, n=6)
+            tot += ms * cnt
+            print(f'level {h}x{w_:<4d} {name:32s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s   x{cnt} = {ms * cnt:6.3f} ms', flush=True)
+    print('sum over levels (with multiplicities):', round(tot, 3), 'ms')
 if only in (None, 'gn'):
     wgt, bias = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     ms = timeit(lambda: ops.group_norm_nhwc(x, 32, wgt, bias, 1e-5, relu=True))

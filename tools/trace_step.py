@@ -57,6 +57,16 @@ with open('gpurun_out/trace_summary.md', 'w') as f:
     f.write('\n| kernel | launches | total ms |\n|---|---:|---:|\n')
     for n, (c, d) in sorted(by_name.items(), key=lambda x: -x[1][1])[:45]:
         f.write(f'| `{n}` | {c} | {1e-3 * d:.3f} |\n')
+    # per-launch view of the two GEMM kernels: (grid size, template) -> launches, total, mean
+    f.write('\n| GEMM launch group (kernel, grid) | launches | total ms | mean us |\n|---|---:|---:|---:|\n')
+    grp = collections.defaultdict(list)
+    for e in ev:
+        if 'gemm_kmajor' in e['name'] or 'gemm_mnmajor' in e['name']:
+            tmpl = e['name'].split('<')[1].split('>')[0] if '<' in e['name'] else ''
+            kind = 'kmajor' if 'kmajor' in e['name'] else 'mnmajor'
+            grp[(kind, tmpl, str(e['args'].get('grid')))].append(e['dur'])
+    for k, v in sorted(grp.items(), key=lambda kv: -sum(kv[1])):
+        f.write(f'| {k[0]}<{k[1]}> grid {k[2]} | {len(v)} | {1e-3 * sum(v):.3f} | {sum(v) / len(v):.1f} |\n')
     gaps.sort(reverse=True)
     f.write('\nlargest idle gaps (us, next kernel): ' + ', '.join(f'{g:.0f} ({n})' for g, n in gaps[:12]) + '\n')
 print(open('gpurun_out/trace_summary.md').read())
