@@ -201,6 +201,37 @@ def test_dcnv2_pack_fused_sigmoid_matches_unfused():
     assert _rel(res[0][0], res[1][0]) < 1e-3 and _rel(res[0][3], res[1][3]) < 1e-3
 
 
+@pytest.mark.parametrize('variant', ['v2', 'pyramid_half', 'pyramid_double'])
+def test_dcn_adjoint_identity_full_size(variant):
+    """BASELINE cfg2 sizes (B=4, 256 ch, level-0 / level-1 grids): the scatter is the exact adjoint of the gather.  With
+    J = d(columns)/d(x) for fixed offsets, <J^T g, x'> == <g, J x'> for arbitrary g, x' — a size-independent property
+    that needs no oracle.  Checked in fp64 on the fp32-accumulated dX; the only inexact step is the bf16 rounding of
+    the gathered columns (2^-9 relative per element, random sign)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    B, C = 4, 256
+    if variant == 'v2':
+        H, W, Ho, Wo, sc = 100, 168, 100, 168, (1.0, 1.0)
+    elif variant == 'pyramid_half':      # level-0 grid sampling level 1
+        H, W, Ho, Wo, sc = 50, 84, 100, 168, (0.5, 0.5)
+    else:                                # level-1 grid sampling level 0
+        H, W, Ho, Wo, sc = 100, 168, 50, 84, (2.0, 2.0)
+    xp = _bf(torch.randn(B, C, H, W, generator=g)).to(DEV).contiguous(memory_format=torch.channels_last)
+    off = (torch.randn(B, 18, Ho, Wo, generator=g) * 1.5).to(DEV).contiguous(memory_format=torch.channels_last)
+    mask = torch.rand(B, 9, Ho, Wo, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if variant == 'v2' else None
+    gcol = _bf(torch.randn(B * Ho * Wo, 9 * C, generator=g)).to(DEV)
+    cfg = (Ho, Wo, 3, 3, (1, 1), (1, 1), (1, 1), sc, 1)
+    col = ops.dcn_im2col(xp, off, mask, *cfg)                       # J x'  (bf16-rounded)
+    dx, doff, dmask = ops.dcn_col2im(gcol, xp, off, mask, *cfg, dx_fp32=True)       # J^T g
+    lhs = float((dx.double() * xp.double()).sum())
+    rhs = float((gcol.double() * col.double()).sum())
+    scale = float(gcol.double().norm() * col.double().norm())
+    # rounding noise of the columns: independent 2^-9 relative errors -> std = 2^-9 * |g||col| / sqrt(n); allow 8 sigma
+    tol = 8 * 2.0 ** -9 * scale / gcol.numel() ** 0.5
+    assert abs(lhs - rhs) < tol, (variant, lhs, rhs, tol)
+    assert torch.isfinite(doff).all() and (dmask is None or torch.isfinite(dmask).all())
+
+
 def test_dcn_out_of_range_and_zero_offsets():
     """P4 / P6: far-away samples contribute nothing; zero offsets + mask 0.5 reduce DCNv2 to 0.5 * conv."""
     ops = _ops()
