@@ -63,15 +63,55 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons every 200 ms during the timed region (B200_PROFILING.md recipe).  Sampled in-process
+    through NVML (nvidia_ml_py): an `nvidia-smi -lms` child takes the driver's global lock for every query, which shows
+    up as multi-ms stalls in the e2e loop (one synchronisation per step); falls back to nvidia-smi without NVML."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.stop_flag, self.thread = None, threading.Event(), None
+        self.sm, self.smax, self.reasons = [], None, set()
+
+    def _nvml_loop(self):
+        n, h = self.nvml
+        bits = {}
+        for name, attr in zip(self.NAMES, ['HwSlowdown', 'HwThermalSlowdown', 'SwThermalSlowdown', 'SwPowerCap']):
+            for pre in ('nvmlClocksEventReason', 'nvmlClocksThrottleReason'):
+                if hasattr(n, pre + attr):
+                    bits[name] = getattr(n, pre + attr)
+                    break
+        get_reasons = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            getattr(n, 'nvmlDeviceGetCurrentClocksThrottleReasons', None)
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(h))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            h = n.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE,
@@ -86,6 +126,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.smax, reasons=sorted(self.reasons),
+                        samples=len(sm), source='nvml')
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         self.proc.terminate()
@@ -94,18 +140,17 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in self.rows:
             try:
                 sm.append(float(r[1])); smax = float(r[2])
-                for n, v in zip(names, r[5:9]):
+                for n, v in zip(self.NAMES, r[5:9]):
                     if v.lower().startswith('active'):
                         reasons.add(n)
             except Exception:
                 pass
         sm.sort()
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=smax, reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), source='nvidia-smi')
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

@@ -102,8 +102,20 @@ class PackedGT:
 
 
 TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
-# run pyramid levels 1.. (25 % of the pixels, launch-latency-bound kernels) on their own streams, beside level 0
-LEVEL_STREAMS = os.environ.get('LSNET_LEVEL_STREAMS', '0') == '1'   # measured: no gain (33.70 vs 33.63 ms)
+# Every pyramid level on its own streams: the kernels of the three small levels (6 % of the pixels, 3-44 CTAs, 15-20 us
+# each) run beside each other instead of one after the other.  Measured (1xB200, B=4): all levels in one chain 29.8 ms,
+# '0|1,2,3,4' 29.7 ms (a persistent level-0 kernel leaves no SM for a chain that is itself serial), '0,1|2|3|4' 26.9 ms,
+# '0|1|2|3|4' 25.4 ms.
+LEVEL_STREAMS = os.environ.get('LSNET_LEVEL_STREAMS', '1') == '1'
+# level groups for LEVEL_STREAMS, e.g. '0,1|2|3|4': one stream pair per group
+LEVEL_GROUPS = os.environ.get('LSNET_LEVEL_GROUPS', '0|1|2|3|4')
+
+
+def _level_groups(L):
+    gs = [[int(t) for t in g.split(',') if int(t) < L] for g in LEVEL_GROUPS.split('|')]
+    gs = [g for g in gs if g]
+    assert sorted(sum(gs, [])) == list(range(L)), LEVEL_GROUPS
+    return gs
 _TOWER_STREAM = {}
 
 
@@ -306,7 +318,7 @@ class LSHead(nn.Module):
         cur = torch.cuda.current_stream()
         dev = feats[0].device
         L = len(feats)
-        groups = [list(range(L))] if not (LEVEL_STREAMS and L > 1) else [[0], list(range(1, L))]
+        groups = [list(range(L))] if not (LEVEL_STREAMS and L > 1) else _level_groups(L)
         cls_feats, outs = [None] * L, [None] * L
         used = []
         for gi, lv in enumerate(groups):
@@ -329,7 +341,7 @@ class LSHead(nn.Module):
             cur.wait_stream(st)
         for l in range(L):
             cls_feats[l].record_stream(cur)
-            if l > 0 and len(groups) > 1:
+            if len(groups) > 1 and l not in groups[0]:
                 for br in outs[l]:
                     for t in outs[l][br]:
                         t.record_stream(cur)
@@ -381,24 +393,36 @@ class LSHead(nn.Module):
             outs[br + '_init'] = [lvl[l][1][br][1] for l in range(L)]
             outs[br + '_refine'] = []
         cur = torch.cuda.current_stream() if feats[0].is_cuda else None
-        side = None
+        sides = {}
         if cur is not None and TOWER_STREAMS and LEVEL_STREAMS and L > 1:
-            side = _tower_stream(feats[0].device, 4)
-            side.wait_stream(cur)
+            for gi, lv in enumerate(_level_groups(L)):
+                if gi == 0:
+                    continue
+                st = _tower_stream(feats[0].device, 100 + gi)
+                st.wait_stream(cur)
+                for l in lv:
+                    sides[l] = st
             for c, o in lvl:            # tower outputs are read by the refine stage of the neighbouring levels
-                c.record_stream(side)
-                for br in o:
-                    for t in o[br]:
-                        t.record_stream(side)
+                for st in set(sides.values()):
+                    c.record_stream(st)
+                    for br in o:
+                        for t in o[br]:
+                            t.record_stream(st)
+        res = {}
         for l in range(L):
-            with torch.cuda.stream(side if (side is not None and l > 0) else cur) if cur is not None else _nullctx():
-                self._refine_level(l, L, lvl, cls_feats, brs, cls_driver, outs)
-        if side is not None:
-            cur.wait_stream(side)
-            for k in outs:
-                for t in outs[k][1:]:
-                    if t is not None:
-                        t.record_stream(cur)
+            lo = {k: [] for k in outs if k == 'cls' or k.endswith('_refine')}
+            with torch.cuda.stream(sides.get(l, cur)) if cur is not None else _nullctx():
+                self._refine_level(l, L, lvl, cls_feats, brs, cls_driver, lo)
+            res[l] = lo
+        for l in range(L):
+            for k, v in res[l].items():
+                outs[k].extend(v)
+        for st in set(sides.values()):
+            cur.wait_stream(st)
+        for l in sides:
+            for v in res[l].values():
+                for t in v:
+                    t.record_stream(cur)
         none = [None] * L
         return (outs['cls'], outs.get('bbox_init', none), outs.get('bbox_refine', none), outs.get('segm_init', none),
                 outs.get('segm_refine', none), outs.get('pose_init', none), outs.get('pose_refine', none))

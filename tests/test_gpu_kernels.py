@@ -216,10 +216,10 @@ def test_dcn_adjoint_identity_full_size(variant):
         H, W, Ho, Wo, sc = 50, 84, 100, 168, (0.5, 0.5)
     else:                                # level-1 grid sampling level 0
         H, W, Ho, Wo, sc = 100, 168, 50, 84, (2.0, 2.0)
-    xp = _bf(torch.randn(B, C, H, W, generator=g)).to(DEV).contiguous(memory_format=torch.channels_last)
+    xp = torch.randn(B, C, H, W, generator=g).to(DEV, torch.bfloat16).contiguous(memory_format=torch.channels_last)
     off = (torch.randn(B, 18, Ho, Wo, generator=g) * 1.5).to(DEV).contiguous(memory_format=torch.channels_last)
     mask = torch.rand(B, 9, Ho, Wo, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) if variant == 'v2' else None
-    gcol = _bf(torch.randn(B * Ho * Wo, 9 * C, generator=g)).to(DEV)
+    gcol = torch.randn(B * Ho * Wo, 9 * C, generator=g).to(DEV, torch.bfloat16)
     cfg = (Ho, Wo, 3, 3, (1, 1), (1, 1), (1, 1), sc, 1)
     col = ops.dcn_im2col(xp, off, mask, *cfg)                       # J x'  (bf16-rounded)
     dx, doff, dmask = ops.dcn_col2im(gcol, xp, off, mask, *cfg, dx_fp32=True)       # J^T g
