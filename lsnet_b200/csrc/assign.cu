@@ -13,6 +13,7 @@
 // builds them (core/anchor/point_generator.py:17-25); validity = (h < valid_h[b][l] && w < valid_w[b][l]) from
 // the image's pad_shape (lsnet_head.py:781-792).
 #include "common.cuh"
+#include <stdint.h>
 #include "lsnet_internal.h"
 
 namespace lsn {
@@ -129,7 +130,8 @@ constexpr int kMaxCand = kMaxLevels * 16;
 __global__ void __launch_bounds__(ASSIGN_THREADS)
 atss_candidates_kernel(const Levels lv, const int* __restrict__ valid_hw, const float* __restrict__ boxes,
                        const float* __restrict__ gt_bbox, const int* __restrict__ gt_count, int Gmax, int topk,
-                       unsigned long long* __restrict__ best_key) {
+                       unsigned long long* __restrict__ best_key, int dist_cap) {
+  extern __shared__ float dist_s[];      // [dist_cap] centre distances of the level being processed
   __shared__ MinPair red[ASSIGN_THREADS / 32];
   __shared__ int cand[kMaxCand];
   __shared__ float cand_iou[kMaxCand];
@@ -149,18 +151,45 @@ atss_candidates_kernel(const Levels lv, const int* __restrict__ valid_hw, const 
     const int k_l = min(topk, vh * vw);
     float pd = -1.f;     // previously selected (distance, index): next pick is the lexicographic successor
     int pi = -1;
-    for (int r = 0; r < k_l; ++r) {
-      MinPair best{3.0e38f, 0x7fffffff};
+    const bool staged = P <= dist_cap;
+    if (staged) {
+      // centre distances of this level once into shared memory (invalid points: +inf); the k_l selection rounds
+      // then scan shared memory instead of re-deriving 22 400 distances from global memory nine times
+      __syncthreads();
       for (int p = threadIdx.x; p < P; p += ASSIGN_THREADS) {
         const int h = p / lv.W[l], w = p % lv.W[l];
-        if (h >= vh || w >= vw) continue;
-        const float* a = bx + static_cast<long long>(lv.off[l] + p) * 4;
-        const float cx = __fdiv_rn(__fadd_rn(a[0], a[2]), 2.f), cy = __fdiv_rn(__fadd_rn(a[1], a[3]), 2.f);
-        const float dx = __fadd_rn(cx, -gcx), dy = __fadd_rn(cy, -gcy);
-        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        const int idx = lv.off[l] + p;
-        if (!lex_less(pd, pi, d, idx)) continue;   // already taken (or before the cursor)
-        if (lex_less(d, idx, best.d, best.i)) { best.d = d; best.i = idx; }
+        float d = __int_as_float(0x7f800000);
+        if (h < vh && w < vw) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(bx + static_cast<long long>(lv.off[l] + p) * 4));
+          const float cx = __fdiv_rn(__fadd_rn(a.x, a.z), 2.f), cy = __fdiv_rn(__fadd_rn(a.y, a.w), 2.f);
+          const float dx = __fadd_rn(cx, -gcx), dy = __fadd_rn(cy, -gcy);
+          d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        }
+        dist_s[p] = d;
+      }
+      __syncthreads();
+    }
+    for (int r = 0; r < k_l; ++r) {
+      MinPair best{3.0e38f, 0x7fffffff};
+      if (staged) {
+        for (int p = threadIdx.x; p < P; p += ASSIGN_THREADS) {
+          const float d = dist_s[p];
+          const int idx = lv.off[l] + p;
+          if (!(d < 3.0e38f) || !lex_less(pd, pi, d, idx)) continue;
+          if (lex_less(d, idx, best.d, best.i)) { best.d = d; best.i = idx; }
+        }
+      } else {
+        for (int p = threadIdx.x; p < P; p += ASSIGN_THREADS) {
+          const int h = p / lv.W[l], w = p % lv.W[l];
+          if (h >= vh || w >= vw) continue;
+          const float* a = bx + static_cast<long long>(lv.off[l] + p) * 4;
+          const float cx = __fdiv_rn(__fadd_rn(a[0], a[2]), 2.f), cy = __fdiv_rn(__fadd_rn(a[1], a[3]), 2.f);
+          const float dx = __fadd_rn(cx, -gcx), dy = __fadd_rn(cy, -gcy);
+          const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+          const int idx = lv.off[l] + p;
+          if (!lex_less(pd, pi, d, idx)) continue;   // already taken (or before the cursor)
+          if (lex_less(d, idx, best.d, best.i)) { best.d = d; best.i = idx; }
+        }
       }
       best = block_min(best, red);
       if (best.i == 0x7fffffff) break;
@@ -326,8 +355,20 @@ extern "C" int lsnet_atss_assign(int num_levels, const int* level_h, const int* 
   const long long n = static_cast<long long>(B) * lv.total;
   cudaMemsetAsync(ws_keys, 0, sizeof(unsigned long long) * static_cast<size_t>(n), st);
   if (Gmax > 0) {
-    atss_candidates_kernel<<<dim3(Gmax, B), ASSIGN_THREADS, 0, st>>>(lv, valid_hw, boxes, gt_bbox, gt_count, Gmax,
-                                                                     topk, ws_keys);
+    int pmax = 0;
+    for (int l = 0; l < lv.n; ++l) pmax = lv.H[l] * lv.W[l] > pmax ? lv.H[l] * lv.W[l] : pmax;
+    static int max_smem = -1;
+    if (max_smem < 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaFuncSetAttribute(atss_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 4096);
+    }
+    // boxes rows are 16-byte aligned (cudaMalloc'ed [B, total, 4] fp32): float4 loads in the staging pass
+    const int cap = (static_cast<size_t>(pmax) * 4 <= static_cast<size_t>(max_smem - 4096) &&
+                     reinterpret_cast<uintptr_t>(boxes) % 16 == 0) ? pmax : 0;
+    atss_candidates_kernel<<<dim3(Gmax, B), ASSIGN_THREADS, static_cast<size_t>(cap) * 4, st>>>(
+        lv, valid_hw, boxes, gt_bbox, gt_count, Gmax, topk, ws_keys, cap);
     if (int rc = check_launch("atss_candidates")) return rc;
   }
   atss_resolve_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(ws_keys, n, assign, max_overlaps);
