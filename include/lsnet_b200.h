@@ -72,6 +72,14 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
                         void* stream);
 
+/* One-pass optimizer step over flat fp32 buffers: L2 clip at max_norm (grad_norm: device scalar holding |g|; NULL or
+ * max_norm <= 0 disables the clip), then SGD with momentum and weight decay (dampening 0, no nesterov).  Replaces
+ * clip_grad_norm_ + torch.optim.SGD.step of mmcv's OptimizerHook.after_train_iter
+ * (mmcv/mmcv/runner/hooks/optimizer.py:19-28) for the GraphTrainer's flat storage. */
+int lsnet_sgd_momentum_step(float* params, const float* grads, float* momentum_buf, long long n,
+                            const float* grad_norm, float max_norm, float lr, float momentum, float weight_decay,
+                            void* stream);
+
 /* Backward-pass gradient staging: dY (fp32 if gy_fp32 else bf16; P rows of C channels, pitch ldg) -> bf16 rows of Cpad
  * channels (zero padded) in `out`, optionally masked by relu_out > 0 (bf16, the forward output of a conv+ReLU), and the
  * per-channel sum of the staged values into colsum[C] (fp32; the bias gradient, replacing

@@ -222,3 +222,44 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
         colsum);
   return check_launch("grad_prep");
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer step over the flat parameter / gradient / momentum buffers in ONE pass (mmcv OptimizerHook.after_train_iter,
+// mmcv/runner/hooks/optimizer.py:19-28: clip_grad_norm_ then torch.optim.SGD with momentum, dampening 0, no nesterov):
+//   s = min(1, max_norm / (|g| + 1e-6))          (|g| = *grad_norm, computed on the device; max_norm <= 0: no clip)
+//   g' = s * g + wd * p ;  m = momentum * m + g' ;  p = p - lr * m
+// HBM-bound: 12 bytes read + 8 bytes written per parameter.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n4,
+                    const float* __restrict__ grad_norm, float max_norm, float lr, float momentum, float wd) {
+  float s = 1.f;
+  if (max_norm > 0.f && grad_norm) s = fminf(1.f, max_norm / (__ldg(grad_norm) + 1e-6f));
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    mv.x = momentum * mv.x + (s * gv.x + wd * pv.x); pv.x -= lr * mv.x;
+    mv.y = momentum * mv.y + (s * gv.y + wd * pv.y); pv.y -= lr * mv.y;
+    mv.z = momentum * mv.z + (s * gv.z + wd * pv.z); pv.z -= lr * mv.z;
+    mv.w = momentum * mv.w + (s * gv.w + wd * pv.w); pv.w -= lr * mv.w;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+}
+
+extern "C" int lsnet_sgd_momentum_step(float* params, const float* grads, float* momentum_buf, long long n,
+                                       const float* grad_norm, float max_norm, float lr, float momentum,
+                                       float weight_decay, void* stream) {
+  if (n <= 0) return 0;
+  if ((n % 4) || (reinterpret_cast<uintptr_t>(params) % 16) || (reinterpret_cast<uintptr_t>(grads) % 16) ||
+      (reinterpret_cast<uintptr_t>(momentum_buf) % 16))
+    return set_error("lsnet_sgd_momentum_step: flat buffers must be 16-byte aligned with n %% 4 == 0 (n=%lld)", n);
+  const long long n4 = n / 4;
+  const int grid = static_cast<int>(n4 / 256 + 1 < 148LL * 8 ? n4 / 256 + 1 : 148LL * 8);
+  sgd_momentum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, momentum_buf, n4, grad_norm,
+                                                                           max_norm, lr, momentum, weight_decay);
+  return check_launch("sgd_momentum");
+}

@@ -5,6 +5,8 @@ mmcv/mmcv/runner/epoch_based_runner.py:20-47) without the reference's per-scalar
 import os
 
 import torch
+
+from . import lib as L
 import torch.distributed as dist
 from torch.nn.parallel import DistributedDataParallel as DDP
 
@@ -215,12 +217,11 @@ class GraphTrainer:
             dist.all_reduce(g)
             g.div_(dist.get_world_size())
         lr = warmup_lr(self.base_lr, self.iter)
-        if self.max_norm is not None:
-            norm = torch.linalg.vector_norm(g)
-            g.mul_((self.max_norm / (norm + 1e-6)).clamp(max=1.0))
-        g.add_(self.flat_p, alpha=self.wd)
-        self.flat_m.mul_(self.momentum).add_(g)
-        self.flat_p.add_(self.flat_m, alpha=-lr)
+        # clip + weight decay + momentum + update in one pass over the flat buffers (lsnet_sgd_momentum_step)
+        norm = torch.linalg.vector_norm(g) if self.max_norm is not None else None
+        L.call('lsnet_sgd_momentum_step', L.ptr(self.flat_p), L.ptr(g), L.ptr(self.flat_m), L.c_ll(g.numel()),
+               L.ptr(norm), L.c_f(float(self.max_norm or 0.0)), L.c_f(float(lr)), L.c_f(float(self.momentum)),
+               L.c_f(float(self.wd)), L.stream())
         self.iter += 1
         log = self.log_vars
         if sync_log:

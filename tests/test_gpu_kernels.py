@@ -424,3 +424,24 @@ def test_groupnorm_forward_backward(B, C, H, W, relu, res):
     assert _rel(gg[1], rg[1]) < 1e-2 and _rel(gg[2], rg[2]) < 1e-2
     if res:
         assert _rel(gg[3].float(), rg[3]) < 2e-2
+
+
+def test_fused_clip_sgd_step_matches_torch():
+    """lsnet_sgd_momentum_step (clip at max_norm + SGD momentum/weight-decay in one pass over the flat buffers) against
+    clip_grad_norm_ + torch.optim.SGD (mmcv OptimizerHook.after_train_iter, optimizer.py:19-28) over three steps."""
+    from lsnet_b200 import lib as L
+    torch.manual_seed(0)
+    n = 64 * 1000
+    p0 = torch.randn(n, device=DEV)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    p, m = p0.clone(), torch.zeros(n, device=DEV)
+    for step, gscale in enumerate([100.0, 0.001, 10.0]):      # clipped, unclipped, clipped
+        g = torch.randn(n, device=DEV) * gscale
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 35.0)
+        opt.step()
+        norm = torch.linalg.vector_norm(g)
+        L.call('lsnet_sgd_momentum_step', L.ptr(p), L.ptr(g), L.ptr(m), L.c_ll(n), L.ptr(norm), L.c_f(35.0), L.c_f(0.01),
+               L.c_f(0.9), L.c_f(1e-4), L.stream())
+        assert _rel(p, ref_p.detach()) < 1e-6, (step, _rel(p, ref_p.detach()))
