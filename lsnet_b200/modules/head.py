@@ -109,6 +109,8 @@ TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
 LEVEL_STREAMS = os.environ.get('LSNET_LEVEL_STREAMS', '1') == '1'
 # level groups for LEVEL_STREAMS, e.g. '0,1|2|3|4': one stream pair per group
 LEVEL_GROUPS = os.environ.get('LSNET_LEVEL_GROUPS', '0|1|2|3|4')
+# classification half of a level's refine stage on its own stream
+REFINE_SPLIT = os.environ.get('LSNET_REFINE_SPLIT', '1') == '1'
 
 
 def _level_groups(L):
@@ -348,36 +350,60 @@ class LSHead(nn.Module):
         return list(zip(cls_feats, outs))
 
     def _refine_level(self, l, L, lvl, cls_feats, brs, cls_driver, outs):
-        """lsnet_head.py:600-755 for one level: the three pyramid DCNs per branch, fusion conv + GN, refine / cls heads."""
+        """lsnet_head.py:600-755 for one level: the three pyramid DCNs per branch, fusion conv + GN, refine / cls heads.
+        The classification half only shares the (tiny) scaled offsets with the regression half, so with REFINE_SPLIT
+        it runs on a second stream of the level."""
         lvls = [l, l + 1, l + 2] if l == 0 else ([l, l - 1, l - 2] if l == L - 1 else [l, l - 1, l + 1])
         bh, bw = cls_feats[l].shape[2:]
-        offs = {br: lvl[l][1][br][2] for br in brs}
-        raws = {br: [] for br in brs}
-        cls_raws = []
+        dev = cls_feats[l].device
         B_, pc = cls_feats[l].shape[0], self.point_feat_channels
-        bufs = {br: torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16) for br in brs}
-        cls_buf = torch.empty((B_, bh, bw, 3 * pc), device=cls_feats[l].device, dtype=torch.bfloat16)
+        # the reference scales views of the offset tensor in place, so the factors accumulate over the three
+        # iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
+        offs = {br: [] for br in brs}
+        geo = []
         for j, lv in enumerate(lvls):
             sh, sw = cls_feats[lv].size(2) / bh, cls_feats[lv].size(3) / bw
-            sc = self._scale_vec(sh, sw, offs[brs[0]].device)
+            sc = self._scale_vec(sh, sw, dev)
+            geo.append((lv, sh, sw))
             for br in brs:
-                # the reference scales views of the offset tensor in place, so the factors accumulate over the
-                # three iterations (lsnet_head.py:628-633; SURVEY parity trap P1)
-                offs[br] = offs[br] * sc
-                raws[br].append(getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br], sh, sw,
-                                                                      out_slice=(bufs[br], j * pc)))
-            cls_raws.append(self.pts_cls_conv(cls_feats[lv], offs[cls_driver], sh, sw, out_slice=(cls_buf, j * pc)))
+                prev = offs[br][-1] if j else lvl[l][1][br][2]
+                offs[br].append(prev * sc)
+        cur = torch.cuda.current_stream() if dev.type == 'cuda' else None
+        side = None
+        if cur is not None and REFINE_SPLIT and TOWER_STREAMS:
+            side = _tower_stream(dev, 200 + l)
+            side.wait_stream(cur)
+            for t in offs[cls_driver]:
+                t.record_stream(side)
+
+        def cls_half():
+            cls_buf = torch.empty((B_, bh, bw, 3 * pc), device=dev, dtype=torch.bfloat16)
+            cls_raws = [self.pts_cls_conv(cls_feats[lv], offs[cls_driver][j], sh, sw, out_slice=(cls_buf, j * pc))
+                        for j, (lv, sh, sw) in enumerate(geo)]
+            t = ops.group_norm_nhwc(self.cls_af_dcn_conv(self._join(cls_buf, cls_raws)), self.cls_GN.num_groups,
+                                    self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
+                                    residual=self.cls_feat_conv(cls_feats[l]))
+            return self.pts_cls_out(t, out_fp32=True)
+
+        if side is not None:
+            with torch.cuda.stream(side):
+                cls_out = cls_half()
         for br in brs:
-            t = getattr(self, f'{br}_af_dcn_conv')(self._join(bufs[br], raws[br]))
+            buf = torch.empty((B_, bh, bw, 3 * pc), device=dev, dtype=torch.bfloat16)
+            raws = [getattr(self, f'pts_{br}_refine_conv')(lvl[lv][1][br][0], offs[br][j], sh, sw, out_slice=(buf, j * pc))
+                    for j, (lv, sh, sw) in enumerate(geo)]
+            t = getattr(self, f'{br}_af_dcn_conv')(self._join(buf, raws))
             gn = getattr(self, f'{br}_GN')
             t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
                                     residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
             t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
             outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
-        t = ops.group_norm_nhwc(self.cls_af_dcn_conv(self._join(cls_buf, cls_raws)), self.cls_GN.num_groups,
-                                self.cls_GN.weight, self.cls_GN.bias, self.cls_GN.eps, relu=True,
-                                residual=self.cls_feat_conv(cls_feats[l]))
-        outs['cls'].append(self.pts_cls_out(t, out_fp32=True))
+        if side is not None:
+            cur.wait_stream(side)
+            cls_out.record_stream(cur)
+        else:
+            cls_out = cls_half()
+        outs['cls'].append(cls_out)
 
     def forward(self, feats):
         L = len(feats)
