@@ -50,60 +50,82 @@ grad_prep_kernel(const void* __restrict__ gy, long long ldg, const __nv_bfloat16
   }
 }
 
-// Vector path (C % 8 == 0, Cpad == C, 16-byte aligned pitches, (C/8) a power of two <= 256): one thread = one 16-byte
-// vector of 8 channels, walking rows with a fixed column, so the column sums live in registers until the end.
-constexpr int PREPV_ROWS = 128;
+// Vector path (C % 8 == 0, Cpad == C, 16-byte aligned pitches, (C/8) a power of two): one thread = one 16-byte vector of
+// 8 channels, walking rows with a fixed column, so the column sums live in registers until the end.  A CTA covers a
+// slice of at most 256 channels (grid.y) x PREPV_RPT rows per row-lane (grid.x), so wide maps (the 1024 / 2048-channel
+// trunk stages) still fill the machine, and every thread keeps PREPV_U independent 16-byte loads in flight.
+constexpr int PREPV_RPT = 8;     // rows per thread
+constexpr int PREPV_U = 4;       // loads in flight per thread
 template <bool FP32_IN>
 __global__ void __launch_bounds__(PREP_THREADS)
 grad_prep_vec_kernel(const void* __restrict__ gy, long long ldg, const __nv_bfloat16* __restrict__ relu_out,
                      long long ldo, long long P, int C, __nv_bfloat16* __restrict__ out, long long ldout,
                      float* __restrict__ colsum) {
-  extern __shared__ float sm[];   // [C]
+  __shared__ float sm[256];        // column sums of this CTA's channel slice
   const int vpp = C / 8;
+  const int vpc = vpp < 32 ? vpp : 32;              // vectors per row handled by this CTA
+  const int lanes = PREP_THREADS / vpc;             // row lanes
+  const int v = blockIdx.y * vpc + threadIdx.x % vpc;
+  const int rl = threadIdx.x / vpc;
   if (colsum) {
-    for (int i = threadIdx.x; i < C; i += PREP_THREADS) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 256; i += PREP_THREADS) sm[i] = 0.f;
     __syncthreads();
   }
-  const int v = threadIdx.x % vpp, rstep = PREP_THREADS / vpp;
-  const long long r0 = static_cast<long long>(blockIdx.x) * PREPV_ROWS;
-  const long long r1 = min(P, r0 + PREPV_ROWS);
+  const long long r0 = static_cast<long long>(blockIdx.x) * lanes * PREPV_RPT + rl;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (long long r = r0 + threadIdx.x / vpp; r < r1; r += rstep) {
-    float f[8];
-    if (FP32_IN) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8 + 4));
-      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    } else {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(gy) + r * ldg + v * 8));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  for (int k0 = 0; k0 < PREPV_RPT; k0 += PREPV_U) {
+    float f[PREPV_U][8];
+    uint4 mk[PREPV_U];
+#pragma unroll
+    for (int u = 0; u < PREPV_U; ++u) {
+      const long long r = r0 + static_cast<long long>(k0 + u) * lanes;
+      const bool ok = r < P;
+      if (FP32_IN) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (ok) {
+          a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8));
+          b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(gy) + r * ldg + v * 8 + 4));
+        }
+        f[u][0] = a.x; f[u][1] = a.y; f[u][2] = a.z; f[u][3] = a.w; f[u][4] = b.x; f[u][5] = b.y; f[u][6] = b.z; f[u][7] = b.w;
+      } else {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(gy) + r * ldg + v * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[u][2 * i] = t.x; f[u][2 * i + 1] = t.y; }
+      }
+      mk[u] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // bf16 1.0: keep everything
+      if (relu_out && ok) mk[u] = __ldg(reinterpret_cast<const uint4*>(relu_out + r * ldo + v * 8));
     }
-    if (relu_out) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(relu_out + r * ldo + v * 8));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int u = 0; u < PREPV_U; ++u) {
+      const long long r = r0 + static_cast<long long>(k0 + u) * lanes;
+      if (r >= P) continue;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&mk[u]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 t = __bfloat1622float2(h[i]);
-        if (!(t.x > 0.f)) f[2 * i] = 0.f;
-        if (!(t.y > 0.f)) f[2 * i + 1] = 0.f;
+        if (!(t.x > 0.f)) f[u][2 * i] = 0.f;
+        if (!(t.y > 0.f)) f[u][2 * i + 1] = 0.f;
       }
-    }
-    if (out)     // out == nullptr: column sums only (the gradient is already in the layout the GEMMs consume)
-      *reinterpret_cast<uint4*>(out + r * ldout + v * 8) =
-          make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      if (out)     // out == nullptr: column sums only (the gradient is already in the layout the GEMMs consume)
+        *reinterpret_cast<uint4*>(out + r * ldout + v * 8) =
+            make_uint4(pack_bf16x2(f[u][0], f[u][1]), pack_bf16x2(f[u][2], f[u][3]), pack_bf16x2(f[u][4], f[u][5]),
+                       pack_bf16x2(f[u][6], f[u][7]));
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      for (int e = 0; e < 8; ++e) acc[e] += f[u][e];
+    }
   }
   if (colsum) {
+    const int cl = (threadIdx.x % vpc) * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&sm[v * 8 + e], acc[e]);
+    for (int e = 0; e < 8; ++e) atomicAdd(&sm[cl + e], acc[e]);
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += PREP_THREADS)
-      if (sm[i] != 0.f) atomicAdd(&colsum[i], sm[i]);
+    for (int i = threadIdx.x; i < vpc * 8; i += PREP_THREADS)
+      if (sm[i] != 0.f) atomicAdd(&colsum[blockIdx.y * vpc * 8 + i], sm[i]);
   }
 }
 
@@ -194,18 +216,20 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
   const int vpp = C / 8;
-  const bool vec = (C % 8 == 0) && Cpad == C && vpp <= PREP_THREADS && (vpp & (vpp - 1)) == 0 &&
+  const bool vec = (C % 8 == 0) && Cpad == C && vpp >= 1 && (vpp & (vpp - 1)) == 0 &&
                    (ldg % (gy_fp32 ? 4 : 8) == 0) && (!out || ldout % 8 == 0) && (!relu_out || ldo % 8 == 0) &&
                    (reinterpret_cast<uintptr_t>(gy) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                    (!relu_out || reinterpret_cast<uintptr_t>(relu_out) % 16 == 0);
   if (vec) {
-    const int gridv = static_cast<int>((P + PREPV_ROWS - 1) / PREPV_ROWS);
+    const int vpc = vpp < 32 ? vpp : 32;
+    const int rows_per_cta = (PREP_THREADS / vpc) * PREPV_RPT;
+    const dim3 gridv(static_cast<unsigned>((P + rows_per_cta - 1) / rows_per_cta), static_cast<unsigned>(vpp / vpc));
     if (gy_fp32)
-      grad_prep_vec_kernel<true><<<gridv, PREP_THREADS, sizeof(float) * C, st>>>(
+      grad_prep_vec_kernel<true><<<gridv, PREP_THREADS, 0, st>>>(
           gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, static_cast<__nv_bfloat16*>(out), ldout,
           colsum);
     else
-      grad_prep_vec_kernel<false><<<gridv, PREP_THREADS, sizeof(float) * C, st>>>(
+      grad_prep_vec_kernel<false><<<gridv, PREP_THREADS, 0, st>>>(
           gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, static_cast<__nv_bfloat16*>(out), ldout,
           colsum);
     return check_launch("grad_prep_vec");
