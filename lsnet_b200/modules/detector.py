@@ -19,7 +19,10 @@ def parse_losses(losses, sync_log=False):
         if isinstance(value, torch.Tensor):
             log_vars[name] = value.mean()
         elif isinstance(value, (list, tuple)):
-            log_vars[name] = sum(v.mean() for v in value)
+            if all(v.dim() == 0 for v in value) and len(value) > 1:
+                log_vars[name] = torch.stack(list(value)).sum()       # one reduction instead of len(value) scalar kernels
+            else:
+                log_vars[name] = sum(v.mean() for v in value)
         else:
             raise TypeError(f'{name} is not a tensor or list of tensors')
     loss = sum(v for k, v in log_vars.items() if 'loss' in k)

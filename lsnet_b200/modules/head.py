@@ -131,6 +131,8 @@ def _tower_stream(device, idx=0):
 import contextlib
 _nullctx = contextlib.nullcontext
 
+from .losses import FocalLoss  # noqa: E402
+
 BRANCHES = {'bbox': ['bbox'], 'segm': ['segm'], 'pose_bbox': ['bbox', 'pose'], 'pose_kbox': ['pose']}
 LOSS_KIND = {'bbox': 'bbox', 'segm': 'polygon', 'pose': 'keypoint'}
 
@@ -611,9 +613,18 @@ class LSHead(nn.Module):
         avg_init = npos_init.clamp(min=1).sum().float()
         avg_ref = npos_ref.clamp(min=1).sum().float()
 
-        losses = {'loss_cls': []}
+        # Per-level loss terms as raw sums; the scalar arithmetic (x loss_weight / avg_factor) is applied ONCE per term on
+        # the stacked per-level vector instead of level by level (the reference's per-level scalar ops are ~300 one-thread
+        # kernels on the critical path between forward and backward).
+        raw = {'loss_cls': []}
+        scale = {}
+        fast_cls = isinstance(self.loss_cls, FocalLoss) and self.loss_cls.reduction == 'mean'
+        if fast_cls:
+            scale['loss_cls'] = self.loss_cls.loss_weight / avg_ref
         for br in brs:
-            losses[f'loss_{br}_init'], losses[f'loss_{br}_refine'] = [], []
+            raw[f'loss_{br}_init'], raw[f'loss_{br}_refine'] = [], []
+            scale[f'loss_{br}_init'] = getattr(self, f'loss_{br}_init').loss_weight / avg_init
+            scale[f'loss_{br}_refine'] = getattr(self, f'loss_{br}_refine').loss_weight / avg_ref
         B = cls_scores[0].shape[0]
         for l, s in enumerate(self.point_strides):
             off, P = int(pyr.offsets[l]), pyr.num_level[l]
@@ -622,16 +633,25 @@ class LSHead(nn.Module):
             rows = torch.as_strided(cs, (B * H * W, C), (cs.stride(3), 1))
             lab = labels[:, off:off + P].reshape(-1)
             lw = lweights[:, off:off + P].reshape(-1)
-            losses['loss_cls'].append(self.loss_cls(rows, lab, lw, avg_factor=avg_ref))
+            if fast_cls:
+                raw['loss_cls'].append(ops.sigmoid_focal_loss_sum(rows.float(), lab, lw, self.loss_cls.gamma,
+                                                                  self.loss_cls.alpha))
+            else:
+                raw['loss_cls'].append(self.loss_cls(rows, lab, lw, avg_factor=avg_ref))
             for br in brs:
                 kind = LOSS_KIND[br]
-                for stage, a, avg in (('init', a_init, avg_init), ('refine', a_ref, avg_ref)):
+                for stage, a in (('init', a_init), ('refine', a_ref)):
                     mod = getattr(self, f'loss_{br}_{stage}')
                     pred = preds[br][0 if stage == 'init' else 1][l]
-                    total = ops.cross_iou_level_loss(pred, a, off, float(s), float(self.point_base_scale), tables[br],
-                                                     gt_bb, gt_vs if kind == 'keypoint' else None, loss_type=kind,
-                                                     eps=mod.eps, alpha=mod.alpha, pstride=mod.stride)
-                    losses[f'loss_{br}_{stage}'].append(mod.loss_weight * total / avg)
+                    raw[f'loss_{br}_{stage}'].append(
+                        ops.cross_iou_level_loss(pred, a, off, float(s), float(self.point_base_scale), tables[br], gt_bb,
+                                                 gt_vs if kind == 'keypoint' else None, loss_type=kind, eps=mod.eps,
+                                                 alpha=mod.alpha, pstride=mod.stride))
+        losses = {}
+        for k, v in raw.items():
+            if k in scale:
+                v = list((torch.stack(v) * scale[k]).unbind(0))
+            losses[k] = v
         if return_aux:
             return losses, dict(assign_init=a_init, assign_refine=a_ref, labels=labels, label_weights=lweights,
                                 npos_init=npos_init, npos_refine=npos_ref, boxes=boxes)
