@@ -72,6 +72,24 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
                         void* stream);
 
+/* LSHead element-wise glue.  pred_reg: o fp32 [P, ldo] = output of pts_*_init_out (n_out channels); sp[P, ldsp] =
+ * softplus(o[:, :n_sp]) (nn.Softplus defaults, lsnet_head.py:96); off[P, ldoff] = the n_off DCN sampling offsets of
+ * LSHead.get_pred_reg (lsnet_head.py:372-400) minus dcn_base_offset: entry j is the signed maximum of the slot pair
+ * (sp[src[j]], sp[src[j]+1]) (mode 0; the '-' slot wins ties and is negated) or the raw channel o[src[j]] (mode 1, the 8
+ * free offsets of task 'bbox').  src / mode / base are HOST arrays of n_off entries.  Backward: go[P, ldgo] (n_out
+ * channels) from gsp (may be NULL) and goff (may be NULL), the offset path scaled by gradient_mul
+ * ((1 - gm) * reg.detach() + gm * reg, lsnet_head.py:585-587).
+ * add_softplus: out = softplus(t + s) (gy NULL) or gy * softplus'(t + s) (refine = softplus(raw + init.detach()),
+ * lsnet_head.py:735-755). */
+int lsnet_pred_reg_fwd(const float* o, long long ldo, long long P, int n_sp, int n_out, int n_off, const int* src,
+                       const int* mode, const float* base, float* sp, long long ldsp, float* off, long long ldoff,
+                       void* stream);
+int lsnet_pred_reg_bwd(const float* o, long long ldo, long long P, int n_sp, int n_out, int n_off, const int* src,
+                       const int* mode, const float* base, const float* gsp, long long ldgsp, const float* goff,
+                       long long ldgoff, float gradient_mul, float* go, long long ldgo, void* stream);
+int lsnet_add_softplus(const float* t, long long ldt, const float* s, long long lds, const float* gy, long long ldgy,
+                       long long P, int C, float* out, long long ldout, void* stream);
+
 /* One-pass optimizer step over flat fp32 buffers: L2 clip at max_norm (grad_norm: device scalar holding |g|; NULL or
  * max_norm <= 0 disables the clip), then SGD with momentum and weight decay (dampening 0, no nesterov).  Replaces
  * clip_grad_norm_ + torch.optim.SGD.step of mmcv's OptimizerHook.after_train_iter

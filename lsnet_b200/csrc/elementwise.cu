@@ -287,3 +287,154 @@ extern "C" int lsnet_sgd_momentum_step(float* params, const float* grads, float*
                                                                            max_norm, lr, momentum, weight_decay);
   return check_launch("sgd_momentum");
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// LSHead element-wise glue (lsnet_head.py:372-400, 502-598, 735-755) as two kernels each way instead of ~20 torch ops
+// per level:
+//   pred_reg:      sp = softplus(o[:, :n_sp])  (beta 1, threshold 20)  and the 18 DCN sampling offsets
+//                  off[j] = signed_pair(sp[src_j], sp[src_j + 1]) - base[j]   (mode 0: '-' slot wins ties and is negated)
+//                  off[j] = o[src_j] - base[j]                                 (mode 1: free offset channels of 'bbox')
+//                  backward: d o = softplus'(o) * (d sp + gradient_mul * routed d off)   (the reference mixes
+//                  (1 - gm) * reg.detach() + gm * reg, i.e. value 1x, gradient gm x)
+//   add_softplus:  y = softplus(t + s) with s detached (refine = softplus(raw + init.detach()))
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PR_MAX_OUT = 160;
+constexpr int PR_MAX_OFF = 32;
+struct PredRegTab {
+  int n_off;                        // DCN offset channels (2 * kernel points)
+  short src[PR_MAX_OFF];            // first source channel of offset j
+  signed char mode[PR_MAX_OFF];     // 0: signed pair (src, src+1) of sp; 1: raw channel src
+  float base[PR_MAX_OFF];           // dcn_base_offset
+  signed char inv_j[PR_MAX_OUT];    // for every channel of o: the offset it feeds (-1: none) ...
+  signed char inv_slot[PR_MAX_OUT]; // ... and its slot in the pair (0 / 1; 2: raw)
+};
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad_f(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+pred_reg_fwd_kernel(const float* __restrict__ o, long long ldo, long long P, int n_sp, const PredRegTab tab,
+                    float* __restrict__ sp, long long ldsp, float* __restrict__ off, long long ldoff) {
+  const long long n1 = P * n_sp, n2 = P * tab.n_off;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n1 + n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < n1) {
+      const long long p = i / n_sp;
+      const int c = static_cast<int>(i - p * n_sp);
+      sp[p * ldsp + c] = softplus_f(__ldg(o + p * ldo + c));
+    } else {
+      const long long k = i - n1, p = k / tab.n_off;
+      const int j = static_cast<int>(k - p * tab.n_off);
+      const float* row = o + p * ldo + tab.src[j];
+      float v;
+      if (tab.mode[j] == 0) {
+        const float a = softplus_f(__ldg(row)), b = softplus_f(__ldg(row + 1));
+        v = (a >= b) ? -a : b;      // torch.max returns the first maximum: the '-' slot wins ties
+      } else {
+        v = __ldg(row);
+      }
+      off[p * ldoff + j] = v - tab.base[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pred_reg_bwd_kernel(const float* __restrict__ o, long long ldo, long long P, int n_sp, int n_out, const PredRegTab tab,
+                    const float* __restrict__ gsp, long long ldgsp, const float* __restrict__ goff, long long ldgoff,
+                    float gmul, float* __restrict__ go, long long ldgo) {
+  const long long n = P * n_out;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / n_out;
+    const int c = static_cast<int>(i - p * n_out);
+    float g = (c < n_sp && gsp) ? __ldg(gsp + p * ldgsp + c) : 0.f;
+    const int j = tab.inv_j[c];
+    if (j >= 0 && goff) {
+      const float gj = gmul * __ldg(goff + p * ldgoff + j);
+      const int slot = tab.inv_slot[c];
+      if (slot == 2) {
+        g += gj;
+      } else {
+        const float* row = o + p * ldo + tab.src[j];
+        const float a = softplus_f(__ldg(row)), b = softplus_f(__ldg(row + 1));
+        const int sel = (a >= b) ? 0 : 1;
+        if (slot == sel) g += sel == 0 ? -gj : gj;
+      }
+    }
+    if (c < n_sp) g *= softplus_grad_f(__ldg(o + p * ldo + c));
+    go[p * ldgo + c] = g;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+add_softplus_kernel(const float* __restrict__ t, long long ldt, const float* __restrict__ s, long long lds,
+                    const float* __restrict__ gy, long long ldgy, long long P, int C, float* __restrict__ out,
+                    long long ldout) {
+  const long long n = P * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / C;
+    const int c = static_cast<int>(i - p * C);
+    const float x = __ldg(t + p * ldt + c) + __ldg(s + p * lds + c);
+    out[p * ldout + c] = BWD ? __ldg(gy + p * ldgy + c) * softplus_grad_f(x) : softplus_f(x);
+  }
+}
+
+static int ew_grid(long long n) {
+  const long long b = (n + 255) / 256;
+  return static_cast<int>(b < 148LL * 16 ? (b < 1 ? 1 : b) : 148LL * 16);
+}
+
+static int fill_tab(PredRegTab* tab, int n_off, const int* src, const int* mode, const float* base, int n_sp, int n_out) {
+  if (n_off < 1 || n_off > PR_MAX_OFF || n_out > PR_MAX_OUT || n_sp > n_out || n_sp < 0)
+    return set_error("lsnet_pred_reg: unsupported sizes (n_off=%d n_sp=%d n_out=%d)", n_off, n_sp, n_out);
+  tab->n_off = n_off;
+  for (int c = 0; c < PR_MAX_OUT; ++c) { tab->inv_j[c] = -1; tab->inv_slot[c] = 0; }
+  for (int j = 0; j < n_off; ++j) {
+    const int last = src[j] + (mode[j] == 0 ? 1 : 0);
+    if (src[j] < 0 || last >= n_out || (mode[j] == 0 && last >= n_sp) || (mode[j] != 0 && mode[j] != 1))
+      return set_error("lsnet_pred_reg: bad table entry %d (src=%d mode=%d)", j, src[j], mode[j]);
+    tab->src[j] = static_cast<short>(src[j]); tab->mode[j] = static_cast<signed char>(mode[j]); tab->base[j] = base[j];
+    if (mode[j] == 0) {
+      tab->inv_j[src[j]] = static_cast<signed char>(j); tab->inv_slot[src[j]] = 0;
+      tab->inv_j[src[j] + 1] = static_cast<signed char>(j); tab->inv_slot[src[j] + 1] = 1;
+    } else {
+      tab->inv_j[src[j]] = static_cast<signed char>(j); tab->inv_slot[src[j]] = 2;
+    }
+  }
+  return 0;
+}
+
+extern "C" int lsnet_pred_reg_fwd(const float* o, long long ldo, long long P, int n_sp, int n_out, int n_off,
+                                  const int* src, const int* mode, const float* base, float* sp, long long ldsp,
+                                  float* off, long long ldoff, void* stream) {
+  if (P <= 0) return 0;
+  PredRegTab tab;
+  if (int rc = fill_tab(&tab, n_off, src, mode, base, n_sp, n_out)) return rc;
+  pred_reg_fwd_kernel<<<ew_grid(P * (n_sp + n_off)), 256, 0, static_cast<cudaStream_t>(stream)>>>(o, ldo, P, n_sp, tab, sp,
+                                                                                                  ldsp, off, ldoff);
+  return check_launch("pred_reg_fwd");
+}
+
+extern "C" int lsnet_pred_reg_bwd(const float* o, long long ldo, long long P, int n_sp, int n_out, int n_off,
+                                  const int* src, const int* mode, const float* base, const float* gsp, long long ldgsp,
+                                  const float* goff, long long ldgoff, float gradient_mul, float* go, long long ldgo,
+                                  void* stream) {
+  if (P <= 0) return 0;
+  PredRegTab tab;
+  if (int rc = fill_tab(&tab, n_off, src, mode, base, n_sp, n_out)) return rc;
+  pred_reg_bwd_kernel<<<ew_grid(P * n_out), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      o, ldo, P, n_sp, n_out, tab, gsp, ldgsp, goff, ldgoff, gradient_mul, go, ldgo);
+  return check_launch("pred_reg_bwd");
+}
+
+extern "C" int lsnet_add_softplus(const float* t, long long ldt, const float* s, long long lds, const float* gy,
+                                  long long ldgy, long long P, int C, float* out, long long ldout, void* stream) {
+  if (P <= 0 || C <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gy) add_softplus_kernel<true><<<ew_grid(P * C), 256, 0, st>>>(t, ldt, s, lds, gy, ldgy, P, C, out, ldout);
+  else add_softplus_kernel<false><<<ew_grid(P * C), 256, 0, st>>>(t, ldt, s, lds, nullptr, 0, P, C, out, ldout);
+  return check_launch("add_softplus");
+}

@@ -109,6 +109,8 @@ TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
 LEVEL_STREAMS = os.environ.get('LSNET_LEVEL_STREAMS', '1') == '1'
 # level groups for LEVEL_STREAMS, e.g. '0,1|2|3|4': one stream pair per group
 LEVEL_GROUPS = os.environ.get('LSNET_LEVEL_GROUPS', '0|1|2|3|4')
+# softplus / get_pred_reg / refine softplus on the library's fused element-wise kernels (torch ops otherwise)
+HEAD_GLUE = os.environ.get('LSNET_HEAD_GLUE', '1') == '1'
 # classification half of a level's refine stage on its own stream
 REFINE_SPLIT = os.environ.get('LSNET_REFINE_SPLIT', '1') == '1'
 
@@ -168,6 +170,7 @@ class LSHead(nn.Module):
         assert self.dcn_kernel % 2 == 1, 'The points number should be an odd square number.'
         base = np.arange(-self.dcn_pad, self.dcn_pad + 1).astype(np.float64)
         base_offset = np.stack([np.repeat(base, self.dcn_kernel), np.tile(base, self.dcn_kernel)], axis=1).reshape(-1)
+        self._base_offset_list = [float(v) for v in base_offset]
         self.register_buffer('dcn_base_offset', torch.tensor(base_offset, dtype=torch.float32).view(1, -1, 1, 1),
                              persistent=False)
         if train_cfg:
@@ -303,6 +306,12 @@ class LSHead(nn.Module):
                 feat = m(feat)
             hid = getattr(self, f'pts_{br}_init_conv')(feat, relu=True)
             o = getattr(self, f'pts_{br}_init_out')(hid, out_fp32=True)
+            if HEAD_GLUE and o.is_cuda:
+                # softplus + get_pred_reg + gradient-mul mix + base offset: one kernel each way (ops/headglue.py)
+                n_sp, src, mode = ops.pred_reg_table(br, self.num_vectors, self.num_kernel_points, o.shape[1])
+                sp, off = ops.pred_reg(o, n_sp, src, mode, self._base_offset_list, self.gradient_mul)
+                out[br] = (feat, sp, off)
+                continue
             if br == 'bbox':
                 sp = self.softplus(o[:, :20])
                 reg = self.get_pred_reg(sp, o[:, 20:])
@@ -399,7 +408,10 @@ class LSHead(nn.Module):
             t = ops.group_norm_nhwc(t, gn.num_groups, gn.weight, gn.bias, gn.eps, relu=True,
                                     residual=getattr(self, f'{br}_feat_conv')(lvl[l][1][br][0]))
             t = getattr(self, f'pts_{br}_refine_out')(t, out_fp32=True)
-            outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
+            if HEAD_GLUE and t.is_cuda:
+                outs[br + '_refine'].append(ops.add_softplus(t, lvl[l][1][br][1]))
+            else:
+                outs[br + '_refine'].append(self.softplus(t + lvl[l][1][br][1].detach()))
         if side is not None:
             cur.wait_stream(side)
             cls_out.record_stream(cur)

@@ -445,3 +445,57 @@ def test_fused_clip_sgd_step_matches_torch():
         L.call('lsnet_sgd_momentum_step', L.ptr(p), L.ptr(g), L.ptr(m), L.c_ll(n), L.ptr(norm), L.c_f(35.0), L.c_f(0.01),
                L.c_f(0.9), L.c_f(1e-4), L.stream())
         assert _rel(p, ref_p.detach()) < 1e-6, (step, _rel(p, ref_p.detach()))
+
+
+@pytest.mark.parametrize('branch,num_vectors,n_out', [('bbox', 4, 28), ('segm', 36, 148), ('pose', 17, 72)])
+def test_head_glue_kernels_vs_torch(branch, num_vectors, n_out):
+    """lsnet_pred_reg_fwd/bwd and lsnet_add_softplus against the reference's torch formulation
+    (LSHead.get_pred_reg + softplus + gradient-mul mix, lsnet_head.py:372-400,585-587,735-755), values and gradients."""
+    import math
+    ops = _ops()
+    gmul = 0.1
+    g = torch.Generator().manual_seed(5)
+    o = (torch.randn(2, n_out, 7, 9, generator=g) * 3).to(DEV)
+    o[0, 0, 0, 0] = 25.0                      # softplus threshold branch
+    o[0, 2, 1, 1] = o[0, 3, 1, 1]             # tie inside a pair: the '-' slot wins
+    base = [float(v) for v in np.stack([np.repeat(np.arange(-1, 2.), 3), np.tile(np.arange(-1, 2.), 3)], 1).reshape(-1)]
+    n_sp, src, mode = ops.pred_reg_table(branch, num_vectors, 9, n_out)
+
+    def signed_pairs(t):
+        r = t.reshape(t.shape[0], -1, 2, *t.shape[2:])
+        val, ind = r.max(dim=2)
+        return torch.where(ind == 0, -val, val)
+
+    def ref_fn(x):
+        sp = F.softplus(x[:, :n_sp])
+        if branch == 'bbox':
+            reg = torch.cat((signed_pairs(sp), x[:, n_sp:]), 1)
+        else:
+            r = sp.reshape(sp.shape[0], -1, 4, *sp.shape[2:])
+            cts, polys = r[:, -1:], r[:, :-1]
+            sel = polys[:, ::math.ceil(num_vectors / 8)] if branch == 'segm' else polys[:, 1::2]
+            offs = torch.cat([sel, cts], 1)
+            reg = signed_pairs(offs.reshape(offs.shape[0], -1, *offs.shape[3:]))
+        reg = (1 - gmul) * reg.detach() + gmul * reg
+        return sp, reg - torch.tensor(base, device=x.device).view(1, -1, 1, 1)
+
+    gsp = torch.randn(2, n_sp, 7, 9, generator=g).to(DEV)
+    goff = torch.randn(2, 18, 7, 9, generator=g).to(DEV)
+    xr = o.clone().requires_grad_(True)
+    sp_r, off_r = ref_fn(xr)
+    (sp_r * gsp).sum().add((off_r * goff).sum()).backward()
+    xg = o.clone().requires_grad_(True)
+    sp, off = ops.pred_reg(xg, n_sp, src, mode, base, gmul)
+    assert sp.shape == sp_r.shape and off.shape == off_r.shape
+    assert torch.allclose(sp, sp_r, rtol=1e-6, atol=1e-6) and torch.allclose(off, off_r, rtol=1e-6, atol=1e-6)
+    (sp * gsp).sum().add((off * goff).sum()).backward()
+    assert torch.allclose(xg.grad, xr.grad, rtol=1e-5, atol=1e-6), float((xg.grad - xr.grad).abs().max())
+    # refine = softplus(raw + init.detach())
+    t = torch.randn(2, n_sp, 7, 9, generator=g).to(DEV)
+    tr, tg = t.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    yr = F.softplus(tr + sp_r.detach())
+    yg = ops.add_softplus(tg, sp.detach())
+    assert torch.allclose(yg, yr, rtol=1e-6, atol=1e-6)
+    (yr * gsp).sum().backward()
+    (yg * gsp).sum().backward()
+    assert torch.allclose(tg.grad, tr.grad, rtol=1e-5, atol=1e-6)
