@@ -284,8 +284,10 @@ def run_gpu(args, rank, world, local_rank):
     # eager: events of all K steps.  graph: one extra replay of the INSTRUMENTED capture of the same step right after
     # the timed region (external event-record nodes; the timed graph itself carries no instrumentation)
     timed_steps = 1 if graph_mode else args.steps
+    serial_ms = None
     if graph_mode:
-        tr.replay_instrumented()
+        tr.replay_instrumented()                  # warm (first replay of this graph)
+        serial_ms = tr.replay_instrumented()
         torch.cuda.synchronize()
     classes = {}
     for cls, name in enumerate(['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)',
@@ -327,7 +329,10 @@ def run_gpu(args, rank, world, local_rank):
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peaks['hbm'], unit='GB/s',
                     frac=achieved / peaks['hbm'], traffic=None)
     roof.update(peak_source=peaks['src'] + (' sustained' if 'gemm' in dom else ''),
-                share_of_step=c['ms'] / (ms * timed_steps / args.steps), avg_launch_ms=per_launch_ms,
+                # graph mode: kernel classes are timed in a SERIALISED instrumented replay of the same step (stream
+                # parallelism off, every kernel alone on the GPU, like an ncu launch list); shares are of that replay
+                share_of_step=c['ms'] / (serial_ms if serial_ms else ms * timed_steps / args.steps),
+                serialized_step_ms=serial_ms, avg_launch_ms=per_launch_ms,
                 launches_timed=c['launches'], timed_steps=timed_steps,
                 classes={k: dict(ms_per_step=v['ms'] / timed_steps, launches_per_step=v['launches'] / timed_steps,
                                  achieved=(v['work'] / (v['ms'] / 1e3) / (1e12 if 'gemm' in k else 1e9)) if v['ms'] > 0 else 0.0,

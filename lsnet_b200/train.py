@@ -171,17 +171,31 @@ class GraphTrainer:
         if self.kernel_timing:
             # a second, instrumented capture of the same step: external event-record nodes around every library
             # kernel.  Kept apart from the graph that is timed end-to-end because ~500 event nodes perturb it.
-            lib.lsnet_timing_reset()
-            lib.lsnet_timing_enable(1)
-            self.graph_timed = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_timed, capture_error_mode='thread_local'):
-                self._fwd_bwd()
-            lib.lsnet_timing_enable(0)
+            # SERIALISED: the head's stream parallelism is switched off for this capture, so every kernel runs alone and
+            # its event-bracketed duration is the kernel's own (as in an ncu launch list), not a share of a busy GPU.
+            from .modules import head as _head
+            saved = (_head.TOWER_STREAMS, _head.LEVEL_STREAMS, _head.REFINE_SPLIT)
+            _head.TOWER_STREAMS = _head.LEVEL_STREAMS = _head.REFINE_SPLIT = False
+            try:
+                lib.lsnet_timing_reset()
+                lib.lsnet_timing_enable(1)
+                self.graph_timed = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_timed, capture_error_mode='thread_local'):
+                    self._fwd_bwd()
+                lib.lsnet_timing_enable(0)
+            finally:
+                _head.TOWER_STREAMS, _head.LEVEL_STREAMS, _head.REFINE_SPLIT = saved
             gemm_ops._PACK_CACHE.clear()
 
     def replay_instrumented(self):
-        """One forward+backward through the instrumented graph (gradients only; no optimizer step)."""
+        """One forward+backward through the instrumented, serialised graph (gradients only; no optimizer step).
+        Returns its duration in ms (CUDA events)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         self.graph_timed.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
 
     def load_batch(self, batch):
         """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host).  The packed GT goes
