@@ -118,7 +118,8 @@ REFINE_SPLIT = os.environ.get('LSNET_REFINE_SPLIT', '1') == '1'
 def _level_groups(L):
     gs = [[int(t) for t in g.split(',') if int(t) < L] for g in LEVEL_GROUPS.split('|')]
     gs = [g for g in gs if g]
-    assert sorted(sum(gs, [])) == list(range(L)), LEVEL_GROUPS
+    if sorted(sum(gs, [])) != list(range(L)):      # a pyramid with another depth than the spec: one group per level
+        gs = [[l] for l in range(L)]
     return gs
 _TOWER_STREAM = {}
 
