@@ -215,7 +215,11 @@ def run_reference(args, rank, world):
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=WORKLOAD, cpu_sample=sample),
+                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
+                            l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
+                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights',
+                            step_mode='reference path on the host cores (oracle port, fp32), rank 0 only',
+                            cpu_sample=sample),
                 cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
                 e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
