@@ -36,6 +36,11 @@ METRIC = 'images/sec training step, LSNet R50-FPN 800x1333'
 WORKLOAD = 'LSNet-bbox R50-FPN 800x1333 (padded 800x1344) bf16, batch 4/GPU, synthetic COCO-shaped'
 IMG_HW = (800, 1333)
 BATCH = 4
+# kernel classes of lsnet_timing_collect (lsnet_internal.h): name -> what bounds it ('tensor': work = FLOPs, 'hbm': bytes)
+CLASS_NAMES = ['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)', 'dcn_im2col(gather)',
+               'dcn_col2im(scatter)', 'dcn_fused_fwd(gather->smem->tcgen05)', 'dcn_fused_wgrad(gather->smem->tcgen05)',
+               'dcn_fused_bwd_data(tcgen05->scatter)']
+TENSOR_BOUND = ('gemm', 'dcn_fused')
 
 
 def usable_cores():
@@ -294,11 +299,11 @@ def run_gpu(args, rank, world, local_rank):
         serial_ms = tr.replay_instrumented()
         torch.cuda.synchronize()
     classes = {}
-    for cls, name in enumerate(['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)',
-                                'dcn_im2col(gather)', 'dcn_col2im(scatter)']):
+    for cls, name in enumerate(CLASS_NAMES):
         tms, n, work = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
         lib.lsnet_timing_collect(cls, ctypes.byref(tms), ctypes.byref(n), ctypes.byref(work))
-        classes[name] = dict(ms=tms.value, launches=n.value, work=work.value)
+        if n.value:
+            classes[name] = dict(ms=tms.value, launches=n.value, work=work.value)
     if not graph_mode:
         lib.lsnet_timing_reset()
     # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
@@ -324,7 +329,7 @@ def run_gpu(args, rank, world, local_rank):
     dom = max(classes, key=lambda k: classes[k]['ms'])
     c = classes[dom]
     per_launch_ms = c['ms'] / max(1, c['launches'])
-    if 'gemm' in dom:
+    if any(t in dom for t in TENSOR_BOUND):
         achieved = c['work'] / (c['ms'] / 1e3) / 1e12 if c['ms'] > 0 else 0.0
         roof = dict(bound='tensor', kernel=dom, achieved=achieved, peak=peaks['tf_sustained'], unit='TFLOP/s',
                     frac=achieved / peaks['tf_sustained'], traffic=None)
@@ -332,15 +337,16 @@ def run_gpu(args, rank, world, local_rank):
         achieved = c['work'] / (c['ms'] / 1e3) / 1e9 if c['ms'] > 0 else 0.0
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peaks['hbm'], unit='GB/s',
                     frac=achieved / peaks['hbm'], traffic=None)
-    roof.update(peak_source=peaks['src'] + (' sustained' if 'gemm' in dom else ''),
+    roof.update(peak_source=peaks['src'] + (' sustained' if any(t in dom for t in TENSOR_BOUND) else ''),
                 # graph mode: kernel classes are timed in a SERIALISED instrumented replay of the same step (stream
                 # parallelism off, every kernel alone on the GPU, like an ncu launch list); shares are of that replay
                 share_of_step=c['ms'] / (serial_ms if serial_ms else ms * timed_steps / args.steps),
                 serialized_step_ms=serial_ms, avg_launch_ms=per_launch_ms,
                 launches_timed=c['launches'], timed_steps=timed_steps,
                 classes={k: dict(ms_per_step=v['ms'] / timed_steps, launches_per_step=v['launches'] / timed_steps,
-                                 achieved=(v['work'] / (v['ms'] / 1e3) / (1e12 if 'gemm' in k else 1e9)) if v['ms'] > 0 else 0.0,
-                                 unit='TFLOP/s' if 'gemm' in k else 'GB/s') for k, v in classes.items()})
+                                 achieved=(v['work'] / (v['ms'] / 1e3) / (1e12 if any(t in k for t in TENSOR_BOUND) else 1e9))
+                                 if v['ms'] > 0 else 0.0,
+                                 unit='TFLOP/s' if any(t in k for t in TENSOR_BOUND) else 'GB/s') for k, v in classes.items()})
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:

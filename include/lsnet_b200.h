@@ -14,9 +14,14 @@
 #ifndef LSNET_B200_H_
 #define LSNET_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* element type of activations / packed weights (accumulation is always fp32) */
+enum { LSNET_DTYPE_BF16 = 0 };
 
 /* ---- status ------------------------------------------------------------------------------------------------ */
 const char* lsnet_last_error(void);             /* message of the last failing call on this thread */
@@ -144,6 +149,63 @@ int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const void* x, int 
                           float scale_h, float scale_w, int deformable_groups, void* dx, long long lddx,
                           int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm, int mask_logits,
                           void* stream);
+
+/* ---- deformable convolution as whole operators ---------------------------------------------------------------------
+ * One call per pybind function of the reference's `deform_conv_ext` (mmdet/ops/dcn/src/deform_conv_ext.cpp:227-250):
+ *   lsnet_dcn_forward          deform_conv_forward :74-90 / modulated_deform_conv_forward :129-147 /
+ *                              pyramid_deform_conv_forward (deform_conv_cuda.cpp:811-919)
+ *   lsnet_dcn_backward_data    deform_conv_backward_input :92-109 / pyramid_..._backward_input (deform_conv_cuda.cpp:921-1036)
+ *                              and the input/offset/mask half of modulated_deform_conv_backward :149-224
+ *   lsnet_dcn_backward_weight  deform_conv_backward_parameters :111-127 / pyramid_..._backward_parameters
+ *                              (deform_conv_cuda.cpp:1038-1154) and the weight half of modulated_deform_conv_backward
+ * The descriptor carries the arguments those functions share (kernel / stride / pad / dilation / groups /
+ * deformable_groups, and LSNet's pyramid scales).  `mask` NULL = DCNv1 / pyramid; mask_logits = 1: `mask` holds the raw
+ * conv_offset outputs (sigmoid applied inside, dmask returned w.r.t. the logits).  Layouts as for lsnet_dcn_im2col_bf16.
+ * forward: the FUSED kernel (dcn_fused.cu: bilinear gather -> SWIZZLE_128B shared-memory A tile -> tcgen05.mma, no column
+ * matrix in HBM) runs when deformable_groups == 1, kh*kw <= 9, C % 64 == 0 and N <= 256; other shapes take gather -> GEMM
+ * through `workspace`.  *_workspace_size returns the scratch bytes the matching call needs (0 = none). */
+typedef struct lsnet_dcn_desc {
+  int B, H, W, C;              /* sampled map x: NHWC, C channels */
+  long long ldx;               /* pixel pitch of x in elements */
+  int Ho, Wo;                  /* sampling / output grid (= offset grid) */
+  int kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  float scale_h, scale_w;      /* pyramid DCN: base grid scale (1 for DCNv1 / DCNv2) */
+  int groups;                  /* weight groups; must be 1 here (grouped: lsnet_dcn_grouped_*) */
+  int deformable_groups;
+  int mask_logits;
+  int dtype;                   /* LSNET_DTYPE_BF16 */
+} lsnet_dcn_desc;
+
+/* A/B switch for tests and measurements: 0 = column-matrix path for every shape, 1 = fused kernels wherever the shape is
+ * supported, 2 = automatic (fused where it measured faster: patches >= 2 waves of the SMs).  Default: env LSNET_DCN_FUSED,
+ * else 2.  Not thread-safe; call between steps. */
+void lsnet_dcn_fused_enable(int on);
+/* 1: the weight gradient of lsnet_dcn_backward_weight is reduced in a fixed order (per-split partials in the workspace +
+ * a second pass) instead of fp32 atomics whose order varies from run to run (default: env LSNET_DETERMINISTIC, else 0). */
+void lsnet_set_deterministic(int on);
+size_t lsnet_dcn_forward_workspace_size(const lsnet_dcn_desc* d, int N);
+/* out[B*Ho*Wo, ldc] (bf16, or fp32 if out_fp32) = DCN(x; offset, mask) . Wp^T (+ bias) (ReLU).  Wp: bf16 [N, kh*kw*C]
+ * (tap-major, channel-minor), N % 16 == 0 (rows beyond the real Cout are zero).  col_out (optional, bf16
+ * [B*Ho*Wo, kh*kw*C]): also emit the column matrix (operand of the unfused weight gradient). */
+int lsnet_dcn_forward(const lsnet_dcn_desc* d, const void* x, const float* offset, long long ldo, const float* mask,
+                      long long ldm, const void* Wp, int N, const float* bias, int relu, void* out, long long ldc,
+                      int out_fp32, void* col_out, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t lsnet_dcn_backward_data_workspace_size(const lsnet_dcn_desc* d, int N);
+/* dy: bf16 [B*Ho*Wo, ldy] (N channels, N % 8 == 0); Wt: bf16 [kh*kw*C, N] (= Wp^T).  dx (NHWC, ACCUMULATED: the caller
+ * zero-fills; bf16, or fp32 if dx_fp32; may be NULL), doffset fp32 [.., lddo], dmask fp32 [.., lddm] (NULL without mask). */
+int lsnet_dcn_backward_data(const lsnet_dcn_desc* d, const void* dy, long long ldy, int N, const void* Wt, const void* x,
+                            const float* offset, long long ldo, const float* mask, long long ldm, void* dx,
+                            long long lddx, int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+size_t lsnet_dcn_backward_weight_workspace_size(const lsnet_dcn_desc* d, int N, int have_col);
+/* dW[N, lddw] (fp32, tap-major [N, kh*kw*C]) += dy^T . columns.  col_saved: the column matrix emitted by the forward
+ * (col_out), or NULL to re-sample x -- inside the FUSED weight-gradient kernel (gather warps write the MN-major B tiles of
+ * a split-K tcgen05 GEMM; needs deformable_groups == 1, kh*kw <= 9, C % 256 == 0), else through `workspace`. */
+int lsnet_dcn_backward_weight(const lsnet_dcn_desc* d, const void* dy, long long ldy, int N, const void* x,
+                              const float* offset, long long ldo, const float* mask, long long ldm, const void* col_saved,
+                              float* dW, long long lddw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- cross-IOU loss ----------------------------------------------------------------------------------------------
  * loss_type: 0 bbox, 1 polygon, 2 keypoint.  Dense form = CrossIOULoss.forward / cross_iou_loss

@@ -36,6 +36,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (no hardware suspend): for a thread that polls several barriers in turn
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (-> launch failure reported through the C ABI) instead of
 // hanging the device.
 __device__ __forceinline__ uint64_t global_ns() {
@@ -147,6 +161,41 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- explicit shared-memory accesses (32-bit addresses)
+// Pointers derived from an aligned-up dynamic shared memory base lose their address space and compile to generic
+// LD/ST; the hot loops use these instead.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16-byte read-only global load at base + idx * pitch (one IMAD.WIDE forms the address)
+__device__ __forceinline__ uint4 ldg128_at(unsigned long long base, uint32_t idx, uint32_t pitch) {
+  uint4 r;
+  asm volatile(
+      "{\n"
+      ".reg .u64 a;\n"
+      "mad.wide.u32 a, %5, %6, %4;\n"
+      "ld.global.nc.v4.u32 {%0, %1, %2, %3}, [a];\n"
+      "}\n"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(base), "r"(idx), "r"(pitch));
+  return r;
 }
 
 // ---------------------------------------------------------------- misc

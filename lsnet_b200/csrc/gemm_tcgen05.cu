@@ -477,7 +477,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // rank-2 bf16 map over a row-major [rows, cols] matrix with row pitch ld (elements); box = [box_cols, box_rows]
-static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                        uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -493,7 +493,7 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return 0;
 }
 // rank-4 bf16 map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1]
-static int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
+int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
                          uint32_t TW, uint32_t TH) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -508,7 +508,7 @@ static int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H
   return 0;
 }
 
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -520,7 +520,7 @@ static int num_sms() {
 }
 
 // choose a spatial patch TH x TW = pixels with the least padding waste
-static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
+void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
   long long best = -1;
   for (int th = 1; th <= pixels; th <<= 1) {
     int tw = pixels / th;

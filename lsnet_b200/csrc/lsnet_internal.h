@@ -1,6 +1,8 @@
 // Internal helpers shared by the translation units of liblsnet_sm100.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace lsn {
 // printf-style; stores the message for lsnet_last_error() and returns a non-zero status.
@@ -9,7 +11,18 @@ int set_error(const char* fmt, ...);
 void count_launch();
 int check_launch(const char* what);
 // kernel classes for the optional device timing (api.cu)
-enum { TC_GEMM = 0, TC_WGRAD = 1, TC_IM2COL = 2, TC_COL2IM = 3 };
+enum { TC_GEMM = 0, TC_WGRAD = 1, TC_IM2COL = 2, TC_COL2IM = 3, TC_DCN_FWD = 4, TC_DCN_WGRAD = 5, TC_DCN_BWD = 6,
+       TC_NUM = 7 };
 int timing_begin(int cls, double work, cudaStream_t st);
 void timing_end(int handle, cudaStream_t st);
+// host helpers of the tcgen05 GEMM family (gemm_tcgen05.cu)
+// rank-2 bf16 SWIZZLE_128B map over a row-major [rows, cols] matrix with row pitch ld (elements); box = [box_cols, box_rows]
+int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                uint32_t box_rows);
+// rank-4 bf16 SWIZZLE_128B map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1]
+int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
+                  uint32_t TW, uint32_t TH);
+int num_sms();
+// spatial patch TH x TW = pixels with the least padding waste over an H x W map
+void pick_patch(int H, int W, int pixels, int* TH, int* TW);
 }  // namespace lsn

@@ -18,6 +18,17 @@ class LsnetError(RuntimeError):
     pass
 
 
+class DcnDesc(ctypes.Structure):
+    """``lsnet_dcn_desc`` of include/lsnet_b200.h."""
+    _fields_ = [('B', c_int), ('H', c_int), ('W', c_int), ('C', c_int), ('ldx', c_ll), ('Ho', c_int), ('Wo', c_int),
+                ('kh', c_int), ('kw', c_int), ('stride_h', c_int), ('stride_w', c_int), ('pad_h', c_int),
+                ('pad_w', c_int), ('dil_h', c_int), ('dil_w', c_int), ('scale_h', c_f), ('scale_w', c_f),
+                ('groups', c_int), ('deformable_groups', c_int), ('mask_logits', c_int), ('dtype', c_int)]
+
+
+DTYPE_BF16 = 0
+
+
 def load():
     global _lib
     if _lib is None:
@@ -26,6 +37,9 @@ def load():
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.lsnet_last_error.restype = ctypes.c_char_p
         _lib.lsnet_launch_count.restype = ctypes.c_ulonglong
+        for n in ('lsnet_dcn_forward_workspace_size', 'lsnet_dcn_backward_data_workspace_size',
+                  'lsnet_dcn_backward_weight_workspace_size'):
+            getattr(_lib, n).restype = ctypes.c_size_t
     return _lib
 
 

@@ -1,7 +1,7 @@
 from .gemm_ops import gemm, gemm_tn, conv2d_nhwc, conv2d_wgrad_nhwc, pack_conv_weight  # noqa: F401
 from .conv import conv2d_same, linear_nhwc  # noqa: F401
 from .dcn import (deform_conv, modulated_deform_conv, modulated_deform_conv_packed, pyramid_deform_conv,  # noqa: F401
-                  dcn_im2col, dcn_col2im,
+                  dcn_im2col, dcn_col2im, dcn_forward, dcn_backward_data, dcn_backward_weight,
                   join_slices)
 from .loss import (cross_iou_loss_rows, cross_iou_level_loss, sigmoid_focal_loss_sum,  # noqa: F401
                    directional_targets)

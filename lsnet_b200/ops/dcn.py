@@ -1,17 +1,17 @@
 """Deformable convolutions on liblsnet_sm100.so with the reference's call signatures
 (mmdet/ops/dcn/deform_conv.py:290-292): ``deform_conv``, ``modulated_deform_conv``, ``pyramid_deform_conv``.
 
-forward  : bilinear-offset gather -> bf16 column matrix [pixels, taps*C]  (lsnet_dcn_im2col_bf16)
-           tcgen05 GEMM columns x W^T (+bias)                               (lsnet_gemm_bf16)
-backward : dCol = dY x W  (lsnet_gemm_bf16) -> scatter to dX / reduce to dOffset, dMask (lsnet_dcn_col2im_bf16)
-           dW = dY^T x columns (lsnet_gemm_tn_bf16, MN-major split-K); the forward's column matrix is kept
-           (HBM is plentiful on B200) instead of being re-gathered as the reference does
-           (deform_conv_cuda.cpp:770-773).
+Each autograd direction is ONE C-ABI call (include/lsnet_b200.h, "deformable convolution as whole operators"):
+forward  : lsnet_dcn_forward — FUSED: bilinear-offset gather -> SWIZZLE_128B shared-memory A tile -> tcgen05.mma; no
+           column matrix in HBM (shapes outside the fused kernel's range go gather -> GEMM through a workspace)
+backward : lsnet_dcn_backward_data   dCol = dY x W (tcgen05) -> scatter to dX / reduce to dOffset, dMask
+           lsnet_dcn_backward_weight dW += dY^T x columns (MN-major split-K tcgen05); the columns are either the
+           forward's optional side output (LSNET_DCN_SAVE_COL=1: kept in HBM, not re-gathered as
+           deform_conv_cuda.cpp:770-773 does) or re-sampled in the backward (LSNET_DCN_SAVE_COL=0: no column matrix
+           survives the forward)
 groups > 1 (the X-101 backbone sites: groups=64, widths 512/1024/2048): v1 runs the SAME kernels on the block-diagonal
 expansion of the grouped weight (dense [Cout, taps*Cin] with zeros outside each group's channel block) and takes the
-block diagonal of the dense weight gradient.  That spends groups x redundant tensor-core FLOPs (0.3 ms per layer at
-~1 PFLOP/s) instead of a dedicated HBM-bound grouped kernel — SURVEY §8 "next" — but is exact: the extra products are
-all multiplications by zero.
+block diagonal of the dense weight gradient.  Exact: the extra products are all multiplications by zero.
 """
 import torch
 from torch.autograd import Function
@@ -86,6 +86,107 @@ def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, 
             dmask.permute(0, 3, 1, 2) if dmask is not None else None)
 
 
+# 1: the fused forward also writes the bf16 column matrix (side output) and the weight gradient reads it back;
+# 0: nothing of the column matrix survives the forward, the weight gradient re-samples x.
+SAVE_COL = os.environ.get('LSNET_DCN_SAVE_COL', '1') == '1'
+
+
+def _desc(x_geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits):
+    B, H, W, C, ldx = x_geom
+    return L.DcnDesc(B, H, W, C, ldx, Ho, Wo, kh, kw, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1],
+                     float(scales[0]), float(scales[1]), 1, dg, int(bool(mask_logits)), L.DTYPE_BF16)
+
+
+def _workspace(nbytes, device):
+    return torch.empty(int(nbytes), device=device, dtype=torch.uint8) if nbytes else None
+
+
+def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False,
+                out=None, out_dtype=torch.bfloat16, relu=False, save_col=False):
+    """Whole forward operator.  x (B,C,H,W) channels_last bf16; wp bf16 [Npad16, kh*kw*C]; returns (out2d [P, N], col or
+    None).  ``out``: write into this [P, N] view (row pitch = out.stride(0))."""
+    import ctypes
+    geom = G.nhwc_geom(x)
+    B, H, W, C, ldx = geom
+    offset, ldo = _pix_major(offset)
+    ldm = 0
+    if mask is not None:
+        mask, ldm = _pix_major(mask)
+    N, P = wp.shape[0], B * Ho * Wo
+    assert wp.dtype == torch.bfloat16 and wp.is_contiguous() and wp.shape[1] == kh * kw * C
+    if out is None:
+        out = torch.empty((P, N), device=x.device, dtype=out_dtype)
+    assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    col = torch.empty((P, kh * kw * C), device=x.device, dtype=torch.bfloat16) if save_col else None
+    ws_bytes = 0 if save_col else L.load().lsnet_dcn_forward_workspace_size(ctypes.byref(d), L.c_int(N))
+    ws = _workspace(ws_bytes, x.device)
+    L.call('lsnet_dcn_forward', ctypes.byref(d), L.ptr(x), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm),
+           L.ptr(wp), L.c_int(N), L.ptr(bias), L.c_int(int(relu)), L.ptr(out), L.c_ll(out.stride(0)),
+           L.c_int(int(out.dtype == torch.float32)), L.ptr(col), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream())
+    return out, col
+
+
+def dcn_backward_data(gy2, wt, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True,
+                      dx_fp32=None, mask_logits=False, packed_out=False):
+    """Whole backward-data operator: gy2 bf16 [P, N]; wt bf16 [kh*kw*C, N].  Returns (dx, doffset, dmask) as logical
+    NCHW views (see dcn_col2im for ``packed_out``)."""
+    import ctypes
+    geom = G.nhwc_geom(x)
+    B, H, W, C, ldx = geom
+    offset, ldo = _pix_major(offset)
+    ldm = 0
+    if mask is not None:
+        mask, ldm = _pix_major(mask)
+    taps = kh * kw
+    N = wt.shape[1]
+    assert gy2.dtype == torch.bfloat16 and gy2.stride(1) == 1 and gy2.shape[1] == N and wt.is_contiguous()
+    dx_fp32 = DX_FP32 if dx_fp32 is None else dx_fp32
+    dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32 if dx_fp32 else torch.bfloat16) if need_dx else None
+    if packed_out:
+        assert mask is not None
+        nom = dg * 3 * taps
+        dom = torch.empty((B, Ho, Wo, nom), device=x.device, dtype=torch.float32)
+        doff, dmask, lddo, lddm = dom, dom[..., dg * 2 * taps:], nom, nom
+    else:
+        doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
+        dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
+        lddo, lddm = dg * 2 * taps, dg * taps
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    ws_bytes = L.load().lsnet_dcn_backward_data_workspace_size(ctypes.byref(d), L.c_int(N))
+    ws = _workspace(ws_bytes, x.device)
+    L.call('lsnet_dcn_backward_data', ctypes.byref(d), L.ptr(gy2), L.c_ll(gy2.stride(0)), L.c_int(N), L.ptr(wt), L.ptr(x),
+           L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.ptr(dx), L.c_ll(C), L.c_int(int(bool(dx_fp32))),
+           L.ptr(doff), L.c_ll(lddo), L.ptr(dmask), L.c_ll(lddm), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream())
+    if packed_out:
+        return dx.permute(0, 3, 1, 2) if dx is not None else None, dom.permute(0, 3, 1, 2), None
+    return (dx.permute(0, 3, 1, 2) if dx is not None else None, doff.permute(0, 3, 1, 2),
+            dmask.permute(0, 3, 1, 2) if dmask is not None else None)
+
+
+def dcn_backward_weight(gy2, x, offset, mask, col, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False,
+                        out=None):
+    """dW [N, kh*kw*C] fp32 (+= into ``out``) from gy2 bf16 [P, N] and either the saved columns or a re-sampling of x."""
+    import ctypes
+    geom = G.nhwc_geom(x)
+    B, H, W, C, ldx = geom
+    offset, ldo = _pix_major(offset)
+    ldm = 0
+    if mask is not None:
+        mask, ldm = _pix_major(mask)
+    N, K = gy2.shape[1], kh * kw * C
+    if out is None:
+        out = torch.zeros((N, K), device=x.device, dtype=torch.float32)
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    ws_bytes = L.load().lsnet_dcn_backward_weight_workspace_size(ctypes.byref(d), L.c_int(N), L.c_int(int(col is not None)))
+    ws = _workspace(ws_bytes, x.device)
+    L.call('lsnet_dcn_backward_weight', ctypes.byref(d), L.ptr(gy2), L.c_ll(gy2.stride(0)), L.c_int(N), L.ptr(x),
+           L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm), L.ptr(col), L.ptr(out), L.c_ll(out.stride(0)),
+           L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream())
+    return out
+
+
 def _out_hw(H, W, kh, kw, stride, pad, dil):
     return ((H + 2 * pad[0] - (dil[0] * (kh - 1) + 1)) // stride[0] + 1,
             (W + 2 * pad[1] - (dil[1] * (kw - 1) + 1)) // stride[1] + 1)
@@ -132,13 +233,6 @@ class _DCN(Function):
             raise ValueError(f'offset grid {tuple(offset.shape[2:])} != output grid {(Ho, Wo)}')
         cfg = (Ho, Wo, kh, kw, stride, pad, dil, scales, dg)
         ctx.packed_om = packed_om
-        if packed_om:
-            om, _ = _pix_major(offset.detach())
-            n2 = 2 * dg * kh * kw
-            col = dcn_im2col(x, om[:, :n2], om[:, n2:], *cfg, mask_logits=True)
-            offset = om
-        else:
-            col = dcn_im2col(x, offset.detach(), None if mask is None else mask.detach(), *cfg)
         npad = (co + 15) // 16 * 16
 
         def pack_fwd(t):
@@ -150,19 +244,28 @@ class _DCN(Function):
         b = None
         if bias is not None:
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
-        ctx.save_for_backward(x, offset, mask, weight, col)
-        ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
-        ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
+        if packed_om:
+            offset, _ = _pix_major(offset.detach())
+            n2 = 2 * dg * kh * kw
+            off_v, mask_v, logits = offset[:, :n2], offset[:, n2:], True
+        else:
+            off_v, mask_v, logits = offset.detach(), None if mask is None else mask.detach(), False
+        save_col = SAVE_COL and weight.requires_grad
+        out2d = None
         if out_slice is not None:
             # write straight into channels [c0, c0+co) of a wider pixel-major buffer (replaces a later torch.cat)
             buf, c0 = out_slice
             assert npad == co and buf.dtype == torch.bfloat16 and buf.shape[:3] == (B, Ho, Wo) and c0 % 8 == 0
             ld = buf.shape[3]
             out2d = torch.as_strided(buf, (B * Ho * Wo, co), (ld, 1), buf.storage_offset() + c0)
-            G.gemm(col, wp, b, False, torch.bfloat16, out=out2d)
+        out2d, col = dcn_forward(x, off_v, mask_v, wp, b, *cfg, mask_logits=logits, out=out2d,
+                                 out_dtype=torch.float32 if out_fp32 else torch.bfloat16, save_col=save_col)
+        ctx.save_for_backward(x, offset, mask, weight, col)
+        ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
+        ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
+        if out_slice is not None:
             return torch.as_strided(buf, (B, co, Ho, Wo), (Ho * Wo * ld, 1, Wo * ld, ld), buf.storage_offset() + c0)
-        out = G.gemm(col, wp, b, False, torch.float32 if out_fp32 else torch.bfloat16)
-        return out.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
+        return out2d.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
 
     @staticmethod
     def backward(ctx, gy):
@@ -183,16 +286,29 @@ class _DCN(Function):
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
         gx = goff = gmask = gw = gb = None
-        # The weight-gradient GEMM (tensor-pipe bound) only needs dY and the saved columns, the scatter (issue bound on
-        # the CUDA cores) only needs dCol: run the former on a side stream so the two overlap on the SMs.  Captured as a
-        # fork/join inside the step's CUDA graph.
+        if ctx.packed_om:
+            n2 = 2 * ctx.cfg[8] * kh * kw
+            off_v, mask_v, logits = offset[:, :n2], offset[:, n2:], True
+        else:
+            off_v, mask_v, logits = offset.detach(), None if mask is None else mask.detach(), False
+
+        def wgrad():
+            direct = ctx.grad2d
+            if direct is not None and tuple(direct.shape) != (cop, kh * kw * ci):
+                direct = None
+            if direct is not None:       # accumulate straight into the parameter's (tap-major) gradient memory
+                dcn_backward_weight(gy2, x, off_v, mask_v, col, *ctx.cfg, mask_logits=logits, out=direct)
+                return None
+            return unpack_dw(dcn_backward_weight(gy2, x, off_v, mask_v, col, *ctx.cfg, mask_logits=logits))
+        # The weight-gradient GEMM (tensor-pipe bound) only needs dY and the columns, the scatter (issue bound on the CUDA
+        # cores) only needs dCol: optionally run the former on a side stream so the two overlap on the SMs.
         side = None
         if OVERLAP_WGRAD and ctx.needs_input_grad[3]:
             cur = torch.cuda.current_stream()
             side = _side_stream(x.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                gw = unpack_dw(G.gemm_tn(gy2, col))
+                gw = wgrad()
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
             # B operand [N = taps*ci, K = co]: W^T, K-major
             def pack_bwd(t):
@@ -201,26 +317,14 @@ class _DCN(Function):
                     p = torch.cat([p, p.new_zeros(p.shape[0], cop - co)], 1)
                 return p.contiguous()
             wt = G.cached_pack(weight, 'dcn_bwd%d_%d' % (cop, groups), pack_bwd)
-            gcol = G.gemm(gy2, wt, None, False, torch.bfloat16)
-            if ctx.packed_om:
-                n2 = 2 * ctx.cfg[8] * kh * kw
-                gx, goff, gmask = dcn_col2im(gcol, x, offset[:, :n2], offset[:, n2:], *ctx.cfg,
-                                             need_dx=ctx.needs_input_grad[0], mask_logits=True, packed_out=True)
-            else:
-                gx, goff, gmask = dcn_col2im(gcol, x, offset.detach(), None if mask is None else mask.detach(), *ctx.cfg,
-                                             need_dx=ctx.needs_input_grad[0])
+            gx, goff, gmask = dcn_backward_data(gy2, wt, x, off_v, mask_v, *ctx.cfg, need_dx=ctx.needs_input_grad[0],
+                                                mask_logits=logits, packed_out=ctx.packed_om)
             if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif ctx.needs_input_grad[3]:
-            direct = ctx.grad2d
-            if direct is not None and tuple(direct.shape) != (cop, kh * kw * ci):
-                direct = None
-            if direct is not None:       # accumulate straight into the parameter's (tap-major) gradient memory
-                G.gemm_tn(gy2, col, out=direct)
-            else:
-                gw = unpack_dw(G.gemm_tn(gy2, col))                    # [cop, taps*ci] fp32
+            gw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
         return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None

@@ -1,0 +1,291 @@
+"""Fused DCN kernels (lsnet_b200/csrc/dcn_fused.cu) through the whole-operator C ABI (lsnet_dcn_forward /
+lsnet_dcn_backward_data / lsnet_dcn_backward_weight):
+
+* against the column-matrix path of the same library on identical inputs (only the fp32 accumulation order inside the
+  tensor core differs: <= 1e-3 of the output scale; the column side output is BIT-exact with lsnet_dcn_im2col_bf16),
+* against the oracle (oracle/dcn_ref.c, the CPU restatement of the reference kernels) for DCNv2 / DCNv1 / pyramid DCN
+  at shapes that exercise every tile edge: ragged patches, several channel blocks, N below / at the 256-wide tile,
+  strides, large offsets (samples outside the map), non-dyadic pyramid scales,
+* at the BASELINE level shapes (B=4, C=256, 100x168 ... 7x11) against the REFERENCE'S OWN CUDA kernels (oracle/_ref,
+  fp32) with an explicit bf16 error budget per output.
+"""
+import pytest
+import torch
+
+from oracle import dcn_ops as OD
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _ops():
+    import lsnet_b200.ops as ops
+    return ops
+
+
+def _lib():
+    from lsnet_b200 import lib
+    return lib.load()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _nhwc(t, dtype=None):
+    t = t.to(DEV)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _pack(w):
+    co, ci, kh, kw = w.shape
+    npad = (co + 15) // 16 * 16
+    p = torch.zeros(npad, kh * kw * ci, dtype=torch.bfloat16, device=DEV)
+    p[:co] = w.permute(0, 2, 3, 1).reshape(co, -1).to(DEV, torch.bfloat16)
+    return p
+
+
+CASES = [
+    # name,        B, C,   H,  W,  Ho, Wo, Co,  stride, mag, mask
+    ('v2_small', 2, 64, 13, 21, 13, 21, 48, 1, 2.5, True),
+    ('v2_c256_n256', 1, 256, 25, 42, 25, 42, 256, 1, 1.5, True),
+    ('v2_far', 2, 128, 9, 10, 9, 10, 256, 1, 12.0, True),       # most samples fall outside the map
+    ('v1_n32', 2, 64, 17, 19, 17, 19, 32, 1, 2.0, False),
+    ('v2_stride2', 2, 64, 24, 30, 12, 15, 64, 2, 1.5, True),
+    ('pyr_up', 2, 64, 13, 21, 25, 42, 64, 1, 2.5, False),        # output grid finer than the sampled map (non-dyadic)
+    ('pyr_down', 2, 128, 25, 42, 13, 21, 128, 1, 2.5, False),
+    ('pyr_tiny', 4, 256, 13, 21, 7, 11, 256, 1, 1.0, False),
+]
+
+
+def _make(case):
+    name, B, C, H, W, Ho, Wo, Co, stride, mag, has_mask = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    off = torch.randn(B, 18, Ho, Wo, generator=g) * mag
+    mask = torch.rand(B, 9, Ho, Wo, generator=g) if has_mask else None
+    w = _bf(torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5)
+    bias = torch.randn(Co, generator=g) if has_mask else None
+    return x, off, mask, w, bias
+
+
+def _geom(case):
+    name, B, C, H, W, Ho, Wo, Co, stride, mag, has_mask = case
+    pyr = name.startswith('pyr')
+    scales = (H / Ho, W / Wo) if pyr else (1.0, 1.0)
+    return (Ho, Wo, 3, 3, (stride, stride), (1, 1), (1, 1), scales, 1)
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_fused_forward_vs_unfused_and_oracle(case):
+    ops, lib = _ops(), _lib()
+    name, B, C, H, W, Ho, Wo, Co, stride, mag, has_mask = case
+    x, off, mask, w, bias = _make(case)
+    cfg = _geom(case)
+    xd, offd = _nhwc(x, torch.bfloat16), _nhwc(off)
+    maskd = _nhwc(mask) if mask is not None else None
+    wp = _pack(w)
+    bd = None
+    if bias is not None:
+        bd = torch.zeros(wp.shape[0], device=DEV)
+        bd[:Co] = bias.to(DEV)
+    try:
+        lib.lsnet_dcn_fused_enable(1)
+        out_f, col_f = ops.dcn_forward(xd, offd, maskd, wp, bd, *cfg, out_dtype=torch.float32, save_col=True)
+        out_f2, _ = ops.dcn_forward(xd, offd, maskd, wp, bd, *cfg, out_dtype=torch.float32, save_col=False)
+        out_b, _ = ops.dcn_forward(xd, offd, maskd, wp, bd, *cfg, out_dtype=torch.bfloat16, relu=True)
+        lib.lsnet_dcn_fused_enable(0)
+        out_u, col_u = ops.dcn_forward(xd, offd, maskd, wp, bd, *cfg, out_dtype=torch.float32, save_col=True)
+    finally:
+        lib.lsnet_dcn_fused_enable(2)
+    torch.cuda.synchronize()
+    # the side output is the same arithmetic as the standalone gather: bit-exact
+    assert torch.equal(col_f, col_u), name
+    assert torch.equal(out_f, out_f2), name
+    assert _rel(out_f, out_u) < 1e-3, (name, _rel(out_f, out_u))
+    assert _rel(out_b.float(), out_u.clamp(min=0)) < 1.5e-2, name
+    # oracle
+    sc = cfg[7]
+    if name.startswith('pyr'):
+        ref = OD.pyramid_deform_conv(x, off, w, sc, stride, 1, 1)
+    elif mask is None:
+        ref = OD.deform_conv(x, off, w, stride, 1, 1)
+    else:
+        ref = OD.modulated_deform_conv(x, off, mask, w, bias, stride, 1, 1)
+    got = out_f.view(B, Ho, Wo, -1)[..., :Co].permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    assert _rel(got, ref) < 4e-3, (name, _rel(got, ref))
+
+
+def test_fused_forward_into_channel_slice_and_logits():
+    """The three pyramid DCNs of a level write into channel slices of ONE [B,H,W,768] buffer (LSHead); DCNv2 reads the
+    mask LOGITS from the conv_offset output."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 64, 11, 13
+    x = _nhwc(_bf(torch.randn(B, C, H, W, generator=g)), torch.bfloat16)
+    om = _nhwc(torch.randn(B, 32, H, W, generator=g))          # conv_offset output padded to 32 channels
+    w = _bf(torch.randn(64, C, 3, 3, generator=g) / 24)
+    wp = _pack(w)
+    cfg = (H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1)
+    buf = torch.full((B, H, W, 192), 7.0, device=DEV, dtype=torch.bfloat16)
+    out2d = torch.as_strided(buf, (B * H * W, 64), (192, 1), 64)
+    ops.dcn_forward(x, om[:, :18], om[:, 18:27], wp, None, *cfg, mask_logits=True, out=out2d)
+    ref, _ = ops.dcn_forward(x, om[:, :18], torch.sigmoid(om[:, 18:27]), wp, None, *cfg, mask_logits=False)
+    torch.cuda.synchronize()
+    assert _rel(buf[..., 64:128].reshape(-1, 64).float(), ref.float()) < 1.5e-2
+    assert float((buf[..., :64] - 7).abs().max()) == 0 and float((buf[..., 128:] - 7).abs().max()) == 0
+
+
+LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+
+
+@pytest.fixture(params=['fused', 'columns'])
+def dcn_path(request):
+    """Run the test once with the fused kernels forced on every supported shape and once on the column-matrix path
+    (the library's default picks per shape)."""
+    lib = _lib()
+    lib.lsnet_dcn_fused_enable(1 if request.param == 'fused' else 0)
+    yield request.param
+    lib.lsnet_dcn_fused_enable(2)
+
+
+def _ref_ext():
+    from oracle import build_ref
+    if build_ref.so_path() is None:
+        pytest.skip('oracle/_ref not built (needs the reference tree at build time)')
+    return build_ref.load_ext()
+
+
+@pytest.mark.parametrize('lvl', range(5))
+def test_dcnv2_baseline_shape_vs_reference_cuda(lvl, dcn_path):
+    """B=4, C=256 -> 256 on the five level grids of the 800x1344 BASELINE config: our bf16 operator (forward + all
+    gradients, through ops.modulated_deform_conv -> the whole-operator C ABI) against the reference's own fp32 CUDA
+    kernels on bf16-representable inputs.  Error budget (relative to the max |reference| of each output):
+      out     4e-3  columns rounded to bf16 (2^-9 per element, averaged over K = 2304 products)
+      dW      4e-3  bf16 columns and dY, fp32 accumulation over up to 67 200 pixels
+      dOffset 2e-2  dCol rounded to bf16 before the <dCol, x> reductions over 256 channels
+      dMask   2e-2  same
+      dX      4e-2  bf16 dCol + packed-bf16 atomic accumulation (default) -- 2e-2 with fp32 accumulation
+      db      1e-3  fp32 column sums of bf16 dY"""
+    ops = _ops()
+    ext = _ref_ext()
+    H, W = LEVELS[lvl]
+    B, C, Co = 4, 256, 256
+    g = torch.Generator().manual_seed(100 + lvl)
+    x = _bf(torch.randn(B, C, H, W, generator=g)).to(DEV)
+    off = (torch.randn(B, 18, H, W, generator=g) * 1.5).to(DEV)
+    mask = torch.rand(B, 9, H, W, generator=g).to(DEV)
+    w = _bf(torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(DEV)
+    b = torch.randn(Co, generator=g).to(DEV)
+    gy = _bf(torch.randn(B, Co, H, W, generator=g)).to(DEV)
+    e = x.new_empty(0)
+    ref_out = torch.empty(B, Co, H, W, device=DEV)
+    ext.modulated_deform_conv_forward(x, w, b, e, off, mask, ref_out, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, True)
+    gi, go, gm, gw, gb = (torch.zeros_like(t) for t in (x, off, mask, w, b))
+    ext.modulated_deform_conv_backward(x, w, b, e, off, mask, e, gi, gw, gb, go, gm, gy.contiguous(), 3, 3, 1, 1, 1, 1, 1,
+                                       1, 1, 1, True)
+    ins = [t.clone().requires_grad_(True) for t in (x, off, mask, w, b)]
+    out = ops.modulated_deform_conv(*ins, 1, 1, 1, out_fp32=True)
+    grads = torch.autograd.grad(out, ins, gy)
+    torch.cuda.synchronize()
+    budget = dict(out=4e-3, dx=4e-2, doff=2e-2, dmask=2e-2, dw=4e-3, db=1e-3)
+    got = dict(out=out, dx=grads[0], doff=grads[1], dmask=grads[2], dw=grads[3], db=grads[4])
+    ref = dict(out=ref_out, dx=gi, doff=go, dmask=gm, dw=gw, db=gb)
+    errs = {k: _rel(got[k].float(), ref[k]) for k in budget}
+    print(f'level {lvl} ({H}x{W}) rel err vs reference CUDA:', {k: f'{v:.2e}' for k, v in errs.items()})
+    for k, tol in budget.items():
+        assert errs[k] < tol, (lvl, k, errs[k])
+
+
+@pytest.mark.parametrize('lvl,src', [(0, 1), (1, 0), (2, 3), (4, 2)])
+def test_pyramid_baseline_shape_vs_reference_cuda(lvl, src, dcn_path):
+    """Pyramid DCN on the BASELINE level grids: output/offset grid = level `lvl`, sampled map = level `src` (scale_h =
+    H_src / H_lvl, non-dyadic for 25->13, 13->7), against the reference's pyramid kernels (fp32)."""
+    ops = _ops()
+    ext = _ref_ext()
+    (Ho, Wo), (H, W) = LEVELS[lvl], LEVELS[src]
+    B, C, Co = 4, 256, 256
+    sh, sw = H / Ho, W / Wo
+    g = torch.Generator().manual_seed(200 + 10 * lvl + src)
+    x = _bf(torch.randn(B, C, H, W, generator=g)).to(DEV)
+    off = (torch.randn(B, 18, Ho, Wo, generator=g) * 2.0).to(DEV)
+    w = _bf(torch.randn(Co, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(DEV)
+    gy = _bf(torch.randn(B, Co, Ho, Wo, generator=g)).to(DEV)
+    e = x.new_empty(0)
+    step = min(64, B)
+    ref_out = torch.empty(B, Co, Ho, Wo, device=DEV)
+    ext.pyramid_deform_conv_forward(x, w, off, ref_out, e, e, 3, 3, 1, 1, 1, 1, 1, 1, sw, sh, 1, 1, step)
+    gi, go, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+    ext.pyramid_deform_conv_backward_input(x, off, gy.contiguous(), gi, go, w, e, 3, 3, 1, 1, 1, 1, 1, 1, sw, sh, 1, 1, step)
+    ext.pyramid_deform_conv_backward_parameters(x, off, gy.contiguous(), gw, e, e, 3, 3, 1, 1, 1, 1, 1, 1, sw, sh, 1, 1, 1,
+                                                step)
+    ins = [t.clone().requires_grad_(True) for t in (x, off, w)]
+    out = ops.pyramid_deform_conv(ins[0], ins[1], ins[2], (sh, sw), 1, 1, 1, out_fp32=True)
+    grads = torch.autograd.grad(out, ins, gy)
+    torch.cuda.synchronize()
+    # dX: up to (sh*sw)^-1 * 36 contributions per input pixel accumulate in packed bf16 (see test_gpu_kernels.py)
+    budget = dict(out=4e-3, dx=6e-2 if sh < 1 else 4e-2, doff=2e-2, dw=4e-3)
+    got = dict(out=out, dx=grads[0], doff=grads[1], dw=grads[2])
+    ref = dict(out=ref_out, dx=gi, doff=go, dw=gw)
+    errs = {k: _rel(got[k].float(), ref[k]) for k in budget}
+    print(f'pyramid {Ho}x{Wo} <- {H}x{W} rel err vs reference CUDA:', {k: f'{v:.2e}' for k, v in errs.items()})
+    for k, tol in budget.items():
+        assert errs[k] < tol, (lvl, src, k, errs[k])
+
+
+WG_CASES = [
+    # name,      B, C,   H,  W,  Ho, Wo, M,  mag, mask
+    ('wg_v2', 2, 256, 13, 21, 13, 21, 256, 2.0, True),
+    ('wg_v2_ragged_m48', 3, 256, 9, 19, 9, 19, 48, 2.0, True),
+    ('wg_c512_m320', 1, 512, 10, 12, 10, 12, 320, 1.5, True),      # 2 channel tiles, 2 cout groups
+    ('wg_pyr_up', 2, 256, 13, 21, 25, 42, 256, 2.5, False),
+    ('wg_pyr_down', 2, 256, 25, 42, 13, 21, 256, 2.5, False),
+    ('wg_level0ish', 1, 256, 50, 84, 50, 84, 256, 1.5, True),
+]
+
+
+@pytest.mark.parametrize('case', WG_CASES, ids=[c[0] for c in WG_CASES])
+def test_fused_weight_gradient(case):
+    """lsnet_dcn_backward_weight without saved columns: the fused kernel re-samples x into the MN-major B tiles.  Against
+    (a) gather -> HBM columns -> split-K GEMM of the same library, (b) fp32 dY^T . columns; the deterministic two-stage
+    reduction must be bit-reproducible."""
+    ops, lib = _ops(), _lib()
+    name, B, C, H, W, Ho, Wo, M, mag, has_mask = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = _nhwc(_bf(torch.randn(B, C, H, W, generator=g)), torch.bfloat16)
+    off = _nhwc(torch.randn(B, 18, Ho, Wo, generator=g) * mag)
+    mask = _nhwc(torch.rand(B, 9, Ho, Wo, generator=g)) if has_mask else None
+    gy2 = _bf(torch.randn(B * Ho * Wo, M, generator=g)).to(DEV, torch.bfloat16)
+    pyr = 'pyr' in name
+    cfg = (Ho, Wo, 3, 3, (1, 1), (1, 1), (1, 1), (H / Ho, W / Wo) if pyr else (1.0, 1.0), 1)
+    try:
+        lib.lsnet_dcn_fused_enable(1)
+        lib.lsnet_set_deterministic(0)
+        dw_f = ops.dcn_backward_weight(gy2, x, off, mask, None, *cfg)
+        acc = torch.full_like(dw_f, 0.5)
+        ops.dcn_backward_weight(gy2, x, off, mask, None, *cfg, out=acc)          # accumulates into `out`
+        lib.lsnet_set_deterministic(1)
+        dw_d1 = ops.dcn_backward_weight(gy2, x, off, mask, None, *cfg)
+        dw_d2 = ops.dcn_backward_weight(gy2, x, off, mask, None, *cfg)
+        lib.lsnet_set_deterministic(0)
+        lib.lsnet_dcn_fused_enable(0)
+        col = ops.dcn_im2col(x, off, mask, *cfg)
+        dw_u = ops.dcn_backward_weight(gy2, x, off, mask, col, *cfg)
+        dw_u2 = ops.dcn_backward_weight(gy2, x, off, mask, None, *cfg)            # re-sampled through the workspace
+    finally:
+        lib.lsnet_dcn_fused_enable(2)
+        lib.lsnet_set_deterministic(0)
+    torch.cuda.synchronize()
+    ref = gy2.float().t() @ col.float()
+    assert torch.equal(dw_d1, dw_d2), name
+    for nm, t in (('fused', dw_f), ('deterministic', dw_d1), ('columns', dw_u), ('resampled', dw_u2)):
+        assert _rel(t, ref) < 2e-3, (name, nm, _rel(t, ref))
+    assert _rel(acc - 0.5, ref) < 2e-3, name

@@ -134,6 +134,76 @@ if only == 'gemm_shapes':
             tot += ms * cnt
             print(f'level {h}x{w_:<4d} {name:32s} {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s   x{cnt} = {ms * cnt:6.3f} ms', flush=True)
     print('sum over levels (with multiplicities):', round(tot, 3), 'ms')
+if only in (None, 'dcn_fwd'):
+    # whole forward operator: fused (gather -> smem A tile -> tcgen05) against gather -> HBM columns -> GEMM
+    from lsnet_b200 import lib as LL
+    cfg = (H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1)
+    fl = 2.0 * P * 256 * 2304
+    for fused in (1, 0):
+        LL.load().lsnet_dcn_fused_enable(fused)
+        tag = 'fused' if fused else 'gather+GEMM'
+        ms = timeit(lambda: ops.dcn_forward(x, off, mask, wp, None, *cfg, out=out))
+        add(f'dcn_forward {tag:12s} DCNv2 100x168 C256 N256', ms, fl, 'TFLOP/s')
+        ms = timeit(lambda: ops.dcn_forward(x, off, mask, wp, None, *cfg, out=out, save_col=True))
+        add(f'dcn_forward {tag:12s} + column side output', ms, fl, 'TFLOP/s')
+    LL.load().lsnet_dcn_fused_enable(1)
+    z = torch.zeros_like(off)
+    ms = timeit(lambda: ops.dcn_forward(x, z, mask, wp, None, *cfg, out=out))
+    add('dcn_forward fused zero offsets (bench towers)', ms, fl, 'TFLOP/s')
+    big = off * 8
+    ms = timeit(lambda: ops.dcn_forward(x, big, mask, wp, None, *cfg, out=out))
+    add('dcn_forward fused offsets x8 (sigma 12 px)', ms, fl, 'TFLOP/s')
+    lv = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    for li, (h, w_) in enumerate(lv):
+        Pl = B * h * w_
+        xl = torch.randn(B, 256, h, w_, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ol = (torch.randn(B, 18, h, w_, generator=g) * 1.5).to(dev).contiguous(memory_format=torch.channels_last)
+        outl = torch.empty(Pl, 256, device=dev, dtype=torch.bfloat16)
+        cl = (h, w_, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1)
+        for fused in (1, 0):
+            LL.load().lsnet_dcn_fused_enable(fused)
+            ms = timeit(lambda: ops.dcn_forward(xl, ol, None, wp, None, *cl, out=outl), n=6)
+            add(f'dcn_forward {"fused" if fused else "unfused":8s} DCNv1 level {li} {h}x{w_}', ms, 2.0 * Pl * 256 * 2304, 'TFLOP/s')
+        # pyramid: this level's grid sampling the next-finer / next-coarser map
+        for (sh_, sw_) in ([lv[li - 1]] if li else []) + ([lv[li + 1]] if li + 1 < len(lv) else []):
+            xs = torch.randn(B, 256, sh_, sw_, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            cp = (h, w_, 3, 3, (1, 1), (1, 1), (1, 1), (sh_ / h, sw_ / w_), 1)
+            for fused in (1, 0):
+                LL.load().lsnet_dcn_fused_enable(fused)
+                ms = timeit(lambda: ops.dcn_forward(xs, ol, None, wp, None, *cp, out=outl), n=6)
+                add(f'dcn_forward {"fused" if fused else "unfused":8s} pyramid {h}x{w_} <- {sh_}x{sw_}', ms, 2.0 * Pl * 256 * 2304, 'TFLOP/s')
+    LL.load().lsnet_dcn_fused_enable(1)
+if only in (None, 'dcn_wgrad'):
+    # weight gradient: fused re-gather (no columns in HBM) against the split-K GEMM over saved columns (+ the gather that
+    # would have to re-create them)
+    from lsnet_b200 import lib as LL
+    cfg = (H, W, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1)
+    fl = 2.0 * P * 256 * 2304
+    dwb = torch.zeros(256, 2304, device=dev)
+    LL.load().lsnet_dcn_fused_enable(1)
+    ms = timeit(lambda: ops.dcn_backward_weight(dy, x, off, mask, None, *cfg, out=dwb))
+    add('dcn_backward_weight fused re-gather 100x168', ms, fl, 'TFLOP/s')
+    LL.load().lsnet_set_deterministic(1)
+    ms = timeit(lambda: ops.dcn_backward_weight(dy, x, off, mask, None, *cfg, out=dwb))
+    add('dcn_backward_weight fused, deterministic 2-stage', ms, fl, 'TFLOP/s')
+    LL.load().lsnet_set_deterministic(0)
+    ms = timeit(lambda: ops.dcn_backward_weight(dy, x, off, mask, col, *cfg, out=dwb))
+    add('dcn_backward_weight saved columns (gemm_mnmajor)', ms, fl, 'TFLOP/s')
+    LL.load().lsnet_dcn_fused_enable(0)
+    ms = timeit(lambda: ops.dcn_backward_weight(dy, x, off, mask, None, *cfg, out=dwb))
+    add('dcn_backward_weight gather -> HBM -> gemm_mnmajor', ms, fl, 'TFLOP/s')
+    LL.load().lsnet_dcn_fused_enable(1)
+    for (h, w_) in [(50, 84), (25, 42), (13, 21), (7, 11)]:
+        Pl = B * h * w_
+        xl = torch.randn(B, 256, h, w_, generator=g).to(dev, torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ol = (torch.randn(B, 18, h, w_, generator=g) * 1.5).to(dev).contiguous(memory_format=torch.channels_last)
+        dyl = torch.randn(Pl, 256, generator=g).to(dev, torch.bfloat16)
+        cl = (h, w_, 3, 3, (1, 1), (1, 1), (1, 1), (1.0, 1.0), 1)
+        coll = ops.dcn_im2col(xl, ol, None, *cl)
+        ms = timeit(lambda: ops.dcn_backward_weight(dyl, xl, ol, None, None, *cl, out=dwb), n=6)
+        add(f'dcn_backward_weight fused          {h}x{w_}', ms, 2.0 * Pl * 256 * 2304, 'TFLOP/s')
+        ms = timeit(lambda: ops.dcn_backward_weight(dyl, xl, ol, None, coll, *cl, out=dwb), n=6)
+        add(f'dcn_backward_weight saved columns  {h}x{w_}', ms, 2.0 * Pl * 256 * 2304, 'TFLOP/s')
 if only in (None, 'gn'):
     wgt, bias = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     ms = timeit(lambda: ops.group_norm_nhwc(x, 32, wgt, bias, 1e-5, relu=True))
