@@ -193,41 +193,48 @@ def cpu_reference_step_factory(threads):
     return run
 
 
+def bench_config(world):
+    """The workload description both arms print verbatim (the driver compares the two `config` objects)."""
+    return dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
+                l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
+                optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights')
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the reference path (oracle port, fp32) on the host cores, ALWAYS at the full 800x1333 resolution --
+    one image per step is the bounded sample; the image is never shrunk, so the number means the same on every box."""
     if rank != 0:
         return
     threads = cpu_threads()
     run = cpu_reference_step_factory(threads)
-    # calibrate on a small image, then pick the largest sample that keeps (warmup+steps) within ~4 minutes
-    t0 = time.perf_counter(); run((384, 512), 0); t_small = time.perf_counter() - t0
-    full_px, small_px = 800 * 1344, 384 * 512
-    budget = 240.0 / max(1, args.steps + args.warmup)
-    scale = min(1.0, budget / (t_small * full_px / small_px))
-    if scale >= 1.0:
-        hw, sample = IMG_HW, '1 image 800x1333 per step (full resolution)'
-    else:
-        f = max(scale, small_px / full_px) ** 0.5
-        hw = (max(384, int(800 * f) // 32 * 32), max(512, int(1333 * f) // 32 * 32))
-        sample = f'1 image {hw[0]}x{hw[1]} per step; value scaled by pixel count to 800x1344-equivalent images'
-    eq = (((hw[0] + 31) // 32 * 32) * ((hw[1] + 31) // 32 * 32)) / full_px
+    sample = '1 image 800x1333 per step (full resolution), all host threads'
     for w in range(args.warmup):
-        run(hw, w)
+        run(IMG_HW, w)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        run(hw, args.warmup + s)
+        run(IMG_HW, args.warmup + s)
     dt = time.perf_counter() - t0
-    value = args.steps * eq / dt
+    value = args.steps / dt
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
-                            l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
-                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights',
-                            step_mode='reference path on the host cores (oracle port, fp32), rank 0 only',
-                            cpu_sample=sample),
+                dtype='f32', data='synthetic', impl='reference', config=bench_config(world),
+                step_mode='reference path on the host cores (oracle port, fp32), rank 0 only',
                 cpu_baseline=dict(value=value, unit='images/s', cores=threads, kind='port', sample=sample),
                 e2e=dict(value=value, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def measured_traffic(kernel_class):
+    """DRAM bytes per launch of a kernel class inside the step (dram__bytes_read.sum + dram__bytes_write.sum), from the
+    committed ncu pass over one whole step (profiles/r02_step_traffic.json, tools/step_traffic.py).  None when the
+    profile does not cover the class."""
+    p = os.path.join(ROOT, 'profiles', 'r02_step_traffic.json')
+    try:
+        d = json.load(open(p))['classes']
+        key = kernel_class.split('(')[0]
+        return float(d[key]['dram_bytes_per_launch']) if key in d else None
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -332,11 +339,11 @@ def run_gpu(args, rank, world, local_rank):
     if any(t in dom for t in TENSOR_BOUND):
         achieved = c['work'] / (c['ms'] / 1e3) / 1e12 if c['ms'] > 0 else 0.0
         roof = dict(bound='tensor', kernel=dom, achieved=achieved, peak=peaks['tf_sustained'], unit='TFLOP/s',
-                    frac=achieved / peaks['tf_sustained'], traffic=None)
+                    frac=achieved / peaks['tf_sustained'], traffic=measured_traffic(dom))
     else:
         achieved = c['work'] / (c['ms'] / 1e3) / 1e9 if c['ms'] > 0 else 0.0
         roof = dict(bound='hbm', kernel=dom, achieved=achieved, peak=peaks['hbm'], unit='GB/s',
-                    frac=achieved / peaks['hbm'], traffic=None)
+                    frac=achieved / peaks['hbm'], traffic=measured_traffic(dom))
     roof.update(peak_source=peaks['src'] + (' sustained' if any(t in dom for t in TENSOR_BOUND) else ''),
                 # graph mode: kernel classes are timed in a SERIALISED instrumented replay of the same step (stream
                 # parallelism off, every kernel alone on the GPU, like an ncu launch list); shares are of that replay
@@ -352,24 +359,19 @@ def run_gpu(args, rank, world, local_rank):
         try:
             threads = cpu_threads()
             run = cpu_reference_step_factory(threads)
-            hw = (384, 640)
-            run(hw, 0)
+            run(IMG_HW, 0)                                   # warm-up (first-touch, thread pools)
             t0 = time.perf_counter(); n = 0
-            while time.perf_counter() - t0 < 15.0 and n < 8:
-                run(hw, 1 + n); n += 1
+            while n < 3 and (n == 0 or time.perf_counter() - t0 < 18.0):
+                run(IMG_HW, 1 + n); n += 1
             dt = time.perf_counter() - t0
-            eq = (384 * 640) / (800 * 1344)
-            cpu = dict(value=n * eq / dt, unit='images/s', cores=threads, kind='port',
-                       sample=f'{n} training steps on 1 image 384x640 (oracle port of the reference path, fp32); value '
-                              'scaled by pixel count to 800x1344-equivalent images/s')
+            cpu = dict(value=n / dt, unit='images/s', cores=threads, kind='port',
+                       sample=f'{n} training steps on 1 image 800x1333 each (oracle port of the reference path, fp32, '
+                              'full resolution, all host threads)')
         except Exception as e:   # the baseline must never take the GPU number down with it
             cpu = dict(value=None, unit='images/s', cores=cpu_threads(), kind='port', sample=f'failed: {e!r}')
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
-                data='synthetic',
-                config=dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
-                            l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
-                            optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights', step_mode=mode),
+                data='synthetic', config=bench_config(world), step_mode=mode,
                 e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clk)

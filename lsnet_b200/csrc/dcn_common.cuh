@@ -115,4 +115,19 @@ __device__ __forceinline__ float2 bf16x2_f2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+// acc += <a, b> over 8 bf16 channels, accumulated pairwise with FFMA2 (sm_100 packed fp32x2; exact products)
+__device__ __forceinline__ float2 dot8(const float2 (&a)[4], const uint4& b, float2 acc) {
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc = __ffma2_rn(a[i], bf16x2_f2(pb[i]), acc);
+  return acc;
+}
+
+__device__ __forceinline__ void axpy8(float w, const uint4& a, float2 (&acc)[4]) {
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  const float2 w2 = make_float2(w, w);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(w2, bf16x2_f2(pa[i]), acc[i]);
+}
+
 }  // namespace lsn

@@ -244,21 +244,6 @@ struct BinCfg {
   int PH, PW, WH, WW, R, skip;
 };
 
-// acc += <a, b> over 8 bf16 channels, accumulated pairwise with FFMA2 (sm_100 packed fp32x2; exact products)
-__device__ __forceinline__ float2 dot8(const float2 (&a)[4], const uint4& b, float2 acc) {
-  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc = __ffma2_rn(a[i], bf16x2_f2(pb[i]), acc);
-  return acc;
-}
-
-__device__ __forceinline__ void axpy8(float w, const uint4& a, float2 (&acc)[4]) {
-  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-  const float2 w2 = make_float2(w, w);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = __ffma2_rn(w2, bf16x2_f2(pa[i]), acc[i]);
-}
-
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_WARPS = BIN_THREADS / 32;
 constexpr int BIN_PT_BYTES = 5 * 16 + 4 * 8;   // shared memory per (pixel, tap): 5 records + 4 CSR entries
@@ -610,6 +595,13 @@ extern "C" int lsnet_dcn_im2col_bf16(const void* x, int B, int H, int W, int C, 
   return check_launch("dcn_im2col");
 }
 
+namespace lsn {
+// TMA-staged adjoint (dcn_adjoint.cu): 0 = launched, 1 = shape not taken, < 0 = error
+int dcn_adjoint_tma(const DcnGeom& g, const void* gcol, const void* x, const float* offset, const float* mask, void* dx,
+                    long long lddx, int dx_fp32, float* doffset, long long lddo, float* dmask, long long lddm,
+                    cudaStream_t st);
+}
+
 extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const void* x, int B, int H, int W, int C,
                                      long long ldx, const float* offset, long long ldo, const float* mask,
                                      long long ldm, int Ho, int Wo, int kh, int kw, int stride_h, int stride_w,
@@ -629,7 +621,12 @@ extern "C" int lsnet_dcn_col2im_bf16(const void* gcol, long long ldcol, const vo
   const int th = timing_begin(TC_COL2IM, bytes, static_cast<cudaStream_t>(stream));
   BinCfg bc;
   size_t bin_smem = 0;
-  if (pick_binned(g, dx != nullptr, &bc, &bin_smem)) {
+  const int rc_tma = dcn_adjoint_tma(g, gcol, x, offset, mask, dx, lddx, dx_fp32, doffset, lddo, dmask, lddm,
+                                     static_cast<cudaStream_t>(stream));
+  if (rc_tma < 0) return 1;
+  if (rc_tma == 0) {
+    // dCol slices staged by TMA (dcn_adjoint.cu)
+  } else if (pick_binned(g, dx != nullptr, &bc, &bin_smem)) {
     dim3 bgrid((Wo + bc.PW - 1) / bc.PW, (Ho + bc.PH - 1) / bc.PH, B);
     static int variant = -1;
     if (variant < 0) { const char* e = getenv("LSNET_BIN_VARIANT"); variant = e ? atoi(e) : 44; }

@@ -508,6 +508,23 @@ int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint6
   return 0;
 }
 
+// rank-5 bf16 SWIZZLE_128B map over a DCN column / dCol matrix [B*Ho*Wo, taps*C] viewed as [B, Ho, Wo, taps, C] (row pitch
+// ldcol elements); box = [64 channels, taps, PW, PH, 1]: one TMA instruction stages the 64-channel slice of a pixel patch
+int make_map_col5d(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t Ho, uint64_t Wo, uint64_t taps, uint64_t C,
+                   uint64_t ldcol, uint32_t PW, uint32_t PH) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[5] = {C, taps, Wo, Ho, B};
+  cuuint64_t strides[4] = {C * 2, ldcol * 2, Wo * ldcol * 2, Ho * Wo * ldcol * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(taps), PW, PH, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled(5d) failed: %d", (int)r);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {

@@ -200,8 +200,9 @@ class LSHead(nn.Module):
         return mods
 
     def _out_dims(self, br):
-        if br == 'bbox':   # lsnet_head.py:170-176, 207-211
-            return 4 * (4 + 1) + (self.num_kernel_points - 4 - 1) * 2, 4 * (4 + 1)
+        if br == 'bbox':   # lsnet_head.py:170-176, 207-211: 4 extreme points + centre, plus the free DCN points
+            nv = self.num_vectors if self.task == 'bbox' else 4
+            return 4 * (nv + 1) + (self.num_kernel_points - nv - 1) * 2, 4 * (nv + 1)
         d = (self.num_vectors + 1) * 4
         return d, d
 
@@ -534,6 +535,24 @@ class LSHead(nn.Module):
             vss.append(v)
         return kps, vss
 
+    @staticmethod
+    def process_keypoints_with_kbox(gt_kps_vs_list):
+        """lsnet_head.py:1787-1828 (task 'pose_kbox'): the ground-truth box of an instance is the extent of its VISIBLE
+        keypoints (invisible ones count as +1e7 for the minimum and -1 for the maximum), its centre the landmark centre.
+        Returns (keypoints+centre (G, 2n+2), key boxes (G,4), visibilities (G,n)); inputs are not modified."""
+        kps, boxes, vss = [], [], []
+        for k in gt_kps_vs_list:
+            x, y, v = k[:, 0::3], k[:, 1::3], k[:, 2::3]
+            hid = v == 0
+            big, neg = torch.full_like(x, 10000000.), torch.full_like(x, -1.)
+            xmin, ymin = torch.where(hid, big, x).min(1)[0], torch.where(hid, big, y).min(1)[0]
+            xmax, ymax = torch.where(hid, neg, x).max(1)[0], torch.where(hid, neg, y).max(1)[0]
+            ct = torch.stack([(xmin + xmax) / 2, (ymin + ymax) / 2], 1)
+            kps.append(torch.cat((torch.stack((x, y), dim=2).reshape(k.size(0), -1), ct), 1))
+            boxes.append(torch.stack([xmin, ymin, xmax, ymax], 1))
+            vss.append(v)
+        return kps, boxes, vss
+
     def loss(self, cls_scores, bbox_pts_preds_init, bbox_pts_preds_refine, segm_pts_preds_init, segm_pts_preds_refine,
              pose_pts_preds_init, pose_pts_preds_refine, gt_bboxes, gt_extremes, gt_keypoints_vs, gt_masks, gt_labels,
              img_metas, gt_bboxes_ignore=None, return_aux=False):
@@ -553,8 +572,9 @@ class LSHead(nn.Module):
             tables['segm'] = self._pack(polys, polys[0].shape[1], dev)
         if task in ('pose_bbox', 'pose_kbox'):
             if task == 'pose_kbox':
-                raise NotImplementedError('pose_kbox target preparation is not built yet')
-            kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
+                kps, gt_bboxes, vss = self.process_keypoints_with_kbox(gt_keypoints_vs)
+            else:
+                kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
             tables['pose'] = self._pack(kps, kps[0].shape[1], dev)
             gt_vs = self._pack(vss, vss[0].shape[1], dev)
         gt_bb = self._pack(gt_bboxes, 4, dev)
@@ -590,8 +610,11 @@ class LSHead(nn.Module):
         if task == 'segm':
             polys, gt_bboxes = self.process_polygons(gt_masks)
             tables['segm'] = pack(polys, polys[0].shape[1])
-        if task == 'pose_bbox':
-            kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
+        if task in ('pose_bbox', 'pose_kbox'):
+            if task == 'pose_kbox':
+                kps, gt_bboxes, vss = self.process_keypoints_with_kbox(gt_keypoints_vs)
+            else:
+                kps, vss = self.process_keypoints_with_bbox(gt_bboxes, gt_keypoints_vs)
             tables['pose'] = pack(kps, kps[0].shape[1])
             gt_vs = pack(vss, vss[0].shape[1])
         bb = pack(gt_bboxes, 4)
@@ -643,7 +666,9 @@ class LSHead(nn.Module):
             off, P = int(pyr.offsets[l]), pyr.num_level[l]
             cs = cls_scores[l]
             Bc, C, H, W = cs.shape
-            rows = torch.as_strided(cs, (B * H * W, C), (cs.stride(3), 1))
+            if not (cs.stride(1) == 1 and cs.stride(2) == W * cs.stride(3) and (Bc == 1 or cs.stride(0) == H * W * cs.stride(3))):
+                cs = cs.contiguous(memory_format=torch.channels_last)      # rows below need pixel-major memory
+            rows = torch.as_strided(cs, (B * H * W, C), (cs.stride(3), 1), cs.storage_offset())
             lab = labels[:, off:off + P].reshape(-1)
             lw = lweights[:, off:off + P].reshape(-1)
             if fast_cls:

@@ -22,9 +22,55 @@ def warmup_lr(base_lr, it, warmup_iters=500, warmup_ratio=0.001):
     return base_lr * (1 - k)
 
 
+def grad_clip_of(cfg):
+    """``max_norm`` of the gradient clip: the reference configs carry it as
+    ``optimizer_config = dict(grad_clip=dict(max_norm=35, norm_type=2))`` (configs/lsnet/lsnet_bbox_r50_fpn_1x_coco.py:65,
+    consumed by OptimizerHook, mmcv/runner/hooks/optimizer.py:10-17); a top-level ``grad_clip`` is accepted too."""
+    clip = (cfg.get('optimizer_config') or {}).get('grad_clip') or cfg.get('grad_clip') or {}
+    nt = clip.get('norm_type', 2)
+    if clip and nt != 2:
+        raise ValueError(f'grad_clip norm_type={nt}: only the L2 norm is implemented')
+    return clip.get('max_norm')
+
+
+class LrSchedule:
+    """``lr_config = dict(policy='step', warmup='linear', warmup_iters=500, warmup_ratio=0.001, step=[8, 11])`` of
+    configs/_base_/schedules/schedule_1x.py (mmcv StepLrUpdaterHook + LrUpdaterHook.get_warmup_lr,
+    mmcv/runner/hooks/lr_updater.py:62-141, 144-172): the regular lr decays by ``gamma`` at each epoch in ``step``; during
+    the first ``warmup_iters`` iterations the (already decayed) regular lr is scaled linearly from ``warmup_ratio``.
+    Epochs need ``iters_per_epoch``; without it the lr never decays."""
+
+    def __init__(self, base_lr, lr_config=None, iters_per_epoch=None):
+        c = dict(lr_config or {})
+        policy = c.get('policy', 'step')
+        if policy not in ('step', 'fixed'):
+            raise ValueError(f'lr_config policy {policy!r} is not implemented (step / fixed)')
+        self.base_lr = base_lr
+        self.steps = sorted([c['step']] if isinstance(c.get('step'), int) else list(c.get('step') or [])) if policy == 'step' else []
+        self.gamma = c.get('gamma', 0.1)
+        self.warmup = c.get('warmup', 'linear')
+        if self.warmup not in (None, 'linear', 'constant', 'exp'):
+            raise ValueError(f'warmup {self.warmup!r}')
+        self.warmup_iters, self.warmup_ratio = c.get('warmup_iters', 500), c.get('warmup_ratio', 0.001)
+        self.iters_per_epoch = iters_per_epoch
+
+    def __call__(self, it):
+        lr = self.base_lr
+        if self.iters_per_epoch and self.steps:
+            epoch = it // self.iters_per_epoch
+            lr = lr * self.gamma ** sum(1 for s in self.steps if epoch >= s)
+        if self.warmup is None or it >= self.warmup_iters:
+            return lr
+        if self.warmup == 'constant':
+            return lr * self.warmup_ratio
+        if self.warmup == 'exp':
+            return lr * self.warmup_ratio ** (1 - it / self.warmup_iters)
+        return lr * (1 - (1 - it / self.warmup_iters) * (1 - self.warmup_ratio))
+
+
 class Trainer:
 
-    def __init__(self, cfg, device='cuda', distributed=False, bucket_cap_mb=64, model=None):
+    def __init__(self, cfg, device='cuda', distributed=False, bucket_cap_mb=64, model=None, iters_per_epoch=None):
         self.device = torch.device(device)
         self.model = model if model is not None else build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'),
                                                                     test_cfg=cfg.get('test_cfg'))
@@ -40,15 +86,15 @@ class Trainer:
         self.params = params
         self.optimizer = torch.optim.SGD(params, lr=opt['lr'], momentum=opt.get('momentum', 0.9),
                                          weight_decay=opt.get('weight_decay', 1e-4), foreach=True)
-        clip = cfg.get('grad_clip') or {}
-        self.max_norm = clip.get('max_norm')
+        self.max_norm = grad_clip_of(cfg)
+        self.lr_at = LrSchedule(self.base_lr, cfg.get('lr_config'), iters_per_epoch)
         self.iter = 0
 
     def step(self, batch, sync_log=False):
         """One training iteration on a per-GPU batch whose image is already on the device.  Returns the loss tensor
         (device) and log_vars (device tensors, or python floats when sync_log)."""
         for g in self.optimizer.param_groups:
-            g['lr'] = warmup_lr(self.base_lr, self.iter)
+            g['lr'] = self.lr_at(self.iter)
         self.optimizer.zero_grad(set_to_none=True)
         losses = self.model(**batch)
         loss, log_vars = parse_losses(losses, sync_log)
@@ -75,8 +121,10 @@ class GraphTrainer:
     Semantics are those of ``Trainer`` / the reference's OptimizerHook: grads averaged over ranks, L2 clip at
     ``max_norm`` on the averaged gradient, torch.optim.SGD update (dampening 0, no nesterov)."""
 
-    def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=16, model=None,
-                 kernel_timing=False):
+    def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=128, model=None,
+                 kernel_timing=False, iters_per_epoch=None):
+        """``capacity``: ground-truth instances per image the static buffers hold (COCO images carry up to ~100); a
+        batch with more makes ``load_batch`` grow the buffers and re-capture the graph."""
         self.device = torch.device(device)
         self.distributed = distributed
         self.model = model if model is not None else build_detector(cfg['model'], train_cfg=cfg.get('train_cfg'),
@@ -85,7 +133,8 @@ class GraphTrainer:
         self.core = self.model
         opt = cfg.get('optimizer', dict(lr=0.01, momentum=0.9, weight_decay=1e-4))
         self.base_lr, self.momentum, self.wd = opt['lr'], opt.get('momentum', 0.9), opt.get('weight_decay', 1e-4)
-        self.max_norm = (cfg.get('grad_clip') or {}).get('max_norm')
+        self.max_norm = grad_clip_of(cfg)
+        self.lr_at = LrSchedule(self.base_lr, cfg.get('lr_config'), iters_per_epoch)
         self.capacity = capacity
         self.kernel_timing = kernel_timing      # capture external event-record nodes around the library's kernels
         self.launches_per_step = 0              # liblsnet_sm100 kernels inside one replay
@@ -200,6 +249,17 @@ class GraphTrainer:
     def load_batch(self, batch):
         """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host).  The packed GT goes
         through two persistent pinned staging sets (no per-step cudaHostAlloc), guarded by an event each."""
+        need = max(int(b.shape[0]) for b in batch['gt_bboxes'])
+        if need > self.capacity:
+            # more instances than the static GT buffers hold: grow them (next power of two) and capture the step again
+            cap = self.capacity
+            while cap < need:
+                cap *= 2
+            self.capacity = cap
+            if hasattr(self, '_stage'):
+                del self._stage, self._stage_ev, self._stage_i
+            self.recaptures = getattr(self, 'recaptures', 0) + 1
+            self._capture(batch)
         self.img.copy_(batch['img'], non_blocking=True)
         if not hasattr(self, '_stage'):
             self._stage, self._stage_ev, self._stage_i = [], [], 0
@@ -230,13 +290,18 @@ class GraphTrainer:
         if self.distributed:
             dist.all_reduce(g)
             g.div_(dist.get_world_size())
-        lr = warmup_lr(self.base_lr, self.iter)
+        lr = self.lr_at(self.iter)
         # clip + weight decay + momentum + update in one pass over the flat buffers (lsnet_sgd_momentum_step)
         norm = torch.linalg.vector_norm(g) if self.max_norm is not None else None
         L.call('lsnet_sgd_momentum_step', L.ptr(self.flat_p), L.ptr(g), L.ptr(self.flat_m), L.c_ll(g.numel()),
                L.ptr(norm), L.c_f(float(self.max_norm or 0.0)), L.c_f(float(lr)), L.c_f(float(self.momentum)),
                L.c_f(float(self.wd)), L.stream())
         self.iter += 1
+        # the raw-pointer update does not bump the parameters' ``_version``: packs cached by an eager forward through this
+        # model (evaluation, parity runs) would go stale
+        from .ops import gemm_ops
+        if gemm_ops._PACK_CACHE:
+            gemm_ops._PACK_CACHE.clear()
         log = self.log_vars
         if sync_log:
             flat = torch.stack([v.detach().float() for v in log.values()])
