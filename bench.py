@@ -36,6 +36,16 @@ METRIC = 'images/sec training step, LSNet R50-FPN 800x1333'
 WORKLOAD = 'LSNet-bbox R50-FPN 800x1333 (padded 800x1344) bf16, batch 4/GPU, synthetic COCO-shaped'
 IMG_HW = (800, 1333)
 BATCH = 4
+# --config: BASELINE.json configs[1] (the default, the configuration the metric is quoted on) and configs[2..4]
+WORKLOADS = {
+    'bbox_r50': dict(workload=WORKLOAD, multiscale=None),
+    'bbox_x101dcn_ms': dict(workload='LSNet-bbox X-101-64x4d-DCN (DCNv2 groups=64 in c3-c5, with_cp), multi-scale short side '
+                                     '480-960 / long side <= 1333, bf16, batch 4/GPU, synthetic COCO-shaped', multiscale=(480, 960)),
+    'segm_r50': dict(workload='LSNet-seg R50-FPN, 36 contour landmarks, 800x1333 (padded 800x1344) bf16, batch 4/GPU, '
+                              'synthetic COCO-shaped', multiscale=None),
+    'pose_x101dcn': dict(workload='LSNet-pose X-101-64x4d-DCN, 17 keypoints + boxes (pose_bbox), 800x1333 (padded 800x1344) bf16, '
+                                  'batch 4/GPU, synthetic COCO-shaped', multiscale=None),
+}
 # kernel classes of lsnet_timing_collect (lsnet_internal.h): name -> what bounds it ('tensor': work = FLOPs, 'hbm': bytes)
 CLASS_NAMES = ['gemm_kmajor(tcgen05 GEMM/implicit conv)', 'gemm_mnmajor(tcgen05 weight grad)', 'dcn_im2col(gather)',
                'dcn_col2im(scatter)', 'dcn_fused_fwd(gather->smem->tcgen05)', 'dcn_fused_wgrad(gather->smem->tcgen05)',
@@ -193,9 +203,9 @@ def cpu_reference_step_factory(threads):
     return run
 
 
-def bench_config(world):
+def bench_config(world, name='bbox_r50'):
     """The workload description both arms print verbatim (the driver compares the two `config` objects)."""
-    return dict(workload=WORKLOAD, global_batch=BATCH * world, parallelism=f'dp{world}',
+    return dict(workload=WORKLOADS[name]['workload'], global_batch=BATCH * world, parallelism=f'dp{world}',
                 l2_policy='inputs+activations per step (>1 GB) far exceed the 126 MB L2; 4 rotating batches',
                 optimizer='SGD lr0.01 m0.9 wd1e-4, grad-clip 35, fp32 master weights')
 
@@ -241,8 +251,10 @@ def measured_traffic(kernel_class):
 def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     from lsnet_b200 import lib as L
-    from lsnet_b200.data import MODEL_CFG, synthetic_batch, to_device
+    from lsnet_b200.data import MODEL_CFG, TASK_OF, synthetic_batch, to_device
     from lsnet_b200.train import Trainer
+    cfg_name = args.config
+    task, ms = TASK_OF[cfg_name], WORKLOADS[cfg_name]['multiscale']
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     distributed = world > 1
@@ -250,15 +262,18 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
     nb = 4
-    host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True) for s in range(nb)]
+    # multi-scale: every image draws its own size, the canvas of a batch is rounded up to a multiple of 128 so that the
+    # CUDA-graph cache sees a handful of shape buckets (the valid extents per image stay exact: pad_shape)
+    host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True, task=task, multiscale=ms, canvas_multiple=128 if ms else None)
+            for s in range(nb)]
     resident = [to_device(b, dev) for b in host]
     mode = 'cuda-graph (fwd+loss+bwd captured; flat all-reduce + clip + SGD eager)'
     if args.eager:
-        tr = Trainer(MODEL_CFG['bbox_r50'], device=dev, distributed=distributed)
+        tr = Trainer(MODEL_CFG[cfg_name], device=dev, distributed=distributed)
         mode = 'eager (torch DDP)'
     else:
         from lsnet_b200.train import GraphTrainer
-        tr = GraphTrainer(MODEL_CFG['bbox_r50'], host[0], device=dev, distributed=distributed, kernel_timing=True)
+        tr = GraphTrainer(MODEL_CFG[cfg_name], host[0], device=dev, distributed=distributed, kernel_timing=True)
     torch.cuda.synchronize()
 
     def barrier():
@@ -281,7 +296,7 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         return float(ms)
 
-    for w in range(max(args.warmup, 3)):
+    for w in range(max(args.warmup, 3, nb if ms else 0)):     # multi-scale: every shape bucket captured before timing
         tr.step(resident[w % nb])
     lib = L.load()
     lib.lsnet_launch_count.restype = ctypes.c_ulonglong
@@ -314,7 +329,7 @@ def run_gpu(args, rank, world, local_rank):
     if not graph_mode:
         lib.lsnet_timing_reset()
     # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
-    h2d = host[0]['img'].numel() * 4
+    h2d = sum(b['img'].numel() * 4 for b in host) // nb
 
     def e2e_step(s):
         # graph mode: pinned host image -> static device buffer directly; eager: .to(device) then the step
@@ -355,7 +370,7 @@ def run_gpu(args, rank, world, local_rank):
                                  if v['ms'] > 0 else 0.0,
                                  unit='TFLOP/s' if any(t in k for t in TENSOR_BOUND) else 'GB/s') for k, v in classes.items()})
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and cfg_name == 'bbox_r50':
         try:
             threads = cpu_threads()
             run = cpu_reference_step_factory(threads)
@@ -371,7 +386,8 @@ def run_gpu(args, rank, world, local_rank):
             cpu = dict(value=None, unit='images/s', cores=cpu_threads(), kind='port', sample=f'failed: {e!r}')
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
-                data='synthetic', config=bench_config(world), step_mode=mode,
+                data='synthetic', config=bench_config(world, cfg_name), step_mode=mode,
+                shapes=sorted({tuple(b['img'].shape[-2:]) for b in host}),
                 e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clk)
@@ -387,12 +403,17 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--config', default='bbox_r50', choices=sorted(WORKLOADS),
+                    help="bbox_r50 = BASELINE.json configs[1] (default, the metric's configuration); the others are "
+                         'configs[2..4]')
     ap.add_argument('--eager', action='store_true', help='per-op eager step with torch DDP instead of the CUDA graph')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
+        if args.config != 'bbox_r50':
+            raise SystemExit('--impl reference is the CPU arm of the default configuration (bbox_r50) only')
         run_reference(args, rank, world)
         return
     run_gpu(args, rank, world, local_rank)

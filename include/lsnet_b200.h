@@ -44,6 +44,11 @@ void lsnet_timing_reset(void);
  * Needs N % 16 == 0, K % 8 == 0, 16-byte aligned row pitches. */
 int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M,
                     int N, int K, const float* bias, int relu, int out_fp32, void* stream);
+/* Block-diagonal product for grouped weights: out[M, N] (bf16), N = ntiles*64; column tile nt =
+ * A[:, (nt % cblks)*64 .. +63] . Bw[nt*64 .. +63, 0..63]^T with A bf16 [M, cblks*64], Bw bf16 [N, 64].  The dCol GEMM of a
+ * grouped DCN (per-group `addmm_` loop of deform_conv_cuda.cpp:746-749) without the groups-times redundant dense FLOPs. */
+int lsnet_gemm_blockdiag_bf16(const void* A, long long lda, const void* Bw, void* out, long long ldc, int M, int N,
+                              int cblks, void* stream);
 
 /* Stride-1 "same" convolution as an implicit GEMM: x NHWC bf16 [B,H,W,C] (pixel pitch ldp), Wt bf16
  * [N, kh*kw*C] (tap-major, channel-minor), out [B*H*W, ldc].  One shifted TMA box per filter tap; zero padding is
@@ -170,7 +175,7 @@ typedef struct lsnet_dcn_desc {
   int Ho, Wo;                  /* sampling / output grid (= offset grid) */
   int kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
   float scale_h, scale_w;      /* pyramid DCN: base grid scale (1 for DCNv1 / DCNv2) */
-  int groups;                  /* weight groups; must be 1 here (grouped: lsnet_dcn_grouped_*) */
+  int groups;                  /* weight groups; > 1 runs the block-diagonal kernels when lsnet_dcn_grouped_supported() */
   int deformable_groups;
   int mask_logits;
   int dtype;                   /* LSNET_DTYPE_BF16 */
@@ -183,6 +188,17 @@ void lsnet_dcn_fused_enable(int on);
 /* 1: the weight gradient of lsnet_dcn_backward_weight is reduced in a fixed order (per-split partials in the workspace +
  * a second pass) instead of fp32 atomics whose order varies from run to run (default: env LSNET_DETERMINISTIC, else 0). */
 void lsnet_set_deterministic(int on);
+/* Grouped weights (ResNeXt conv2 sites, mmdet/models/backbones/resnext.py:50-74: groups = 64, C = N = 512/1024/2048) run on
+ * 64-channel blocks that hold whole groups -- 1 when the descriptor qualifies (C == N, C % 256 == 0, 64 % (C/groups) == 0,
+ * deformable_groups == 1).  Operand layouts then are:
+ *   forward          Wp  bf16 [C, kh*kw*64]: row o, column tap*64 + j = weight of out channel o for input channel
+ *                        (o/64)*64 + j (zero when that channel is outside o's group)
+ *   backward_data    Wt  bf16 [kh*kw*C, 64]: row tap*C + blk*64 + j, column o' = weight of out channel blk*64 + o' for
+ *                        input channel blk*64 + j (zero outside the group)
+ *   backward_weight  dW  fp32 [C, kh*kw*256] (+=): row o, column tap*256 + c' = gradient for input channel (o/256)*256 + c'
+ *                        (the caller keeps the entries of o's own group)
+ * Otherwise callers expand the weight to a dense block-diagonal pack and pass groups = 1. */
+int lsnet_dcn_grouped_supported(const lsnet_dcn_desc* d, int N);
 size_t lsnet_dcn_forward_workspace_size(const lsnet_dcn_desc* d, int N);
 /* out[B*Ho*Wo, ldc] (bf16, or fp32 if out_fp32) = DCN(x; offset, mask) . Wp^T (+ bias) (ReLU).  Wp: bf16 [N, kh*kw*C]
  * (tap-major, channel-minor), N % 16 == 0 (rows beyond the real Cout are zero).  col_out (optional, bf16

@@ -48,6 +48,9 @@ struct FusedFwdArgs {
   int N;                              // logical output channels
   int tiles_h, tiles_w, TH, TW, tw_shift, num_tiles;   // TW = 1 << tw_shift
   int taps, cblks;
+  // grouped (block-diagonal weights on 64-channel blocks): every channel block is its own accumulation group -- 9 K
+  // blocks -> BN = 64 output columns at column offset cb * 64; weights packed [C, taps * 64]
+  int grouped;
   void* out;
   long long ldc;
   int out_fp32, relu;
@@ -110,6 +113,8 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_k_iters = p.taps * p.cblks;
+  const int acc_groups = p.grouped ? p.cblks : 1;               // accumulators per patch
+  const int k_per_group = p.grouped ? p.taps : num_k_iters;     // K blocks per accumulator
   const int per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0) {
@@ -123,7 +128,8 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sB = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kBBytes);
-            tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.g.C + cb * FK, 0);
+            if (p.grouped) tma_load_2d(sB, &tmB, &full_bar[stage], tap * FK, cb * FK);
+            else tma_load_2d(sB, &tmB, &full_bar[stage], tap * p.g.C + cb * FK, 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -138,24 +144,26 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int it = 0; it < num_k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int grp = 0; grp < acc_groups; ++grp) {
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sB = sA + Cfg::kABytes;
-          const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sB, 16, 1024);
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+          for (int it = 0; it < k_per_group; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sB = sA + Cfg::kABytes;
+            const uint64_t adesc = umma_desc_sw128(sA, 16, 1024);
+            const uint64_t bdesc = umma_desc_sw128(sB, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < FK / 16; ++k)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (it == num_k_iters - 1) umma_commit(&tfull_bar[as]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < FK / 16; ++k)
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (it == k_per_group - 1) umma_commit(&tfull_bar[as]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
   } else if (warp < F_G0) {
@@ -175,61 +183,65 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
       };
       bool valid;
       const long long row = row_of(r, &valid);
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      for (int grp = 0; grp < acc_groups; ++grp) {
+        const int n_base = grp * BN;          // first output column of this accumulator (grouped: the channel block)
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c, v);
-        tmem_ld_wait();
-        if (c >= p.N) continue;     // warp-uniform
-        float f[32];
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          const int c = n_base + c0;
+          if (c >= p.N) continue;     // warp-uniform
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c + j < p.N) f[j] += __ldg(p.bias + c + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.out_fp32) {
-          if (valid) {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + c;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.N) f[j] += __ldg(p.bias + c + j);
           }
-        } else {
-          // stage the 32x32 bf16 block in shared memory (row pitch 80 B), then store 8 rows x 64 contiguous bytes per
-          // warp instruction instead of 32 rows x 16 bytes
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 20 + j * 4) =
-                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          __syncwarp();
-          const int seg = lane & 3;
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_fp32) {
+            if (valid) {
+              float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + c;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = (lane >> 2) + 8 * i;
-            bool ok;
-            const long long grow = row_of(q * 32 + rr, &ok);
-            if (ok && c + seg * 8 < p.N) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + c + seg * 8) = val;
+              for (int j = 0; j < 32; j += 4)
+                if (c + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             }
+          } else {
+            // stage the 32x32 bf16 block in shared memory (row pitch 80 B), then store 8 rows x 64 contiguous bytes per
+            // warp instruction instead of 32 rows x 16 bytes
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 20 + j * 4) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            __syncwarp();
+            const int seg = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i;
+              bool ok;
+              const long long grow = row_of(q * 32 + rr, &ok);
+              if (ok && c + seg * 8 < p.N) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + c + seg * 8) = val;
+              }
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
     // ===================== gather warps (6..21): the A-operand producer =====================
@@ -374,6 +386,8 @@ struct FusedWgradArgs {
   int M;                               // couts (rows of dW)
   int tiles_h, tiles_w, TH, TW, tw_shift, k_chunks;   // 64-pixel patches: k_chunks = B * tiles_h * tiles_w
   int taps, n_tiles, m_groups, splits, chunks_per_split;
+  int diag;                            // grouped weights: only the tiles on the block diagonal (cout group == channel
+                                       // tile) are computed, written compactly as out[m, tap * 256 + c_in_tile]
   float* out;                          // dW [M, ldw]  (or the partial workspace in deterministic mode)
   long long ldw;
   long long split_stride;              // 0: accumulate with reds into `out`; else elements between per-split partials
@@ -417,6 +431,7 @@ dcn_fused_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const FusedWgrad
     *mg = item % p.m_groups; item /= p.m_groups;
     *nt = item % p.n_tiles; item /= p.n_tiles;
     *tap = item;
+    if (p.diag) *mg = *nt;
   };
 
   if (warp == 0) {
@@ -500,7 +515,8 @@ dcn_fused_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const FusedWgrad
           tmem_ld_wait();
           const int col0 = nt * 256 + c;
           if (m < p.M && col0 < p.g.C) {
-            float* o = obase + static_cast<long long>(m) * p.ldw + static_cast<long long>(tap) * p.g.C + col0;
+            float* o = obase + static_cast<long long>(m) * p.ldw +
+                       (p.diag ? static_cast<long long>(tap) * 256 + c : static_cast<long long>(tap) * p.g.C + col0);
             if (p.split_stride) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -703,7 +719,7 @@ static int launch_fused_fwd(const CUtensorMap& tmB, const FusedFwdArgs& a, cudaS
   }
   const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
   const double px = static_cast<double>(a.g.B) * a.g.Ho * a.g.Wo;
-  const int th = timing_begin(TC_DCN_FWD, 2.0 * px * a.N * a.taps * a.g.C, st);
+  const int th = timing_begin(TC_DCN_FWD, 2.0 * px * a.N * a.taps * (a.grouped ? FK : a.g.C), st);
   dcn_fused_fwd_kernel<BN, STAGES, SAVE_COL><<<grid, F_THREADS, Cfg::kSmemBytes, st>>>(tmB, a);
   timing_end(th, st);
   cudaError_t e = cudaGetLastError();
@@ -723,10 +739,12 @@ static int dispatch_fused_fwd(const CUtensorMap& tmB, const FusedFwdArgs& a, cud
   return stages == 3 ? launch_fused_fwd<BN, 3, false>(tmB, a, st) : launch_fused_fwd<BN, 2, false>(tmB, a, st);
 }
 
+// grouped != 0: Wp is the block-diagonal pack [N = C, taps * 64] (see lsnet_dcn_forward)
 int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, const float* mask, const void* Wp, int N,
-                      const float* bias, int relu, void* out, long long ldc, int out_fp32, void* col,
-                      cudaStream_t st) {
+                      const float* bias, int relu, void* out, long long ldc, int out_fp32, void* col, cudaStream_t st,
+                      int grouped) {
   FusedFwdArgs a{};
+  a.grouped = grouped ? 1 : 0;
   a.g = g;
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.offset = offset;
@@ -744,8 +762,8 @@ int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, cons
   a.num_tiles = g.B * a.tiles_h * a.tiles_w;
   a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
   a.col = static_cast<__nv_bfloat16*>(col);
-  const int BN = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-  const long long K = static_cast<long long>(a.taps) * g.C;
+  const int BN = grouped ? 64 : (N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)));
+  const long long K = grouped ? static_cast<long long>(a.taps) * FK : static_cast<long long>(a.taps) * g.C;
   CUtensorMap tmB;
   if (int rc = make_map_2d(&tmB, Wp, N, K, K, 64, BN)) return rc;
   switch (BN) {
@@ -759,24 +777,25 @@ int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, cons
 
 // Weight gradient with re-sampled columns.  `partial` (optional, fp32 [splits, M, ldw] from
 // dcn_fused_wgrad_partial_bytes) selects the deterministic two-stage reduction.
-static int wgrad_splits(const DcnGeom& g, int M, int* k_chunks, int* TH, int* TW) {
+static int wgrad_splits(const DcnGeom& g, int M, int* k_chunks, int* TH, int* TW, int diag = 0) {
   pick_patch(g.Ho, g.Wo, WK, TH, TW);
   *k_chunks = g.B * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
-  const int base = g.kh * g.kw * ((g.C + 255) / 256) * ((M + 255) / 256);
+  const int base = g.kh * g.kw * ((g.C + 255) / 256) * (diag ? 1 : (M + 255) / 256);
   int splits = (num_sms() + base / 2) / base;          // ~ one item per SM
   if (splits > *k_chunks) splits = *k_chunks;
   if (splits < 1) splits = 1;
   return splits;
 }
 
-size_t dcn_fused_wgrad_partial_bytes(const DcnGeom& g, int M, long long ldw) {
+size_t dcn_fused_wgrad_partial_bytes(const DcnGeom& g, int M, long long ldw, int diag) {
   int kc, TH, TW;
-  const int splits = wgrad_splits(g, M, &kc, &TH, &TW);
+  const int splits = wgrad_splits(g, M, &kc, &TH, &TW, diag);
   return static_cast<size_t>(splits) * M * ldw * sizeof(float);
 }
 
+// diag != 0 (grouped weights, M == C): dW is the compact [M, taps * 256] block-diagonal form (ldw = taps * 256)
 int dcn_fused_wgrad(const DcnGeom& g, const void* dy, long long ldy, int M, const void* x, const float* offset,
-                    const float* mask, float* dW, long long ldw, float* partial, cudaStream_t st) {
+                    const float* mask, float* dW, long long ldw, float* partial, cudaStream_t st, int diag) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(dcn_fused_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM);
@@ -790,7 +809,8 @@ int dcn_fused_wgrad(const DcnGeom& g, const void* dy, long long ldy, int M, cons
   a.mask = mask;
   a.M = M;
   int TH = 4, TW = 16, kc = 0;
-  a.splits = wgrad_splits(g, M, &kc, &TH, &TW);
+  a.diag = diag ? 1 : 0;
+  a.splits = wgrad_splits(g, M, &kc, &TH, &TW, diag);
   a.k_chunks = kc;
   a.TH = TH; a.TW = TW;
   a.tw_shift = 0;
@@ -799,7 +819,7 @@ int dcn_fused_wgrad(const DcnGeom& g, const void* dy, long long ldy, int M, cons
   a.tiles_w = (g.Wo + TW - 1) / TW;
   a.taps = g.kh * g.kw;
   a.n_tiles = (g.C + 255) / 256;
-  a.m_groups = (M + 255) / 256;
+  a.m_groups = diag ? 1 : (M + 255) / 256;
   a.chunks_per_split = (kc + a.splits - 1) / a.splits;
   a.ldw = ldw;
   if (partial) {
@@ -816,7 +836,7 @@ int dcn_fused_wgrad(const DcnGeom& g, const void* dy, long long ldy, int M, cons
   const int items = a.taps * a.n_tiles * a.m_groups * a.splits;
   const int grid = items < num_sms() ? items : num_sms();
   const double px = static_cast<double>(g.B) * g.Ho * g.Wo;
-  const int th = timing_begin(TC_DCN_WGRAD, 2.0 * px * M * a.taps * g.C, st);
+  const int th = timing_begin(TC_DCN_WGRAD, 2.0 * px * M * a.taps * (diag ? 256 : g.C), st);
   dcn_fused_wgrad_kernel<<<grid, F_THREADS, W_SMEM, st>>>(tmA, a);
   if (partial) {
     const long long n4 = static_cast<long long>(M) * ldw / 4;

@@ -33,6 +33,9 @@ struct GemmArgs {
   long long ldc;
   int out_fp32, relu;
   const float* bias;   // [N] or null
+  // block-diagonal mode (grouped DCN dCol): ONE K block per tile; the N tile nt (64 columns) multiplies the 64-column
+  // block (nt % blockdiag) of A with B[n0 .. n0+63, 0..63]; 0 = off
+  int blockdiag;
 };
 
 template <int BN>
@@ -115,7 +118,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tma_load_4d(sA, &tmA, &full_bar[stage], cb * BK, w0 - p.pad_w + dx * p.dil_w,
                         h0 - p.pad_h + dy * p.dil_h, b);
           } else {
-            tma_load_2d(sA, &tmA, &full_bar[stage], it * BK, m0);
+            tma_load_2d(sA, &tmA, &full_bar[stage], p.blockdiag ? (nt % p.blockdiag) * BK : it * BK, m0);
           }
           tma_load_2d(sB, &tmB, &full_bar[stage], it * BK, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -603,6 +606,21 @@ extern "C" int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, lon
   a.M = M; a.N = N; a.num_k_iters = (K + BK - 1) / BK; a.m_tiles = (M + BM - 1) / BM;
   a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
   return dispatch_kmajor(tmA, Bw, N, K, ldb, a, static_cast<cudaStream_t>(stream));
+}
+
+// out[M, N] (bf16) with N = nblk_rows * 64: column tile nt = A[:, (nt % cblks) * 64 .. +63] . Bw[nt * 64 .. +63, 0..63]^T
+extern "C" int lsnet_gemm_blockdiag_bf16(const void* A, long long lda, const void* Bw, void* out, long long ldc, int M,
+                                         int N, int cblks, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if ((N % 64) || cblks < 1 || (lda % 8) || (ldc % 8) || lda < 64LL * cblks)
+    return set_error("lsnet_gemm_blockdiag_bf16: need N %% 64 == 0, cblks >= 1, 16-byte aligned pitches");
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_2d(&tmA, A, M, 64ull * cblks, lda, 64, BM)) return rc;
+  if (int rc = make_map_2d(&tmB, Bw, N, 64, 64, 64, 64)) return rc;
+  GemmArgs a{};
+  a.M = M; a.N = N; a.num_k_iters = 1; a.m_tiles = (M + BM - 1) / BM; a.n_tiles = N / 64;
+  a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = 0; a.relu = 0; a.bias = nullptr; a.blockdiag = cblks;
+  return launch_kmajor<64>(tmA, tmB, a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt,

@@ -91,10 +91,53 @@ def dcn_col2im(gcol, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, 
 SAVE_COL = os.environ.get('LSNET_DCN_SAVE_COL', '1') == '1'
 
 
-def _desc(x_geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits):
+def _desc(x_geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits, groups=1):
     B, H, W, C, ldx = x_geom
     return L.DcnDesc(B, H, W, C, ldx, Ho, Wo, kh, kw, stride[0], stride[1], pad[0], pad[1], dil[0], dil[1],
-                     float(scales[0]), float(scales[1]), 1, dg, int(bool(mask_logits)), L.DTYPE_BF16)
+                     float(scales[0]), float(scales[1]), groups, dg, int(bool(mask_logits)), L.DTYPE_BF16)
+
+
+def grouped_native(C, N, kh, kw, groups, dg):
+    """True when the library runs this grouped weight on its block-diagonal kernels (lsnet_dcn_grouped_supported)."""
+    import ctypes
+    if groups <= 1:
+        return False
+    d = L.DcnDesc(1, 8, 8, C, C, 8, 8, kh, kw, 1, 1, 1, 1, 1, 1, 1.0, 1.0, groups, dg, 0, L.DTYPE_BF16)
+    return bool(L.load().lsnet_dcn_grouped_supported(ctypes.byref(d), L.c_int(N)))
+
+
+def pack_grouped_fwd(w, groups):
+    """(C, C/groups, kh, kw) -> bf16 [C, kh*kw*64]: row o, column tap*64 + j = weight of out channel o for input channel
+    (o // 64) * 64 + j (zero outside o's group)."""
+    C, cpg, kh, kw = w.shape
+    taps = kh * kw
+    o = torch.arange(C, device=w.device)
+    j0 = (o // cpg) * cpg - (o // 64) * 64
+    out = torch.zeros((C, taps, 64), device=w.device, dtype=torch.bfloat16)
+    jj = j0[:, None, None] + torch.arange(cpg, device=w.device)[None, None, :]
+    out[o[:, None, None], torch.arange(taps, device=w.device)[None, :, None], jj] = \
+        w.permute(0, 2, 3, 1).reshape(C, taps, cpg).to(torch.bfloat16)
+    return out.view(C, taps * 64)
+
+
+def pack_grouped_bwd(w, groups):
+    """bf16 [kh*kw*C, 64]: row tap*C + blk*64 + j, column o' = weight of out channel blk*64 + o' for input channel
+    blk*64 + j."""
+    C, cpg, kh, kw = w.shape
+    taps = kh * kw
+    wg = pack_grouped_fwd(w, groups).view(C // 64, 64, taps, 64)          # [blk, o', tap, j]
+    return wg.permute(2, 0, 3, 1).reshape(taps * C, 64).contiguous()
+
+
+def unpack_grouped_dw(dwc, groups, kh, kw, dtype):
+    """compact [C, kh*kw*256] fp32 (row o: its 256-channel tile per tap) -> (C, C/groups, kh, kw)."""
+    C = dwc.shape[0]
+    cpg, taps = C // groups, kh * kw
+    o = torch.arange(C, device=dwc.device)
+    j0 = ((o % 256) // cpg) * cpg
+    jj = j0[:, None, None] + torch.arange(cpg, device=dwc.device)[None, None, :]
+    d = dwc.view(C, taps, 256)[o[:, None, None], torch.arange(taps, device=dwc.device)[None, :, None], jj]   # (C,taps,cpg)
+    return d.permute(0, 2, 1).reshape(C, cpg, kh, kw).to(dtype)
 
 
 def _workspace(nbytes, device):
@@ -102,7 +145,7 @@ def _workspace(nbytes, device):
 
 
 def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False,
-                out=None, out_dtype=torch.bfloat16, relu=False, save_col=False):
+                out=None, out_dtype=torch.bfloat16, relu=False, save_col=False, groups=1):
     """Whole forward operator.  x (B,C,H,W) channels_last bf16; wp bf16 [Npad16, kh*kw*C]; returns (out2d [P, N], col or
     None).  ``out``: write into this [P, N] view (row pitch = out.stride(0))."""
     import ctypes
@@ -113,11 +156,11 @@ def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, sca
     if mask is not None:
         mask, ldm = _pix_major(mask)
     N, P = wp.shape[0], B * Ho * Wo
-    assert wp.dtype == torch.bfloat16 and wp.is_contiguous() and wp.shape[1] == kh * kw * C
+    assert wp.dtype == torch.bfloat16 and wp.is_contiguous() and wp.shape[1] == kh * kw * (64 if groups > 1 else C)
     if out is None:
         out = torch.empty((P, N), device=x.device, dtype=out_dtype)
     assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
-    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits, groups)
     col = torch.empty((P, kh * kw * C), device=x.device, dtype=torch.bfloat16) if save_col else None
     ws_bytes = 0 if save_col else L.load().lsnet_dcn_forward_workspace_size(ctypes.byref(d), L.c_int(N))
     ws = _workspace(ws_bytes, x.device)
@@ -128,7 +171,7 @@ def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, sca
 
 
 def dcn_backward_data(gy2, wt, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, need_dx=True,
-                      dx_fp32=None, mask_logits=False, packed_out=False):
+                      dx_fp32=None, mask_logits=False, packed_out=False, groups=1):
     """Whole backward-data operator: gy2 bf16 [P, N]; wt bf16 [kh*kw*C, N].  Returns (dx, doffset, dmask) as logical
     NCHW views (see dcn_col2im for ``packed_out``)."""
     import ctypes
@@ -139,8 +182,9 @@ def dcn_backward_data(gy2, wt, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil
     if mask is not None:
         mask, ldm = _pix_major(mask)
     taps = kh * kw
-    N = wt.shape[1]
-    assert gy2.dtype == torch.bfloat16 and gy2.stride(1) == 1 and gy2.shape[1] == N and wt.is_contiguous()
+    N = gy2.shape[1]
+    assert gy2.dtype == torch.bfloat16 and gy2.stride(1) == 1 and wt.is_contiguous() and \
+        wt.shape == (taps * C, 64 if groups > 1 else N)
     dx_fp32 = DX_FP32 if dx_fp32 is None else dx_fp32
     dx = torch.zeros((B, H, W, C), device=x.device, dtype=torch.float32 if dx_fp32 else torch.bfloat16) if need_dx else None
     if packed_out:
@@ -152,7 +196,7 @@ def dcn_backward_data(gy2, wt, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil
         doff = torch.empty((B, Ho, Wo, dg * 2 * taps), device=x.device, dtype=torch.float32)
         dmask = torch.empty((B, Ho, Wo, dg * taps), device=x.device, dtype=torch.float32) if mask is not None else None
         lddo, lddm = dg * 2 * taps, dg * taps
-    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits, groups)
     ws_bytes = L.load().lsnet_dcn_backward_data_workspace_size(ctypes.byref(d), L.c_int(N))
     ws = _workspace(ws_bytes, x.device)
     L.call('lsnet_dcn_backward_data', ctypes.byref(d), L.ptr(gy2), L.c_ll(gy2.stride(0)), L.c_int(N), L.ptr(wt), L.ptr(x),
@@ -165,8 +209,9 @@ def dcn_backward_data(gy2, wt, x, offset, mask, Ho, Wo, kh, kw, stride, pad, dil
 
 
 def dcn_backward_weight(gy2, x, offset, mask, col, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False,
-                        out=None):
-    """dW [N, kh*kw*C] fp32 (+= into ``out``) from gy2 bf16 [P, N] and either the saved columns or a re-sampling of x."""
+                        out=None, groups=1):
+    """dW [N, kh*kw*C] fp32 (+= into ``out``) from gy2 bf16 [P, N] and either the saved columns or a re-sampling of x.
+    groups > 1: the compact block-diagonal form [N, kh*kw*256] (unpack_grouped_dw)."""
     import ctypes
     geom = G.nhwc_geom(x)
     B, H, W, C, ldx = geom
@@ -174,11 +219,11 @@ def dcn_backward_weight(gy2, x, offset, mask, col, Ho, Wo, kh, kw, stride, pad, 
     ldm = 0
     if mask is not None:
         mask, ldm = _pix_major(mask)
-    N, K = gy2.shape[1], kh * kw * C
+    N, K = gy2.shape[1], kh * kw * (256 if groups > 1 else C)
     if out is None:
         out = torch.zeros((N, K), device=x.device, dtype=torch.float32)
     assert out.dtype == torch.float32 and out.stride(1) == 1
-    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits)
+    d = _desc(geom, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits, groups)
     ws_bytes = L.load().lsnet_dcn_backward_weight_workspace_size(ctypes.byref(d), L.c_int(N), L.c_int(int(col is not None)))
     ws = _workspace(ws_bytes, x.device)
     L.call('lsnet_dcn_backward_weight', ctypes.byref(d), L.ptr(gy2), L.c_ll(gy2.stride(0)), L.c_int(N), L.ptr(x),
@@ -234,13 +279,18 @@ class _DCN(Function):
         cfg = (Ho, Wo, kh, kw, stride, pad, dil, scales, dg)
         ctx.packed_om = packed_om
         npad = (co + 15) // 16 * 16
+        # grouped weights: the library's block-diagonal kernels when the shape qualifies (X-101 sites), else the dense
+        # kernels on the zero-expanded weight
+        ctx.native_groups = native = groups if grouped_native(ci, co, kh, kw, groups, dg) else 1
 
         def pack_fwd(t):
+            if native > 1:
+                return pack_grouped_fwd(t, groups)
             p = _expand_groups(t, groups).permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(torch.bfloat16)
             if npad != co:
                 p = torch.cat([p, p.new_zeros(npad - co, p.shape[1])], 0)
             return p.contiguous()
-        wp = G.cached_pack(weight, 'dcn_fwd%d' % groups, pack_fwd)
+        wp = G.cached_pack(weight, 'dcn_fwd%d_%d' % (groups, native), pack_fwd)
         b = None
         if bias is not None:
             b = G.cached_pack(bias, 'bias%d' % npad, lambda t: torch.cat([t.float(), t.new_zeros(npad - co).float()]))
@@ -250,7 +300,7 @@ class _DCN(Function):
             off_v, mask_v, logits = offset[:, :n2], offset[:, n2:], True
         else:
             off_v, mask_v, logits = offset.detach(), None if mask is None else mask.detach(), False
-        save_col = SAVE_COL and weight.requires_grad
+        save_col = SAVE_COL and weight.requires_grad and native == 1
         out2d = None
         if out_slice is not None:
             # write straight into channels [c0, c0+co) of a wider pixel-major buffer (replaces a later torch.cat)
@@ -259,7 +309,7 @@ class _DCN(Function):
             ld = buf.shape[3]
             out2d = torch.as_strided(buf, (B * Ho * Wo, co), (ld, 1), buf.storage_offset() + c0)
         out2d, col = dcn_forward(x, off_v, mask_v, wp, b, *cfg, mask_logits=logits, out=out2d,
-                                 out_dtype=torch.float32 if out_fp32 else torch.bfloat16, save_col=save_col)
+                                 out_dtype=torch.float32 if out_fp32 else torch.bfloat16, save_col=save_col, groups=native)
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
         ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
@@ -292,7 +342,12 @@ class _DCN(Function):
         else:
             off_v, mask_v, logits = offset.detach(), None if mask is None else mask.detach(), False
 
+        native = ctx.native_groups
+
         def wgrad():
+            if native > 1:
+                dwc = dcn_backward_weight(gy2, x, off_v, mask_v, None, *ctx.cfg, mask_logits=logits, groups=native)
+                return unpack_grouped_dw(dwc[:co], native, kh, kw, weight.dtype)
             direct = ctx.grad2d
             if direct is not None and tuple(direct.shape) != (cop, kh * kw * ci):
                 direct = None
@@ -312,13 +367,15 @@ class _DCN(Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or (mask is not None and ctx.needs_input_grad[2]):
             # B operand [N = taps*ci, K = co]: W^T, K-major
             def pack_bwd(t):
+                if native > 1:
+                    return pack_grouped_bwd(t, groups)
                 p = _expand_groups(t, groups).permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16)
                 if cop != co:
                     p = torch.cat([p, p.new_zeros(p.shape[0], cop - co)], 1)
                 return p.contiguous()
-            wt = G.cached_pack(weight, 'dcn_bwd%d_%d' % (cop, groups), pack_bwd)
+            wt = G.cached_pack(weight, 'dcn_bwd%d_%d_%d' % (cop, groups, native), pack_bwd)
             gx, goff, gmask = dcn_backward_data(gy2, wt, x, off_v, mask_v, *ctx.cfg, need_dx=ctx.needs_input_grad[0],
-                                                mask_logits=logits, packed_out=ctx.packed_om)
+                                                mask_logits=logits, packed_out=ctx.packed_om, groups=native)
             if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
         if side is not None:

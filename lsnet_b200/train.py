@@ -122,7 +122,7 @@ class GraphTrainer:
     ``max_norm`` on the averaged gradient, torch.optim.SGD update (dampening 0, no nesterov)."""
 
     def __init__(self, cfg, sample_batch, device='cuda', distributed=False, capacity=128, model=None,
-                 kernel_timing=False, iters_per_epoch=None):
+                 kernel_timing=False, iters_per_epoch=None, max_graphs=8):
         """``capacity``: ground-truth instances per image the static buffers hold (COCO images carry up to ~100); a
         batch with more makes ``load_batch`` grow the buffers and re-capture the graph."""
         self.device = torch.device(device)
@@ -137,7 +137,6 @@ class GraphTrainer:
         self.lr_at = LrSchedule(self.base_lr, cfg.get('lr_config'), iters_per_epoch)
         self.capacity = capacity
         self.kernel_timing = kernel_timing      # capture external event-record nodes around the library's kernels
-        self.launches_per_step = 0              # liblsnet_sm100 kernels inside one replay
         self.iter = 0
         if distributed:     # identical replicas: broadcast rank 0's initial parameters/buffers once
             for t in list(self.model.parameters()) + list(self.model.buffers()):
@@ -167,59 +166,99 @@ class GraphTrainer:
                 p.data = self.flat_p[o:o + k].view_as(p)
                 p.grad = self.flat_g[o:o + k].view_as(p)
             o += (k + al - 1) // al * al
-        # ---- static inputs ----
-        self.img = torch.empty_like(sample_batch['img'], device=self.device).contiguous(memory_format=torch.channels_last)
-        self.metas = sample_batch['img_metas']
-        self.sizes = None
-        self.gt = None
-        self.graph = None
-        self.loss = None
-        self.log_vars = None
-        self._capture(sample_batch)
+        # ---- captured steps, one per input canvas (H, W): multi-scale training (configs/lsnet/*mstrain*) replays the
+        # graph of the batch's shape bucket; all graphs share ONE memory pool (they never run concurrently), so the
+        # footprint is that of the largest shape ----
+        self.steps = {}
+        self.max_graphs = max_graphs
+        self._pool = None
+        self.recaptures = 0
+        self.cur = self._entry(sample_batch)
 
-    def _pack(self, batch, pin=False):
-        return self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes,
-                                           self.device, gt_extremes=batch.get('gt_extremes'),
-                                           gt_keypoints_vs=batch.get('gt_keypoints'), gt_masks=batch.get('gt_masks'),
-                                           capacity=self.capacity, pin=pin)
+    # per-shape state: static image / GT buffers, the captured graph, its loss tensors, pinned GT staging
+    class _Step:
+        pass
 
-    def _fwd_bwd(self):
+    @property
+    def graph(self):
+        return self.cur.graph
+
+    @property
+    def graph_timed(self):
+        return self.cur.graph_timed
+
+    @property
+    def loss(self):
+        return self.cur.loss
+
+    @property
+    def log_vars(self):
+        return self.cur.log_vars
+
+    @property
+    def launches_per_step(self):
+        return self.cur.launches
+
+    def _gt_kwargs(self, batch):
+        return dict(gt_extremes=batch.get('gt_extremes'), gt_keypoints_vs=batch.get('gt_keypoints'),
+                    gt_masks=batch.get('gt_masks'))
+
+    def _fwd_bwd(self, st):
         self.flat_g.zero_()
-        losses = self.model(img=self.img, img_metas=self.metas, gt_bboxes=self.gt, gt_labels=None)
+        losses = self.model(img=st.img, img_metas=st.metas, gt_bboxes=st.gt, gt_labels=None)
         loss, log_vars = parse_losses(losses)
         loss.backward()
         return loss, log_vars
 
+    def _entry(self, batch):
+        key = tuple(batch['img'].shape)
+        st = self.steps.get(key)
+        if st is None:
+            if len(self.steps) >= self.max_graphs:          # drop the least recently used shape
+                old = min(self.steps, key=lambda k: self.steps[k].last_use)
+                del self.steps[old]
+            st = self._capture(batch)
+            self.steps[key] = st
+        st.last_use = self.iter
+        return st
+
     def _capture(self, batch):
         from .ops import gemm_ops
+        st = GraphTrainer._Step()
         with torch.no_grad():          # pyramid geometry of this input size
             feats = self.core.extract_feat(batch['img'][:1].to(self.device))
-        self.sizes = [tuple(f.shape[-2:]) for f in feats]
+        st.sizes = [tuple(f.shape[-2:]) for f in feats]
         del feats
-        self.img.copy_(batch['img'].to(self.device))
-        self.gt = self._pack(batch)
+        st.img = torch.empty_like(batch['img'], device=self.device).contiguous(memory_format=torch.channels_last)
+        st.img.copy_(batch['img'].to(self.device))
+        st.metas = batch['img_metas']
+        head = self.core.bbox_head
+        st.gt = head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes, self.device,
+                             capacity=self.capacity, **self._gt_kwargs(batch))
         # warm-up on a side stream (allocator / cuDNN autotune / cudaFuncSetAttribute happen outside the capture)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
-                self._fwd_bwd()
+                self._fwd_bwd(st)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         gemm_ops._PACK_CACHE.clear()           # the packs must be re-done INSIDE the captured region
         from . import lib as L
         lib = L.load()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
         n0 = L.launch_count()
-        self.graph = torch.cuda.CUDAGraph()
+        st.graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
-            self.loss, self.log_vars = self._fwd_bwd()
-        self.launches_per_step = L.launch_count() - n0
+        with torch.cuda.graph(st.graph, pool=self._pool, capture_error_mode='thread_local'):
+            st.loss, st.log_vars = self._fwd_bwd(st)
+        st.launches = L.launch_count() - n0
         gemm_ops._PACK_CACHE.clear()
-        self.graph_timed = None
-        if self.kernel_timing:
-            # a second, instrumented capture of the same step: external event-record nodes around every library
-            # kernel.  Kept apart from the graph that is timed end-to-end because ~500 event nodes perturb it.
+        st.graph_timed = None
+        if self.kernel_timing and not self.steps:
+            # a second, instrumented capture of the same step (first shape only): external event-record nodes around every
+            # library kernel.  Kept apart from the graph that is timed end-to-end because ~500 event nodes perturb it.
             # SERIALISED: the head's stream parallelism is switched off for this capture, so every kernel runs alone and
             # its event-bracketed duration is the kernel's own (as in an ncu launch list), not a share of a busy GPU.
             from .modules import head as _head
@@ -228,13 +267,16 @@ class GraphTrainer:
             try:
                 lib.lsnet_timing_reset()
                 lib.lsnet_timing_enable(1)
-                self.graph_timed = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph_timed, capture_error_mode='thread_local'):
-                    self._fwd_bwd()
+                st.graph_timed = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(st.graph_timed, capture_error_mode='thread_local'):
+                    self._fwd_bwd(st)
                 lib.lsnet_timing_enable(0)
             finally:
                 _head.TOWER_STREAMS, _head.LEVEL_STREAMS, _head.REFINE_SPLIT = saved
             gemm_ops._PACK_CACHE.clear()
+        st.stage = None
+        st.last_use = self.iter
+        return st
 
     def replay_instrumented(self):
         """One forward+backward through the instrumented, serialised graph (gradients only; no optimizer step).
@@ -247,40 +289,36 @@ class GraphTrainer:
         return e0.elapsed_time(e1)
 
     def load_batch(self, batch):
-        """Refresh the static inputs from a batch (host or device image tensor; GT lists on the host).  The packed GT goes
-        through two persistent pinned staging sets (no per-step cudaHostAlloc), guarded by an event each."""
+        """Select (or capture) the step of the batch's canvas and refresh its static inputs (host or device image tensor;
+        GT lists on the host).  The packed GT goes through two persistent pinned staging sets per shape (no per-step
+        cudaHostAlloc), guarded by an event each."""
         need = max(int(b.shape[0]) for b in batch['gt_bboxes'])
         if need > self.capacity:
-            # more instances than the static GT buffers hold: grow them (next power of two) and capture the step again
+            # more instances than the static GT buffers hold: grow them (next power of two) and capture the steps again
             cap = self.capacity
             while cap < need:
                 cap *= 2
             self.capacity = cap
-            if hasattr(self, '_stage'):
-                del self._stage, self._stage_ev, self._stage_i
-            self.recaptures = getattr(self, 'recaptures', 0) + 1
-            self._capture(batch)
-        self.img.copy_(batch['img'], non_blocking=True)
-        if not hasattr(self, '_stage'):
-            self._stage, self._stage_ev, self._stage_i = [], [], 0
+            self.steps.clear()
+            self.recaptures += 1
+        st = self.cur = self._entry(batch)
+        head = self.core.bbox_head
+        st.img.copy_(batch['img'], non_blocking=True)
+        if st.stage is None:
+            st.stage, st.stage_ev, st.stage_i = [], [], 0
             for _ in range(2):
-                host = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes,
-                                                   'cpu', gt_extremes=batch.get('gt_extremes'),
-                                                   gt_keypoints_vs=batch.get('gt_keypoints'),
-                                                   gt_masks=batch.get('gt_masks'), capacity=self.capacity, pin=True)
-                self._stage.append(host)
-                self._stage_ev.append(torch.cuda.Event())
-        i = self._stage_i
-        self._stage_i ^= 1
-        self._stage_ev[i].synchronize()          # the previous async copy out of this staging set has finished
-        fresh = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], self.sizes, 'cpu',
-                                            gt_extremes=batch.get('gt_extremes'),
-                                            gt_keypoints_vs=batch.get('gt_keypoints'), gt_masks=batch.get('gt_masks'),
-                                            capacity=self.capacity, pin=False)
-        st = self._stage[i]
-        st.copy_from(fresh)                       # host -> pinned host (a few KB)
-        self.gt.copy_from(st)                     # pinned host -> static device buffers, async
-        self._stage_ev[i].record()
+                st.stage.append(head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes, 'cpu',
+                                             capacity=self.capacity, pin=True, **self._gt_kwargs(batch)))
+                st.stage_ev.append(torch.cuda.Event())
+        i = st.stage_i
+        st.stage_i ^= 1
+        st.stage_ev[i].synchronize()          # the previous async copy out of this staging set has finished
+        fresh = head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes, 'cpu',
+                             capacity=self.capacity, pin=False, **self._gt_kwargs(batch))
+        sg = st.stage[i]
+        sg.copy_from(fresh)                   # host -> pinned host (a few KB)
+        st.gt.copy_from(sg)                   # pinned host -> static device buffers, async
+        st.stage_ev[i].record()
 
     def step(self, batch=None, sync_log=False):
         if batch is not None:

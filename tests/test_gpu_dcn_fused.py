@@ -289,3 +289,43 @@ def test_fused_weight_gradient(case):
     for nm, t in (('fused', dw_f), ('deterministic', dw_d1), ('columns', dw_u), ('resampled', dw_u2)):
         assert _rel(t, ref) < 2e-3, (name, nm, _rel(t, ref))
     assert _rel(acc - 0.5, ref) < 2e-3, name
+
+
+@pytest.mark.parametrize('C,groups,stride', [(256, 64, 1), (512, 64, 2), (256, 8, 1)])
+def test_grouped_dcn_native_vs_oracle(C, groups, stride):
+    """DCNv2 with grouped weights on the library's block-diagonal kernels (the X-101-64x4d backbone sites, groups = 64,
+    stride 2 in the first block of a stage: resnext.py:50-74, 114-118): forward, dX, dOffset, dMask, dW against the grouped
+    oracle, and against the dense kernels on the zero-expanded weight."""
+    ops = _ops()
+    import lsnet_b200.ops.dcn as dcn_mod
+    assert dcn_mod.grouped_native(C, C, 3, 3, groups, 1)
+    B, H, W = 2, 12, 14
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    g = torch.Generator().manual_seed(C + groups + stride)
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    off = torch.randn(B, 18, Ho, Wo, generator=g) * 1.5
+    mask = torch.rand(B, 9, Ho, Wo, generator=g)
+    w = _bf(torch.randn(C, C // groups, 3, 3, generator=g) / (C // groups * 9) ** 0.5)
+    gy = _bf(torch.randn(B, C, Ho, Wo, generator=g))
+    ins_r = [t.clone().requires_grad_(True) for t in (x, off, mask, w)]
+    ref = OD.modulated_deform_conv(*ins_r, None, stride, 1, 1, groups)
+    rg = torch.autograd.grad(ref, ins_r, gy)
+    ins = [t.to(DEV).requires_grad_(True) for t in (x, off, mask, w)]
+    out = ops.modulated_deform_conv(*ins, None, stride, 1, 1, groups, out_fp32=True)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 4e-3, _rel(out, ref)
+    gg = torch.autograd.grad(out, ins, gy.to(DEV))
+    for name, a, r in zip(['x', 'offset', 'mask', 'w'], gg, rg):
+        assert a.shape == r.shape, name
+        assert _rel(a.float(), r) < (4e-2 if name == 'x' else 2e-2), (C, groups, name, _rel(a.float(), r))
+    # same op through the dense kernels on the expanded weight
+    saved = dcn_mod.grouped_native
+    dcn_mod.grouped_native = lambda *a, **k: False
+    try:
+        ins2 = [t.to(DEV).requires_grad_(True) for t in (x, off, mask, w)]
+        out2 = ops.modulated_deform_conv(*ins2, None, stride, 1, 1, groups, out_fp32=True)
+        gg2 = torch.autograd.grad(out2, ins2, gy.to(DEV))
+    finally:
+        dcn_mod.grouped_native = saved
+    assert _rel(out, out2) < 2e-3
+    assert _rel(gg[3], gg2[3]) < 5e-3
