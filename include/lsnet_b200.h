@@ -277,6 +277,14 @@ int lsnet_assign_targets(int num_levels, const int* level_h, const int* level_w,
 int lsnet_pred_boxes(const float* pred, long long ldp, int NP, int polygon, int B, int Hl, int Wl, float stride,
                      int level_off, int total_points, float* boxes, void* stream);
 
+/* ---- inference decode: greedy NMS (mmdet/ops/nms/nms_wrapper.py:7-157, src/cuda/nms_kernel.cu; called from
+ * multiclass_nms_lsvr, mmdet/core/post_processing/bbox_nms.py:60-99).  boxes: fp32 [n,4] (x1,y1,x2,y2), 16-byte aligned,
+ * sorted by DESCENDING score; box j is dropped when an earlier kept box overlaps it with IoU > iou_thr (areas without +1).
+ * keep[n]: indices of the kept boxes in order, *num_keep their count (both device).  No host synchronisation. */
+size_t lsnet_nms_workspace_size(int n);
+int lsnet_nms(const float* boxes, int n, float iou_thr, void* workspace, size_t workspace_bytes, int* keep, int* num_keep,
+              void* stream);
+
 /* ---- host-side parity hooks (CPU, no device): the row arithmetic the loss kernels run ----------------------- */
 float lsnet_host_cross_iou_row(int loss_type, const float* pred, const float* target, const unsigned char* pos_inds,
                                int D, const float* anchor, const float* bbox_gt, const float* vs, float eps,

@@ -49,8 +49,9 @@ struct FusedFwdArgs {
   int tiles_h, tiles_w, TH, TW, tw_shift, num_tiles;   // TW = 1 << tw_shift
   int taps, cblks;
   // grouped (block-diagonal weights on 64-channel blocks): every channel block is its own accumulation group -- 9 K
-  // blocks -> BN = 64 output columns at column offset cb * 64; weights packed [C, taps * 64]
-  int grouped;
+  // blocks -> BN = 64 output columns at column offset cb * 64; weights packed [C, taps * 64].  The blocks are independent,
+  // so a patch's blocks are dealt to cb_parts work items (small maps: a patch alone would run C/64 * 9 K blocks serially)
+  int grouped, cb_parts, cb_per_part;
   void* out;
   long long ldc;
   int out_fp32, relu;
@@ -113,17 +114,26 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_k_iters = p.taps * p.cblks;
-  const int acc_groups = p.grouped ? p.cblks : 1;               // accumulators per patch
   const int k_per_group = p.grouped ? p.taps : num_k_iters;     // K blocks per accumulator
   const int per_img = p.tiles_h * p.tiles_w;
+  const int num_items = p.num_tiles * p.cb_parts;               // work item = (patch, range of channel blocks)
+  // item -> patch index, first / one-past-last channel block
+  auto item_of = [&](int item, int* tile, int* cb0, int* cb1) {
+    *tile = item / p.cb_parts;
+    const int part = item - *tile * p.cb_parts;
+    *cb0 = part * p.cb_per_part;
+    *cb1 = min(p.cblks, *cb0 + p.cb_per_part);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer: weight tiles =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int cb = 0; cb < p.cblks; ++cb) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tile, cb0, cb1;
+        item_of(item, &tile, &cb0, &cb1);
+        for (int cb = cb0; cb < cb1; ++cb) {
           for (int tap = 0; tap < p.taps; ++tap) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sB = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
@@ -143,7 +153,10 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int tile, cb0, cb1;
+        item_of(item, &tile, &cb0, &cb1);
+        const int acc_groups = p.grouped ? cb1 - cb0 : 1;
         for (int grp = 0; grp < acc_groups; ++grp) {
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           tc_fence_after();
@@ -173,7 +186,10 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
     int as = 0;
     uint32_t aphase = 0;
     uint32_t* stg = staging + (warp - F_EPI0) * (32 * 20);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tile, cb0, cb1;
+      item_of(item, &tile, &cb0, &cb1);
+      const int acc_groups = p.grouped ? cb1 - cb0 : 1;
       const int b = tile / per_img, t2 = tile % per_img;
       const int h_base = (t2 / p.tiles_w) * p.TH, w_base = (t2 % p.tiles_w) * p.TW;
       auto row_of = [&](int rr, bool* ok) -> long long {
@@ -184,7 +200,7 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
       bool valid;
       const long long row = row_of(r, &valid);
       for (int grp = 0; grp < acc_groups; ++grp) {
-        const int n_base = grp * BN;          // first output column of this accumulator (grouped: the channel block)
+        const int n_base = p.grouped ? (cb0 + grp) * BN : 0;   // first output column (grouped: the channel block)
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -254,7 +270,10 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
     const uint32_t smem_s = smem_u32(smem), gidx_s = smem_u32(gidx), gwt_s = smem_u32(gwt), gpix_s = smem_u32(gpix);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int tile, cb0, cb1;
+      item_of(item, &tile, &cb0, &cb1);
+      const int item_k_iters = (cb1 - cb0) * p.taps;
       const int b = tile / per_img, t2 = tile % per_img;
       const int h_base = (t2 / p.tiles_w) * p.TH, w_base = (t2 % p.tiles_w) * p.TW;
       // every gather warp is done with the previous patch's records
@@ -302,12 +321,12 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
     ld[u][3] = ldg128_at(xc_, ci_.w, ldxb);                                                 \
   }
 #pragma unroll
-      for (int u = 0; u < F_UPW; ++u) LSN_ISSUE(u, 0, 0)
-      int tap = 0, cb = 0;
-      for (int it = 0; it < num_k_iters; ++it) {
+      for (int u = 0; u < F_UPW; ++u) LSN_ISSUE(u, 0, cb0)
+      int tap = 0, cb = cb0;
+      for (int it = 0; it < item_k_iters; ++it) {
         int ntap = tap + 1, ncb = cb;
         if (ntap == p.taps) { ntap = 0; ++ncb; }
-        const bool has_next = it + 1 < num_k_iters;
+        const bool has_next = it + 1 < item_k_iters;
         mbar_wait(&empty_bar[stage], phase ^ 1);      // the tensor core is done reading this stage
         const uint32_t sA = smem_s + stage * Cfg::kStageBytes;
 #pragma unroll
@@ -717,7 +736,8 @@ static int launch_fused_fwd(const CUtensorMap& tmB, const FusedFwdArgs& a, cudaS
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(dcn_fused_fwd<%d,%d>): %s", BN, STAGES, cudaGetErrorString(e));
     attr_done = true;
   }
-  const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  const long long items = static_cast<long long>(a.num_tiles) * a.cb_parts;
+  const int grid = items < num_sms() ? static_cast<int>(items) : num_sms();
   const double px = static_cast<double>(a.g.B) * a.g.Ho * a.g.Wo;
   const int th = timing_begin(TC_DCN_FWD, 2.0 * px * a.N * a.taps * (a.grouped ? FK : a.g.C), st);
   dcn_fused_fwd_kernel<BN, STAGES, SAVE_COL><<<grid, F_THREADS, Cfg::kSmemBytes, st>>>(tmB, a);
@@ -760,6 +780,14 @@ int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, cons
   a.tiles_h = (g.Ho + TH - 1) / TH;
   a.tiles_w = (g.Wo + TW - 1) / TW;
   a.num_tiles = g.B * a.tiles_h * a.tiles_w;
+  a.cb_parts = 1;
+  a.cb_per_part = a.cblks;
+  if (a.grouped) {      // deal the independent channel blocks of a patch to several work items until the SMs are covered twice
+    while (a.cb_per_part > 1 && static_cast<long long>(a.num_tiles) * a.cb_parts < 2LL * num_sms()) {
+      a.cb_per_part = (a.cb_per_part + 1) / 2;
+      a.cb_parts = (a.cblks + a.cb_per_part - 1) / a.cb_per_part;
+    }
+  }
   a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
   a.col = static_cast<__nv_bfloat16*>(col);
   const int BN = grouped ? 64 : (N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32)));

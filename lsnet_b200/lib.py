@@ -38,7 +38,7 @@ def load():
         _lib.lsnet_last_error.restype = ctypes.c_char_p
         _lib.lsnet_launch_count.restype = ctypes.c_ulonglong
         for n in ('lsnet_dcn_forward_workspace_size', 'lsnet_dcn_backward_data_workspace_size',
-                  'lsnet_dcn_backward_weight_workspace_size'):
+                  'lsnet_dcn_backward_weight_workspace_size', 'lsnet_nms_workspace_size'):
             getattr(_lib, n).restype = ctypes.c_size_t
     return _lib
 

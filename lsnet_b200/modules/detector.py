@@ -1,6 +1,7 @@
 """LSDetector: backbone -> neck -> LSHead.forward_train, with the reference's registry name, constructor arguments,
 ``forward`` / ``train_step`` / ``_parse_losses`` contract (mmdet/models/detectors/lsnet.py:14-56, single_stage.py:16-57,
-base.py:161-243).  Inference (simple_test / aug_test_vote) is SURVEY §8 row f3 ("next")."""
+base.py:161-243) and the single-scale inference path ``simple_test`` (lsnet.py:58-95).  Test-time augmentation /
+instance voting (``aug_test_vote``, lsnet.py:97-409) is out of scope."""
 from collections import OrderedDict
 
 import torch
@@ -74,7 +75,35 @@ class LSDetector(nn.Module):
     def forward(self, img, img_metas, return_loss=True, **kwargs):
         if return_loss:
             return self.forward_train(img, img_metas, **kwargs)
-        raise NotImplementedError('LSDetector test-time paths are not built (SURVEY §8 row f3)')
+        return self.forward_test(img, img_metas, **kwargs)
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """base.py:118-159: one augmentation = simple_test; several = aug_test (not built)."""
+        if torch.is_tensor(imgs):
+            imgs, img_metas = [imgs], [img_metas]
+        if len(imgs) != 1:
+            raise NotImplementedError('test-time augmentation (aug_test_vote, lsnet.py:97-409) is out of scope')
+        return self.simple_test(imgs[0], img_metas[0], **kwargs)
+
+    @torch.no_grad()
+    def simple_test(self, img, img_metas, rescale=False, show=False, out_dir=False):
+        """lsnet.py:58-95: decode + NMS per image, converted to the per-class numpy lists of ``bbox_extreme2result`` /
+        ``bbox_poly2result`` (mmdet/core/bbox/transforms.py:198-218)."""
+        x = self.extract_feat(img)
+        outs = self.bbox_head(x)
+        dets = self.bbox_head.get_bboxes(*outs, img_metas, rescale=rescale)
+        nc, nv = self.bbox_head.num_classes, self.bbox_head.num_vectors
+        width = 8 if self.bbox_head.task == 'bbox' else 2 * nv
+        results = []
+        for boxes, pts, labels in dets:
+            if boxes.shape[0] == 0:
+                import numpy as np
+                results.append([[np.zeros((0, 5), np.float32) for _ in range(nc)],
+                                [np.zeros((0, width), np.float32) for _ in range(nc)]])
+                continue
+            b, p, l = boxes.cpu().numpy(), pts.cpu().numpy(), labels.cpu().numpy()
+            results.append([[b[l == i] for i in range(nc)], [p[l == i] for i in range(nc)]])
+        return results
 
     def _parse_losses(self, losses, sync_log=False):
         return parse_losses(losses, sync_log)

@@ -695,5 +695,108 @@ class LSHead(nn.Module):
                                 npos_init=npos_init, npos_refine=npos_ref, boxes=boxes)
         return losses
 
-    def get_bboxes(self, *args, **kwargs):
-        raise NotImplementedError('inference decode (lsnet_head.py:1439-1668) is SURVEY §8 row f3 ("next")')
+    # ------------------------------------------------------------------------------------------ inference decode
+    @staticmethod
+    def _signed(pts):
+        """max over each (-,+) slot pair, '-' wins ties and is negated -> (B, n, 2, H, W) as (y, x) pairs."""
+        r = pts.view(pts.shape[0], -1, 2, *pts.shape[2:])
+        val, ind = torch.max(r, dim=2)
+        val = torch.where(ind == 0, -val, val)
+        return val.view(val.shape[0], -1, 2, *val.shape[2:])
+
+    def extreme_points2bbox(self, pts, y_first=True, extreme=False):
+        """lsnet_head.py:321-347: 4 extreme points (top, left, bottom, right) -> box (left.x, top.y, right.x, bottom.y)."""
+        v = self._signed(pts)
+        pts_y, pts_x = (v[:, :, 0], v[:, :, 1]) if y_first else (v[:, :, 1], v[:, :, 0])
+        bbox = torch.stack([pts_x[:, 1], pts_y[:, 0], pts_x[:, 3], pts_y[:, 2]], dim=1)
+        if not extreme:
+            return bbox
+        extremes = torch.stack([pts_x[:, 0], pts_y[:, 0], pts_x[:, 1], pts_y[:, 1], pts_x[:, 2], pts_y[:, 2],
+                                pts_x[:, 3], pts_y[:, 3]], dim=1)
+        return extremes, bbox
+
+    def vectors2bbox(self, pts, y_first=True, vector=False):
+        """lsnet_head.py:349-370: the landmark vectors without the centre (last 4 channels) -> their extent box."""
+        v = self._signed(pts[:, :-4])
+        pts_y, pts_x = (v[:, :, 0], v[:, :, 1]) if y_first else (v[:, :, 1], v[:, :, 0])
+        bbox = torch.stack([pts_x.min(1)[0], pts_y.min(1)[0], pts_x.max(1)[0], pts_y.max(1)[0]], 1)
+        if not vector:
+            return bbox
+        vectors = torch.stack([pts_x, pts_y], 2).reshape(pts_y.shape[0], -1, *pts_y.shape[2:])
+        return vectors, bbox
+
+    def get_bboxes(self, cls_scores, bbox_pts_preds_init, bbox_pts_preds_refine, segm_pts_preds_init,
+                   segm_pts_preds_refine, pose_pts_preds_init, pose_pts_preds_refine, img_metas, cfg=None, rescale=False,
+                   nms=True):
+        """lsnet_head.py:1439-1512: refine-stage landmarks -> boxes + landmark vectors per level, then per image
+        ``_get_bboxes_single``.  Returns one (det_bboxes (n,5), det_pts (n, 2*num_vectors), det_labels (n,)) per image."""
+        task = self.task
+        f32 = lambda ts: [t.detach().float() for t in ts]
+        if task in ('bbox', 'pose_bbox'):
+            ext = [self.extreme_points2bbox(p, extreme=True) for p in f32(bbox_pts_preds_refine)]
+        if task == 'segm':
+            vec = [self.vectors2bbox(p, vector=True) for p in f32(segm_pts_preds_refine)]
+        if task in ('pose_bbox', 'pose_kbox'):
+            vec = [self.vectors2bbox(p, vector=True) for p in f32(pose_pts_preds_refine)]
+        box_src = ext if task in ('bbox', 'pose_bbox') else vec
+        pts_src = ext if task == 'bbox' else vec
+        L_ = len(cls_scores)
+        dev = cls_scores[0].device
+        points = []
+        for i in range(L_):                       # PointGenerator.grid_points (point_generator.py:17-25): (x, y, stride)
+            h, w = cls_scores[i].shape[-2:]
+            s = self.point_strides[i]
+            xs = torch.arange(0., w, device=dev) * s
+            ys = torch.arange(0., h, device=dev) * s
+            points.append(torch.stack([xs.repeat(h), ys.view(-1, 1).repeat(1, w).view(-1)], -1))
+        out = []
+        for img_id, meta in enumerate(img_metas):
+            out.append(self._get_bboxes_single([cls_scores[i][img_id].detach().float() for i in range(L_)],
+                                               [box_src[i][1][img_id] for i in range(L_)],
+                                               [pts_src[i][0][img_id] for i in range(L_)], points, meta['img_shape'],
+                                               meta['scale_factor'], cfg, rescale, nms))
+        return out
+
+    def _get_bboxes_single(self, cls_scores, bbox_preds, pts_preds, mlvl_points, img_shape, scale_factor, cfg, rescale=False,
+                           nms=True):
+        """lsnet_head.py:1514-1668: top-``nms_pre`` points per level by their best class score, decode (prediction x
+        stride + point), clamp to the image, multi-class NMS (``multiclass_nms_lsvr``)."""
+        cfg = self.test_cfg if cfg is None else cfg
+        nv = self.num_vectors
+        mb, mp, ms = [], [], []
+        for i, (cs, bp, pp, points) in enumerate(zip(cls_scores, bbox_preds, pts_preds, mlvl_points)):
+            scores = cs.permute(1, 2, 0).reshape(-1, self.cls_out_channels).sigmoid()
+            bp = bp.permute(1, 2, 0).reshape(-1, 4)
+            pp = pp.permute(1, 2, 0).reshape(-1, nv * 2)
+            nms_pre = _cfg_get(cfg, 'nms_pre', -1)
+            if nms_pre > 0 and scores.shape[0] > nms_pre:
+                _, topk = scores.max(dim=1)[0].topk(nms_pre)
+                points, bp, pp, scores = points[topk], bp[topk], pp[topk], scores[topk]
+            s = self.point_strides[i]
+            bboxes = bp * s + torch.cat([points, points], dim=1)
+            pts = pp * s + points.repeat(1, nv)
+            H, W = img_shape[0], img_shape[1]
+            x1, y1 = bboxes[:, 0].clamp(min=0, max=W), bboxes[:, 1].clamp(min=0, max=H)
+            x2, y2 = bboxes[:, 2].clamp(min=0, max=W), bboxes[:, 3].clamp(min=0, max=H)
+            mb.append(torch.stack([x1, y1, x2, y2], dim=-1))
+            if self.task == 'bbox':
+                # the box sides replace the matching coordinate of each extreme point (:1590-1595)
+                xt, yl = pts[:, 0].clamp(min=0, max=W), pts[:, 3].clamp(min=0, max=H)
+                xb, yr = pts[:, 4].clamp(min=0, max=W), pts[:, 7].clamp(min=0, max=H)
+                mp.append(torch.stack([xt, y1, x1, yl, xb, y2, x2, yr], dim=-1))
+            else:
+                px, py = pts[:, 0::2].clamp(min=0, max=W), pts[:, 1::2].clamp(min=0, max=H)
+                mp.append(torch.stack([px, py], 2).reshape(pts.size(0), -1))
+            ms.append(scores)
+        mb, mp, ms = torch.cat(mb), torch.cat(mp), torch.cat(ms)
+        if rescale:
+            sf = np.atleast_1d(np.asarray(scale_factor, dtype=np.float32))
+            sf = np.tile(sf, 4)[:4] if sf.size == 1 else sf
+            mb = mb / mb.new_tensor(sf)
+            reps = 2 if self.task == 'bbox' else nv
+            mp = mp / mp.new_tensor(np.tile(sf, 2) if self.task == 'bbox' else np.tile(sf[:2], reps))
+        ms = torch.cat([ms, ms.new_zeros(ms.shape[0], 1)], dim=1)
+        if not nms:
+            return mb, mp, ms
+        return ops.multiclass_nms_lsvr(mb, mp, ms, nv, _cfg_get(cfg, 'score_thr'), dict(_cfg_get(cfg, 'nms')),
+                                       _cfg_get(cfg, 'max_per_img'))

@@ -210,7 +210,21 @@ class GraphTrainer:
         loss.backward()
         return loss, log_vars
 
+    def _ensure_capacity(self, batch):
+        """More instances than the static GT buffers hold: grow them (next power of two) and drop the captured steps (they
+        are captured again on their next use)."""
+        need = max(int(b.shape[0]) for b in batch['gt_bboxes'])
+        if need > self.capacity:
+            cap = self.capacity
+            while cap < need:
+                cap *= 2
+            self.capacity = cap
+            if self.steps:
+                self.steps.clear()
+                self.recaptures += 1
+
     def _entry(self, batch):
+        self._ensure_capacity(batch)
         key = tuple(batch['img'].shape)
         st = self.steps.get(key)
         if st is None:
@@ -292,15 +306,6 @@ class GraphTrainer:
         """Select (or capture) the step of the batch's canvas and refresh its static inputs (host or device image tensor;
         GT lists on the host).  The packed GT goes through two persistent pinned staging sets per shape (no per-step
         cudaHostAlloc), guarded by an event each."""
-        need = max(int(b.shape[0]) for b in batch['gt_bboxes'])
-        if need > self.capacity:
-            # more instances than the static GT buffers hold: grow them (next power of two) and capture the steps again
-            cap = self.capacity
-            while cap < need:
-                cap *= 2
-            self.capacity = cap
-            self.steps.clear()
-            self.recaptures += 1
         st = self.cur = self._entry(batch)
         head = self.core.bbox_head
         st.img.copy_(batch['img'], non_blocking=True)

@@ -133,8 +133,38 @@ def assign_golden():
     print('assign', len(rec))
 
 
+def decode_golden():
+    """LSHead.get_bboxes of the reference (lsnet_head.py:1439-1668 + multiclass_nms_lsvr) on seeded head outputs; the
+    reference's compiled nms_ext is absent here, its CPU entry point is served by oracle.decode_ref.greedy_nms."""
+    from oracle import decode_ref as DR
+    rh.load()
+    sys.modules['mmdet.ops.nms.nms_ext'].nms = lambda dets, thr: DR.greedy_nms(dets, thr)
+    rec = {}
+    for task, cfgname in CFG.items():
+        model, cfg = rh.build_reference_detector(cfgname)
+        head = model.bbox_head
+        none = [None] * 5
+        for seed in (7, 8):
+            cls, box, lm, metas = DR.synth_head_outputs(task, seed)
+            args = dict(bbox=(cls, none, box, none, none, none, none), segm=(cls, none, none, none, lm, none, none),
+                        pose_bbox=(cls, none, box, none, none, none, lm))[task]
+            for rescale in (False, True):
+                res = head.get_bboxes(*args, metas, rescale=rescale)
+                for i, (b, p, l) in enumerate(res):
+                    key = f'{task}.{seed}.{int(rescale)}.{i}'
+                    rec[key + '.boxes'] = b.detach().numpy().astype(np.float32)
+                    rec[key + '.pts'] = p.detach().numpy().astype(np.float32)
+                    rec[key + '.labels'] = l.detach().numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, 'decode.npz'), **rec)
+    print('decode', len(rec), {k: v.shape for k, v in list(rec.items())[:3]})
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
+    if 'decode' in sys.argv:
+        decode_golden()
+        sys.exit(0)
     loss_golden()
     assign_golden()
     detector_golden()
+    decode_golden()
