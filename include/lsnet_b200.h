@@ -81,6 +81,11 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
                         int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
                         void* stream);
+/* _acc: dgamma / dbeta are ADDED to their targets (the parameters' gradient memory: no memset, no accumulate kernel). */
+int lsnet_groupnorm_bwd_acc(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy, long long lddy,
+                            int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
+                            const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma,
+                            float* dbeta, void* stream);
 
 /* LSHead element-wise glue.  pred_reg: o fp32 [P, ldo] = output of pts_*_init_out (n_out channels); sp[P, ldsp] =
  * softplus(o[:, :n_sp]) (nn.Softplus defaults, lsnet_head.py:96); off[P, ldoff] = the n_off DCN sampling offsets of
@@ -114,6 +119,9 @@ int lsnet_sgd_momentum_step(float* params, const float* grads, float* momentum_b
  * `grad_bias.addmv_(grad_output, ones)` of deform_conv_cuda.cpp:788-794).  relu_out / colsum may be NULL. */
 int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P, int C,
                     int Cpad, void* out, long long ldout, float* colsum, void* stream);
+/* _acc: the column sums are ADDED to colsum (the bias parameter's gradient memory). */
+int lsnet_grad_prep_acc(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P,
+                        int C, int Cpad, void* out, long long ldout, float* colsum, void* stream);
 
 /* Frozen-statistics BatchNorm folded into the preceding conv (ResNet trunk with norm_eval=True,
  * mmdet/models/backbones/resnet.py:636-646): Wb[o] = W[o]*s[o] (bf16, OHWI order), bias[o] = beta[o] - mean[o]*s[o],

@@ -209,12 +209,12 @@ extern "C" int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const floa
   return check_launch("bn_fold_bwd");
 }
 
-extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo,
-                               long long P, int C, int Cpad, void* out, long long ldout, float* colsum, void* stream) {
+static int grad_prep_impl(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P,
+                          int C, int Cpad, void* out, long long ldout, float* colsum, int accumulate, void* stream) {
   if (P <= 0) return 0;
   if (Cpad < C || Cpad > 8192) return set_error("lsnet_grad_prep: bad channel counts C=%d Cpad=%d", C, Cpad);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
+  if (colsum && !accumulate) cudaMemsetAsync(colsum, 0, sizeof(float) * C, st);
   const int vpp = C / 8;
   const bool vec = (C % 8 == 0) && Cpad == C && vpp >= 1 && (vpp & (vpp - 1)) == 0 &&
                    (ldg % (gy_fp32 ? 4 : 8) == 0) && (!out || ldout % 8 == 0) && (!relu_out || ldo % 8 == 0) &&
@@ -245,6 +245,16 @@ extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const
         gy, ldg, static_cast<const __nv_bfloat16*>(relu_out), ldo, P, C, Cpad, static_cast<__nv_bfloat16*>(out), ldout,
         colsum);
   return check_launch("grad_prep");
+}
+
+extern "C" int lsnet_grad_prep(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo,
+                               long long P, int C, int Cpad, void* out, long long ldout, float* colsum, void* stream) {
+  return grad_prep_impl(gy, gy_fp32, ldg, relu_out, ldo, P, C, Cpad, out, ldout, colsum, 0, stream);
+}
+// same, but the column sums are ADDED to colsum (the bias parameter's gradient memory) instead of replacing it
+extern "C" int lsnet_grad_prep_acc(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo,
+                                   long long P, int C, int Cpad, void* out, long long ldout, float* colsum, void* stream) {
+  return grad_prep_impl(gy, gy_fp32, ldg, relu_out, ldo, P, C, Cpad, out, ldout, colsum, 1, stream);
 }
 
 

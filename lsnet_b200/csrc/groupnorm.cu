@@ -295,18 +295,20 @@ extern "C" int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2,
   return check_launch("gn_apply");
 }
 
-extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
-                                   long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
-                                   float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
-                                   float* dgamma, float* dbeta, void* stream) {
+static int groupnorm_bwd_impl(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
+                              long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
+                              float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
+                              float* dgamma, float* dbeta, int accumulate, void* stream) {
   if (B <= 0 || HW <= 0) return 0;
   if (int rc = gn_check("lsnet_groupnorm_bwd", C, G, ldx, lddx)) return rc;
   if (lddy % 8) return set_error("lsnet_groupnorm_bwd: dy pitch must be a multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GnArgs a{B, HW, C, G, ldx, ldx2, 0, eps, relu};
   cudaMemsetAsync(ws_bstats, 0, sizeof(double) * 2 * B * G, st);
-  cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
-  cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
+  if (!accumulate) {
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
+  }
   dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
   const float2* mr = reinterpret_cast<const float2*>(stats + 2 * B * G);
   gn_bwd_stats_kernel<<<grid, GN_THREADS, sizeof(float) * (2 * C + 2 * (C / 8)), st>>>(
@@ -321,4 +323,20 @@ extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2,
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, s12, gamma, beta, static_cast<__nv_bfloat16*>(dx),
       lddx);
   return check_launch("gn_bwd_apply");
+}
+
+extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
+                                   long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
+                                   float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
+                                   float* dgamma, float* dbeta, void* stream) {
+  return groupnorm_bwd_impl(x, ldx, x2, ldx2, dy, lddy, B, HW, C, G, gamma, beta, eps, relu, stats, ws_bstats, dx, lddx,
+                            dgamma, dbeta, 0, stream);
+}
+// same, but dgamma / dbeta are ADDED to (the affine parameters' gradient memory; no memset, no separate add kernel)
+extern "C" int lsnet_groupnorm_bwd_acc(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
+                                       long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
+                                       float eps, int relu, const double* stats, double* ws_bstats, void* dx,
+                                       long long lddx, float* dgamma, float* dbeta, void* stream) {
+  return groupnorm_bwd_impl(x, ldx, x2, ldx2, dy, lddy, B, HW, C, G, gamma, beta, eps, relu, stats, ws_bstats, dx, lddx,
+                            dgamma, dbeta, 1, stream);
 }

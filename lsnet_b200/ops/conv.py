@@ -27,6 +27,7 @@ class _ConvSame(Function):
         assert not (relu and out_fp32)
         ctx.cfg = (pad, dil, relu, bias is not None, ci)
         ctx.grad2d = G.direct_grad(weight)
+        ctx.bias_param = bias
         return out
 
     @staticmethod
@@ -35,7 +36,9 @@ class _ConvSame(Function):
         pad, dil, relu, has_bias, ci = ctx.cfg
         co, _, kh, kw = weight.shape
         # one pass: cast to bf16, pad channels to 8, apply the ReLU mask, column-sum for the bias gradient
-        gyp, colsum = G.grad_prep(gy, out if relu else None, has_bias and ctx.needs_input_grad[2])
+        # the bias gradient is added straight into the parameter's gradient memory when the trainer exposes it
+        gyp, colsum = G.grad_prep(gy, out if relu else None, has_bias and ctx.needs_input_grad[2],
+                                  colsum_into=G.direct_vec(ctx.bias_param))
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             wt = G.cached_pack(weight, 'bwd', lambda t: G.pack_conv_weight(t, flip_transpose=True))

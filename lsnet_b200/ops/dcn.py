@@ -313,6 +313,7 @@ class _DCN(Function):
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
         ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
+        ctx.bias_param = bias
         if out_slice is not None:
             return torch.as_strided(buf, (B, co, Ho, Wo), (Ho * Wo * ld, 1, Wo * ld, ld), buf.storage_offset() + c0)
         return out2d.view(B, Ho, Wo, npad).permute(0, 3, 1, 2)[:, :co]
@@ -332,7 +333,8 @@ class _DCN(Function):
                 d = d.view(groups, co // groups, kh, kw, groups, ci // groups)[idx, :, :, :, idx]
                 d = d.reshape(co, kh, kw, ci // groups)
             return d.permute(0, 3, 1, 2).to(weight.dtype)
-        gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4])
+        gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4],
+                                  colsum_into=G.direct_vec(ctx.bias_param))
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
         gx = goff = gmask = gw = gb = None

@@ -164,12 +164,30 @@ def pad_channels_nhwc(t, mult=8, dtype=torch.bfloat16):
     return buf.permute(0, 3, 1, 2)
 
 
-def grad_prep(gy, relu_out=None, want_colsum=False, mult=8):
+def direct_vec(param):
+    """The fp32 gradient memory of a 1-D parameter (bias, norm affine) that kernels may ADD into directly -- GraphTrainer
+    keeps every gradient as a view of its flat buffer, zeroed once per step -- or None."""
+    if param is None or not getattr(param, '_lsnet_direct_vec', False):
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.dim() != 1:
+        return None
+    return g
+
+
+def grad_prep(gy, relu_out=None, want_colsum=False, mult=8, colsum_into=None):
     """Stage an upstream gradient (B,C,H,W) for the backward GEMMs in ONE pass: bf16 pixel-major with C padded to
     ``mult``, ReLU-masked by ``relu_out`` (the forward output) if given, plus the per-channel sum (bias gradient).
     Returns (gy_bf16 (B,Cpad,H,W) view, colsum or None).  A gradient that is already bf16 / pixel-major / aligned and
-    needs neither mask nor sum is passed through untouched."""
+    needs neither mask nor sum is passed through untouched.  ``colsum_into`` (fp32 [C], e.g. the bias parameter's gradient
+    memory): the sums are ADDED there by the kernel and None is returned in their place."""
     B, C, H, W = gy.shape
+    fn = 'lsnet_grad_prep'
+    if colsum_into is not None and want_colsum:
+        assert colsum_into.numel() == C and colsum_into.dtype == torch.float32
+        fn = 'lsnet_grad_prep_acc'
+    else:
+        colsum_into = None
     Cp = (C + mult - 1) // mult * mult
     pix_major = gy.stride(1) == 1 and gy.stride(2) == W * gy.stride(3) and (B == 1 or gy.stride(0) == H * W * gy.stride(3))
     if relu_out is None and not want_colsum and pix_major and gy.dtype == torch.bfloat16 and Cp == C \
@@ -178,10 +196,10 @@ def grad_prep(gy, relu_out=None, want_colsum=False, mult=8):
     if relu_out is None and pix_major and gy.dtype == torch.bfloat16 and Cp == C and gy.stride(3) % 8 == 0 \
             and (C // 8) & (C // 8 - 1) == 0 and C // 8 <= 256 and gy.data_ptr() % 16 == 0:
         # already in the GEMM layout: only the bias gradient is missing -> read-only column-sum pass
-        colsum = torch.empty(C, device=gy.device, dtype=torch.float32)
-        L.call('lsnet_grad_prep', L.ptr(gy), L.c_int(0), L.c_ll(gy.stride(3)), L.ptr(None), L.c_ll(0), L.c_ll(B * H * W),
+        colsum = colsum_into if colsum_into is not None else torch.empty(C, device=gy.device, dtype=torch.float32)
+        L.call(fn, L.ptr(gy), L.c_int(0), L.c_ll(gy.stride(3)), L.ptr(None), L.c_ll(0), L.c_ll(B * H * W),
                L.c_int(C), L.c_int(Cp), L.ptr(None), L.c_ll(0), L.ptr(colsum), L.stream())
-        return gy, colsum
+        return gy, (None if colsum_into is not None else colsum)
     if not pix_major or gy.dtype not in (torch.float32, torch.bfloat16):
         gy = gy.contiguous(memory_format=torch.channels_last)
         if gy.dtype not in (torch.float32, torch.bfloat16):
@@ -191,7 +209,8 @@ def grad_prep(gy, relu_out=None, want_colsum=False, mult=8):
         assert relu_out.dtype == torch.bfloat16
         ldo = nhwc_geom(relu_out)[4]
     out = torch.empty((B, H, W, Cp), device=gy.device, dtype=torch.bfloat16)
-    colsum = torch.empty(C, device=gy.device, dtype=torch.float32) if want_colsum else None
-    L.call('lsnet_grad_prep', L.ptr(gy), L.c_int(int(gy.dtype == torch.float32)), L.c_ll(gy.stride(3)), L.ptr(relu_out),
+    colsum = (colsum_into if colsum_into is not None else torch.empty(C, device=gy.device, dtype=torch.float32)) \
+        if want_colsum else None
+    L.call(fn, L.ptr(gy), L.c_int(int(gy.dtype == torch.float32)), L.c_ll(gy.stride(3)), L.ptr(relu_out),
            L.c_ll(ldo), L.c_ll(B * H * W), L.c_int(C), L.c_int(Cp), L.ptr(out), L.c_ll(Cp), L.ptr(colsum), L.stream())
-    return out.permute(0, 3, 1, 2), colsum
+    return out.permute(0, 3, 1, 2), (None if colsum_into is not None else colsum)

@@ -25,6 +25,7 @@ class _GroupNorm(Function):
                L.ptr(y), L.c_ll(C), L.stream())
         ctx.save_for_backward(x, x2, w, b, stats)
         ctx.cfg = (num_groups, eps, relu)
+        ctx.affine = (weight, bias)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -37,13 +38,18 @@ class _GroupNorm(Function):
         lddy = G.nhwc_geom(gy)[4]
         bstats = torch.empty((B, num_groups, 3), device=x.device, dtype=torch.float64)
         dx = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
-        dgamma = torch.empty(C, device=x.device, dtype=torch.float32)
-        dbeta = torch.empty(C, device=x.device, dtype=torch.float32)
-        L.call('lsnet_groupnorm_bwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.ptr(gy), L.c_ll(lddy),
+        # affine gradients: added straight into the parameters' gradient memory when the trainer exposes it
+        tg, tb = G.direct_vec(ctx.affine[0]), G.direct_vec(ctx.affine[1])
+        direct = tg is not None and tb is not None and ctx.needs_input_grad[2] and ctx.needs_input_grad[3]
+        dgamma = tg if direct else torch.empty(C, device=x.device, dtype=torch.float32)
+        dbeta = tb if direct else torch.empty(C, device=x.device, dtype=torch.float32)
+        L.call('lsnet_groupnorm_bwd_acc' if direct else 'lsnet_groupnorm_bwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.ptr(gy), L.c_ll(lddy),
                L.c_int(B), L.c_int(H * W), L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps),
                L.c_int(int(relu)), L.ptr(stats), L.ptr(bstats), L.ptr(dx), L.c_ll(C), L.ptr(dgamma), L.ptr(dbeta),
                L.stream())
         dxv = dx.permute(0, 3, 1, 2)
+        if direct:
+            dgamma = dbeta = None
         return dxv, (dxv if x2 is not None else None), dgamma, dbeta, None, None, None
 
 

@@ -107,6 +107,7 @@ class Trainer:
 
 
 DIRECT_WGRAD = os.environ.get('LSNET_DIRECT_WGRAD', '1') == '1'
+DIRECT_VEC = os.environ.get('LSNET_DIRECT_VEC', '1') == '1'
 
 
 class GraphTrainer:
@@ -165,6 +166,8 @@ class GraphTrainer:
                 self.flat_p[o:o + k].copy_(p.data.reshape(-1))
                 p.data = self.flat_p[o:o + k].view_as(p)
                 p.grad = self.flat_g[o:o + k].view_as(p)
+                # biases / norm affines: the backward kernels add into this memory directly (ops.gemm_ops.direct_vec)
+                p._lsnet_direct_vec = DIRECT_VEC and p.dim() == 1
             o += (k + al - 1) // al * al
         # ---- captured steps, one per input canvas (H, W): multi-scale training (configs/lsnet/*mstrain*) replays the
         # graph of the batch's shape bucket; all graphs share ONE memory pool (they never run concurrently), so the
@@ -266,7 +269,13 @@ class GraphTrainer:
         st.graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
         with torch.cuda.graph(st.graph, pool=self._pool, capture_error_mode='thread_local'):
-            st.loss, st.log_vars = self._fwd_bwd(st)
+            loss, log_vars = self._fwd_bwd(st)
+        # Keep only DETACHED views of the static outputs: a live grad_fn would keep this capture's autograd graph -- and its
+        # AccumulateGrad nodes, bound to the streams of this capture -- alive; a later capture with another stream layout
+        # (the serialised timing graph, another shape) would then find leaf streams that are not part of it.
+        st.loss = loss.detach()
+        st.log_vars = type(log_vars)((k, v.detach()) for k, v in log_vars.items())
+        del loss, log_vars
         st.launches = L.launch_count() - n0
         gemm_ops._PACK_CACHE.clear()
         st.graph_timed = None
@@ -325,9 +334,49 @@ class GraphTrainer:
         st.gt.copy_from(sg)                   # pinned host -> static device buffers, async
         st.stage_ev[i].record()
 
-    def step(self, batch=None, sync_log=False):
+    def prefetch(self, batch):
+        """Start moving the NEXT batch to the device on a copy stream while the current step computes: the image goes
+        host -> a device staging buffer of its shape, the packed ground truth host -> pinned -> device staging.  The
+        following ``step(batch)`` (same object) then only waits for the copy and moves staging -> static inputs on the
+        device (a 50 MB device-to-device copy, ~20 us) before replaying the graph."""
+        st = self._entry(batch)
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if getattr(st, 'pre_img', None) is None:
+            st.pre_img = torch.empty_like(st.img)
+            st.pre_gt = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes,
+                                                    self.device, capacity=self.capacity, **self._gt_kwargs(batch))
+            st.pre_pin = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes,
+                                                     'cpu', capacity=self.capacity, pin=True, **self._gt_kwargs(batch))
+            st.pre_ev = torch.cuda.Event()
+            st.pre_done = torch.cuda.Event()
+        else:
+            st.pre_done.synchronize()            # the step that consumed the previous prefetch of this shape has read it
+        fresh = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes, 'cpu',
+                                            capacity=self.capacity, pin=False, **self._gt_kwargs(batch))
+        st.pre_pin.copy_from(fresh)
+        cs = self._copy_stream                # (pre_done above already guarantees nobody still reads the staging buffers)
+        with torch.cuda.stream(cs):
+            st.pre_img.copy_(batch['img'], non_blocking=True)
+            st.pre_gt.copy_from(st.pre_pin)
+            st.pre_ev.record(cs)
+        st.pre_batch = batch
+
+    def step(self, batch=None, sync_log=False, next_batch=None):
+        """One training iteration.  ``next_batch``: prefetch it (host -> device on a copy stream) while this step runs."""
         if batch is not None:
-            self.load_batch(batch)
+            st = self.steps.get(tuple(batch['img'].shape))
+            if st is not None and getattr(st, 'pre_batch', None) is batch:
+                # prefetched: wait for the copy stream, staging -> static inputs on the device
+                self.cur = st
+                st.last_use = self.iter
+                torch.cuda.current_stream(self.device).wait_event(st.pre_ev)
+                st.img.copy_(st.pre_img, non_blocking=True)
+                st.gt.copy_from(st.pre_gt)
+                st.pre_done.record()
+                st.pre_batch = None
+            else:
+                self.load_batch(batch)
         self.graph.replay()
         g = self.flat_g
         if self.distributed:
@@ -346,9 +395,12 @@ class GraphTrainer:
         if gemm_ops._PACK_CACHE:
             gemm_ops._PACK_CACHE.clear()
         log = self.log_vars
+        loss = self.loss
+        if next_batch is not None:
+            self.prefetch(next_batch)
         if sync_log:
             flat = torch.stack([v.detach().float() for v in log.values()])
             if self.distributed:
                 dist.all_reduce(flat.div_(dist.get_world_size()))
             log = dict(zip(log.keys(), flat.tolist()))
-        return self.loss, log
+        return loss, log

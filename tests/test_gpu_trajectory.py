@@ -183,3 +183,37 @@ def test_graph_cache_multiscale():
         assert abs(le - lg) < 6e-2 * abs(le), (le, lg)
     assert len(graph.steps) == len(set(shapes))
     assert graph.capacity >= max(int(x.shape[0]) for b in batches for x in b['gt_bboxes']) > 4
+
+
+def test_prefetch_feeds_the_right_batch():
+    """GraphTrainer.step(batch, next_batch=...) moves the next batch host -> device staging on a copy stream while the
+    step computes; the following step must run on exactly that batch's image and packed ground truth (the static inputs
+    of the captured graph are compared bit for bit), and the first three losses must agree with the plain path (later
+    steps from random initialisation flip ATSS assignments between two runs of the SAME code, see
+    test_graph_trainer_matches_eager_trainer)."""
+    from lsnet_b200.data import MODEL_CFG, synthetic_batch
+    from lsnet_b200.train import GraphTrainer
+    batches = [synthetic_batch(s, batch=1, img_hw=(256, 320), pin=True) for s in range(5)]
+    torch.manual_seed(0)
+    tr = GraphTrainer(MODEL_CFG['bbox_r50'], batches[0])
+    sd = {k: v.clone() for k, v in tr.core.state_dict().items()}
+    plain = [float(tr.step(b)[0]) for b in batches[:3]]
+    torch.manual_seed(0)
+    tr = GraphTrainer(MODEL_CFG['bbox_r50'], batches[0])
+    tr.core.load_state_dict(sd)
+    head = tr.core.bbox_head
+    pre = []
+    for i, b in enumerate(batches):
+        nb = batches[i + 1] if i + 1 < len(batches) else None
+        loss, _ = tr.step(b, next_batch=nb)
+        pre.append(float(loss))
+        torch.cuda.synchronize()
+        st = tr.cur
+        assert torch.equal(st.img.cpu(), b['img']), i
+        want = head.pack_gt(b['gt_bboxes'], b['gt_labels'], b['img_metas'], st.sizes, 'cpu', capacity=tr.capacity,
+                            gt_extremes=b['gt_extremes'])
+        assert torch.equal(st.gt.bbox.cpu(), want.bbox) and torch.equal(st.gt.count.cpu(), want.count), i
+        assert torch.equal(st.gt.tables['bbox'].cpu(), want.tables['bbox']) and torch.equal(st.gt.labels.cpu(), want.labels), i
+        assert np.isfinite(pre[-1])
+    for a, c in zip(plain, pre):
+        assert abs(a - c) < 2e-2 * abs(a), (plain, pre)

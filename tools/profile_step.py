@@ -8,12 +8,14 @@ from lsnet_b200.data import MODEL_CFG, synthetic_batch, to_device
 from lsnet_b200.train import GraphTrainer, Trainer
 
 eager = '--eager' in sys.argv
-host = [synthetic_batch(s, 0, 4, (800, 1333), pin=True) for s in range(2)]
+cfg_name = sys.argv[sys.argv.index('--config') + 1] if '--config' in sys.argv else 'bbox_r50'
+from lsnet_b200.data import TASK_OF
+host = [synthetic_batch(s, 0, 4, (800, 1333), pin=True, task=TASK_OF[cfg_name]) for s in range(2)]
 if eager:
-    tr = Trainer(MODEL_CFG['bbox_r50'], device='cuda:0')
+    tr = Trainer(MODEL_CFG[cfg_name], device='cuda:0')
     batches = [to_device(b, 'cuda:0') for b in host]
 else:
-    tr = GraphTrainer(MODEL_CFG['bbox_r50'], host[0], device='cuda:0')
+    tr = GraphTrainer(MODEL_CFG[cfg_name], host[0], device='cuda:0')
     batches = host
 for w in range(3):
     tr.step(batches[w % 2])
