@@ -44,6 +44,12 @@ void lsnet_timing_reset(void);
  * Needs N % 16 == 0, K % 8 == 0, 16-byte aligned row pitches. */
 int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M,
                     int N, int K, const float* bias, int relu, int out_fp32, void* stream);
+/* lsnet_gemm_bf16 with the full epilogue: v = acc + bias + resid[row,:] (bf16, pitch ldr); ReLU; v = 0 where mask[row,:]
+ * (bf16, pitch ldm) <= 0.  The trunk's 1x1 convolutions: conv3 + folded BN + identity add + ReLU of a Bottleneck
+ * (mmdet/models/backbones/resnet.py:286-299) is ONE call with resid = the block input. */
+int lsnet_gemm_ex_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M,
+                       int N, int K, const float* bias, const void* resid, long long ldr, const void* mask,
+                       long long ldm, int relu, int out_fp32, void* stream);
 /* Block-diagonal product for grouped weights: out[M, N] (bf16), N = ntiles*64; column tile nt =
  * A[:, (nt % cblks)*64 .. +63] . Bw[nt*64 .. +63, 0..63]^T with A bf16 [M, cblks*64], Bw bf16 [N, 64].  The dCol GEMM of a
  * grouped DCN (per-group `addmm_` loop of deform_conv_cuda.cpp:746-749) without the groups-times redundant dense FLOPs. */
@@ -59,12 +65,35 @@ int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long 
                            int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out, long long ldc,
                            const float* bias, int relu, int out_fp32, void* stream);
 
+/* General strided / phase-decomposed convolution as ONE implicit GEMM (every conv entry point above is a special case):
+ *   out[b, ho*osh+ooh, wo*osw+oow, n] = sum_t sum_c x[b, ho*ish+tap_dy[t], wo*isw+tap_dx[t], c] * Wt[n, t*Cpad64 + c]
+ *                                       (+ bias[n]) (+ resid[same pixel, n]) (ReLU) (0 where mask[same pixel, n] <= 0)
+ * for ho < Ho, wo < Wo; x NHWC bf16 [B,H,W,C] read through a TMA map with element strides (ish, isw) (out-of-range taps
+ * are zero fill), out an OH x OW pixel grid with row pitch ldc.  tap_dy / tap_dx: host int arrays, <= 16 taps; Wt holds
+ * wt_taps blocks of Cpad64 columns and tap t multiplies block tap_kblk[t] (NULL: block t).
+ *  - forward of a stride-s convolution: ish = isw = s, taps (ky*dil - pad, kx*dil - pad), osh = 1 (the trunk's
+ *    Bottleneck convs incl. the stride-2 conv2 / downsample, mmdet/models/backbones/resnet.py:165-223, 261-301, and FPN's
+ *    stride-2 extra levels, necks/fpn.py:203-211), bias + identity add + ReLU in the epilogue (resnet.py:286-299);
+ *  - its input gradient: one call per output phase (osh = s, ooh = phase) over the taps that reach that phase,
+ *    Wt = the transposed pack, mask = the ReLU output of the layer below (replaces cuDNN dgrad + a mask pass). */
+int lsnet_conv2d_taps_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt, int N, int ntaps,
+                           const int* tap_dy, const int* tap_dx, const int* tap_kblk, int wt_taps, int ish, int isw,
+                           int Ho, int Wo, void* out,
+                           long long ldc, int osh, int osw, int ooh, int oow, int OH, int OW, const float* bias,
+                           const void* resid, long long ldr, const void* mask, long long ldm, int relu, int out_fp32,
+                           void* stream);
+
 /* out[M,N] (fp32) += A[P,M]^T . Bm[P,N]  (reduction over the P rows = pixels; split-K, fp32 red.global.add; the
  * caller zero-fills `out`).  Weight-gradient GEMM: replaces `grad_weight[g].addmm_(grad_output, columns^T)`
  * (deform_conv_cuda.cpp:782-787, 1113-1124).  Needs M % 8 == 0, N % 8 == 0. */
 int lsnet_gemm_tn_bf16(const void* A, long long lda, const void* Bm, long long ldb, float* out, long long ldc, int P,
                        int M, int N, void* stream);
 
+/* dw[N, kh*kw, C] (fp32) += sum over the Ho x Wo output pixels p of dy[p, n] * x[p*stride - pad + tap*dil, c]: weight
+ * gradient of a strided convolution (x through a TMA map with element strides). */
+int lsnet_conv2d_wgrad_strided_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B, int H, int W,
+                                         int C, int Ho, int Wo, int N, int kh, int kw, int stride_h, int stride_w,
+                                         int pad_h, int pad_w, int dil_h, int dil_w, float* dw, void* stream);
 /* dw[N, kh*kw, C] (fp32) += sum_pixels dy[p, n] * x[p + tap, c]: weight gradient of lsnet_conv2d_nhwc_bf16. */
 int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B, int H, int W,
                                  int C, int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, float* dw,
@@ -132,6 +161,26 @@ int lsnet_bn_fold_fwd(const float* W, const float* gamma, const float* beta, con
 int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const float* W, const float* gamma, const float* mean,
                       const float* var, float eps, int O, int I, int KK, float* gW, float* ggamma, float* gbeta,
                       void* stream);
+/* The same fold for the library's own trunk convolutions: W element (o,i,k) at o*I*KK + i*si + k*sk (OIHW: si=KK, sk=1;
+ * tap-major: si=1, sk=I).  fwd writes both GEMM operand packs -- Wb bf16 [O, KK*I] (forward / weight-gradient order) and
+ * Wt bf16 [I, KK*O] (B operand of the input-gradient GEMM).  bwd takes gWb fp32 [O, KK*I] as lsnet_conv2d_wgrad_* leaves
+ * it; accumulate != 0 adds gW / ggamma / gbeta into the parameters' gradient memory. */
+int lsnet_bn_fold2_fwd(const float* W, long long si, long long sk, const float* gamma, const float* beta,
+                       const float* mean, const float* var, float eps, int O, int I, int KK, void* Wb, void* Wt,
+                       float* bias, void* stream);
+int lsnet_bn_fold2_bwd(const float* gWb, const float* gbias, const float* W, long long si, long long sk,
+                       const float* gamma, const float* mean, const float* var, float eps, int O, int I, int KK,
+                       float* gW, float* ggamma, float* gbeta, int accumulate, void* stream);
+
+/* ResNet stem (mmdet/models/backbones/resnet.py:509-520, 619-623: conv1 7x7/2 -> norm1 (frozen) -> relu -> maxpool 3x3/2).
+ * x: [B,3,H,W] image, fp32 (x_bf16 = 0) or bf16, ANY element strides (sb, sc, sh, sw) -- NCHW or NHWC; Wp bf16 [64, 192]:
+ * column ky*24 + kx*3 + ch holds the BN-folded weight of tap (ky,kx), channel ch, zeros elsewhere; bias fp32 [64] = the BN
+ * shift; out bf16 NHWC [B, (H-1)/2+1, (W-1)/2+1, 64] = relu(conv + bias).  Implicit GEMM on tcgen05 whose A tile is built in
+ * shared memory from the input window. */
+int lsnet_stem_conv7x7s2_bf16(const void* x, int x_bf16, long long sb, long long sc, long long sh, long long sw, int B,
+                              int H, int W, const void* Wp, const float* bias, void* out, void* stream);
+/* y[B, (H-1)/2+1, (W-1)/2+1, C] = 3x3 / stride 2 / pad 1 max-pool of x NHWC bf16 (C % 8 == 0). */
+int lsnet_maxpool3x3s2_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream);
 
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)

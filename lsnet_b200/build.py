@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblsnet_sm100.so')
-SOURCES = ['api.cu', 'gemm_tcgen05.cu', 'dcn_gather.cu', 'dcn_fused.cu', 'dcn_adjoint.cu', 'dcn_api.cu', 'loss.cu', 'assign.cu', 'groupnorm.cu', 'elementwise.cu', 'nms.cu']
+SOURCES = ['api.cu', 'gemm_tcgen05.cu', 'dcn_gather.cu', 'dcn_fused.cu', 'dcn_adjoint.cu', 'dcn_api.cu', 'loss.cu', 'assign.cu', 'groupnorm.cu', 'elementwise.cu', 'nms.cu', 'stem.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

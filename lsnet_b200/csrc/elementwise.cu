@@ -187,6 +187,79 @@ __global__ void bn_fold_bwd_kernel(const __nv_bfloat16* __restrict__ gWb, const 
   }
 }
 
+
+// ---- GEMM-operand variant of the fold (own tcgen05 trunk convolutions) -------------------------------------------
+// W fp32 with element (o, i, k) at o*I*KK + i*si + k*sk (OIHW: si = KK, sk = 1; tap-major OHWI: si = 1, sk = I).
+// forward : Wb[o][k][i] = W*s[o]  (bf16, A-side pack [O, KK*I]),  Wt[i][k][o] = the same value (bf16, pack of the input-
+//           gradient GEMM [I, KK*O]),  bias[o] = beta[o] - mean[o]*s[o].  32 x 32 (o, i) tiles through shared memory so
+//           that both packs are written with unit stride.
+// backward: gW(o,i,k) (+)= gWb[o][k][i]*s[o]  (gWb fp32 [O, KK*I] straight from the weight-gradient GEMM),
+//           ggamma[o] (+)= (sum gWb*W - gbias*mean)*r,  gbeta[o] (+)= gbias[o].
+__global__ void bn_fold2_fwd_kernel(const float* __restrict__ W, long long si, long long sk,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var, float eps, int O, int I,
+                                    int KK, __nv_bfloat16* __restrict__ Wb, __nv_bfloat16* __restrict__ Wt,
+                                    float* __restrict__ bias) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32, k = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // (32, 8)
+  const bool i_fast = si == 1;
+  for (int r = ty; r < 32; r += 8) {
+    // read with the unit-stride index on tx
+    const int o = i_fast ? o0 + r : o0 + tx, i = i_fast ? i0 + tx : i0 + r;
+    float v = 0.f;
+    if (o < O && i < I) v = W[static_cast<long long>(o) * I * KK + i * si + k * sk] * (gamma[o] * rsqrtf(var[o] + eps));
+    if (i_fast) tile[r][tx] = v; else tile[tx][r] = v;      // tile[o - o0][i - i0]
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, i = i0 + tx;
+    if (o < O && i < I) Wb[(static_cast<long long>(o) * KK + k) * I + i] = __float2bfloat16(tile[r][tx]);
+    const int i2 = i0 + r, o2 = o0 + tx;
+    if (o2 < O && i2 < I) Wt[(static_cast<long long>(i2) * KK + k) * O + o2] = __float2bfloat16(tile[tx][r]);
+  }
+  if (blockIdx.x == 0 && k == 0 && ty == 0 && o0 + tx < O) {
+    const int o = o0 + tx;
+    bias[o] = beta[o] - mean[o] * gamma[o] * rsqrtf(var[o] + eps);
+  }
+}
+
+__global__ void bn_fold2_bwd_kernel(const float* __restrict__ gWb, const float* __restrict__ gbias,
+                                    const float* __restrict__ W, long long si, long long sk,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, int I, int KK, float* __restrict__ gW,
+                                    float* __restrict__ ggamma, float* __restrict__ gbeta, int accumulate) {
+  __shared__ float red[32];
+  const int o = blockIdx.x;
+  const float r = rsqrtf(var[o] + eps);
+  const float s = gamma[o] * r;
+  const int n = I * KK;
+  const float* w = W + static_cast<long long>(o) * n;
+  const float* g = gWb + static_cast<long long>(o) * n;
+  float* d = gW + static_cast<long long>(o) * n;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {      // j = k*I + i
+    const int k = j / I, i = j - k * I;
+    const long long e = i * si + k * sk;
+    const float gv = g[j];
+    acc += gv * w[e];
+    d[e] = accumulate ? d[e] + gv * s : gv * s;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) {
+      const float gb = gbias ? gbias[o] : 0.f;
+      const float gg = (v - gb * mean[o]) * r;
+      ggamma[o] = accumulate ? ggamma[o] + gg : gg;
+      gbeta[o] = accumulate ? gbeta[o] + gb : gb;
+    }
+  }
+}
+
 }  // namespace lsn
 
 using namespace lsn;
@@ -207,6 +280,27 @@ extern "C" int lsnet_bn_fold_bwd(const void* gWb, const float* gbias, const floa
   bn_fold_bwd_kernel<<<O, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(gWb), gbias, W,
                                                                       gamma, mean, var, eps, I, KK, gW, ggamma, gbeta);
   return check_launch("bn_fold_bwd");
+}
+
+extern "C" int lsnet_bn_fold2_fwd(const float* W, long long si, long long sk, const float* gamma, const float* beta,
+                                  const float* mean, const float* var, float eps, int O, int I, int KK, void* Wb,
+                                  void* Wt, float* bias, void* stream) {
+  if (O <= 0) return 0;
+  if (!((si == 1 && sk == I) || (si == KK && sk == 1)))
+    return set_error("lsnet_bn_fold2_fwd: weight must be OIHW-contiguous or tap-major (si=%lld sk=%lld)", si, sk);
+  dim3 grid((I + 31) / 32, (O + 31) / 32, KK);
+  bn_fold2_fwd_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      W, si, sk, gamma, beta, mean, var, eps, O, I, KK, static_cast<__nv_bfloat16*>(Wb), static_cast<__nv_bfloat16*>(Wt), bias);
+  return check_launch("bn_fold2_fwd");
+}
+
+extern "C" int lsnet_bn_fold2_bwd(const float* gWb, const float* gbias, const float* W, long long si, long long sk,
+                                  const float* gamma, const float* mean, const float* var, float eps, int O, int I,
+                                  int KK, float* gW, float* ggamma, float* gbeta, int accumulate, void* stream) {
+  if (O <= 0) return 0;
+  bn_fold2_bwd_kernel<<<O, 256, 0, static_cast<cudaStream_t>(stream)>>>(gWb, gbias, W, si, sk, gamma, mean, var, eps, I,
+                                                                       KK, gW, ggamma, gbeta, accumulate);
+  return check_launch("bn_fold2_bwd");
 }
 
 static int grad_prep_impl(const void* gy, int gy_fp32, long long ldg, const void* relu_out, long long ldo, long long P,

@@ -23,16 +23,28 @@ constexpr int BM = 128;       // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int BK = 64;        // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kThreads = 320;   // warp0 TMA, warp1 MMA, warps2-9 epilogue (two warps per TMEM lane quarter)
 
+constexpr int kMaxTaps = 16;
+
 struct GemmArgs {
   int M, N;            // logical output extent (N multiple of 16)
   int num_k_iters;     // K/64, or taps * C/64 in conv mode
   int m_tiles, n_tiles;
-  // conv mode (A through a 4-D NHWC map); ignored when conv == 0
-  int conv, H, W, tiles_h, tiles_w, TH, TW, kw, cblks, pad_h, pad_w, dil_h, dil_w;
+  // conv mode (A through a 4-D NHWC map); ignored when conv == 0.  The GEMM rows are the pixels of a logical Ho x Wo grid
+  // (tiled TH x TW); filter tap t reads input pixel (h*ish + tap_dy[t], w*isw + tap_dx[t]) -- the map's element strides
+  // are (ish, isw), out-of-range coordinates are TMA zero fill -- and the row is written to pixel
+  // (h*osh + ooh, w*osw + oow) of an OH x OW output grid (osh = 1, ooh = 0: plain; osh = 2: one phase of the input
+  // gradient of a stride-2 convolution).
+  int conv, Ho, Wo, tiles_h, tiles_w, TH, TW, tw_shift, cblks, ish, isw, osh, osw, ooh, oow, OH, OW;   // TW = 1 << tw_shift
+  signed char tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_kb[kMaxTaps];   // tap_kb: K block (of cblks*64 columns) of the weight pack
   void* out;           // [M, ldc] bf16 or fp32
   long long ldc;
   int out_fp32, relu;
   const float* bias;   // [N] or null
+  // epilogue extras (same row mapping as out):  v = acc + bias + resid;  relu;  v = mask > 0 ? v : 0
+  const __nv_bfloat16* resid;
+  long long ldr;
+  const __nv_bfloat16* mask;
+  long long ldm;
   // block-diagonal mode (grouped DCN dCol): ONE K block per tile; the N tile nt (64 columns) multiplies the 64-column
   // block (nt % blockdiag) of A with B[n0 .. n0+63, 0..63]; 0 = off
   int blockdiag;
@@ -112,15 +124,15 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           uint8_t* sB = sA + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          int kb = it;
           if (p.conv) {
             const int tap = it / p.cblks, cb = it % p.cblks;
-            const int dy = tap / p.kw, dx = tap % p.kw;
-            tma_load_4d(sA, &tmA, &full_bar[stage], cb * BK, w0 - p.pad_w + dx * p.dil_w,
-                        h0 - p.pad_h + dy * p.dil_h, b);
+            kb = p.tap_kb[tap] * p.cblks + cb;
+            tma_load_4d(sA, &tmA, &full_bar[stage], cb * BK, w0 * p.isw + p.tap_dx[tap], h0 * p.ish + p.tap_dy[tap], b);
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], p.blockdiag ? (nt % p.blockdiag) * BK : it * BK, m0);
           }
-          tma_load_2d(sB, &tmB, &full_bar[stage], it * BK, n0);
+          tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -166,15 +178,24 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int n0 = nt * BN;
-      // output row (and validity) of accumulator row rr of this tile
+      // Output row (and validity) of accumulator row rr of this tile.  The tile's origin is decoded ONCE per tile (the
+      // per-row part is shifts / masks: TW is a power of two); the rows this thread stores in the transposed write-out
+      // are precomputed too -- with the divisions inside the column loop the epilogue of a conv tile was ALU bound.
+      int tb = 0, th0 = 0, tw0 = 0;
+      if (p.conv) {
+        const int per_img = p.tiles_h * p.tiles_w;
+        tb = mt / per_img;
+        const int t2 = mt - tb * per_img;
+        const int ty = t2 / p.tiles_w;
+        th0 = ty * p.TH;
+        tw0 = (t2 - ty * p.tiles_w) * p.TW;
+      }
       auto row_of = [&](int rr, bool* ok) -> long long {
         if (p.conv) {
-          const int per_img = p.tiles_h * p.tiles_w;
-          const int b = mt / per_img, t2 = mt % per_img;
-          const int h = (t2 / p.tiles_w) * p.TH + rr / p.TW;
-          const int w = (t2 % p.tiles_w) * p.TW + rr % p.TW;
-          *ok = (h < p.H) && (w < p.W);
-          return (static_cast<long long>(b) * p.H + h) * p.W + w;
+          const int h = th0 + (rr >> p.tw_shift), w = tw0 + (rr & (p.TW - 1));
+          const int oh = h * p.osh + p.ooh, ow = w * p.osw + p.oow;
+          *ok = (h < p.Ho) && (w < p.Wo) && (oh < p.OH) && (ow < p.OW);
+          return (static_cast<long long>(tb) * p.OH + oh) * p.OW + ow;
         }
         const long long g = static_cast<long long>(mt) * BM + rr;
         *ok = g < p.M;
@@ -182,6 +203,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       };
       bool valid;
       const long long row = row_of(r, &valid);
+      long long srow[4];
+      bool sok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) srow[i] = row_of(q * 32 + (lane >> 2) + 8 * i, &sok[i]);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -196,14 +221,45 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+        if (p.bias) {      // N % 16 == 0 and the bias vector is 16-byte aligned (host-checked): whole float4 groups
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4)
+            if (col0 + j < p.N) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
+        }
+        if (p.resid && valid) {
+          const __nv_bfloat16* rp = p.resid + row * p.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < p.N) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[8 * j + 2 * i] += __uint_as_float(rw[i] << 16);
+                f[8 * j + 2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+              }
+            }
         }
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.mask && valid) {
+          const __nv_bfloat16* mp = p.mask + row * p.ldm + col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col0 + 8 * j < p.N) {
+              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mp) + j);
+              const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {      // bf16 > 0  <=>  sign clear and not (+)zero
+                if (!((mw[i] & 0xffffu) - 1u < 0x7fffu)) f[8 * j + 2 * i] = 0.f;
+                if (!((mw[i] >> 16) - 1u < 0x7fffu)) f[8 * j + 2 * i + 1] = 0.f;
+              }
+            }
         }
         if (p.out_fp32) {
           if (valid) {
@@ -226,11 +282,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i;
-            bool ok;
-            const long long grow = row_of(q * 32 + rr, &ok);
-            if (ok && col0 + seg * 8 < p.N) {
+            if (sok[i] && col0 + seg * 8 < p.N) {
               const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + col0 + seg * 8) = val;
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + srow[i] * p.ldc + col0 + seg * 8) = val;
             }
           }
           __syncwarp();
@@ -262,7 +316,7 @@ struct WgradArgs {
   int taps;              // 1 (plain) or kh*kw (conv)
   int splits;            // split-K factor over pixel chunks
   int k_chunks;          // total 64-pixel chunks (plain: ceil(P/64); conv: B * tiles_h * tiles_w)
-  int conv, tiles_h, tiles_w, TH, TW, kw, pad_h, pad_w, dil_h, dil_w;
+  int conv, tiles_h, tiles_w, TH, TW, kw, pad_h, pad_w, dil_h, dil_w, ish, isw;   // (ish, isw): stride of the convolution
   float* out;            // [M, taps, N] fp32 (row stride ldc = taps*N)
   long long ldc;
 };
@@ -352,7 +406,7 @@ gemm_mnmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < BNW / 64; ++j)
               tma_load_4d(sB + j * (BK * 128), &tmB, &full_bar[stage], nt * BNW + j * 64,
-                          w0 - p.pad_w + dx * p.dil_w, h0 - p.pad_h + dy * p.dil_h, b);
+                          w0 * p.isw - p.pad_w + dx * p.dil_w, h0 * p.ish - p.pad_h + dy * p.dil_h, b);
           } else {
 #pragma unroll
             for (int j = 0; j < MT * BM / 64; ++j)
@@ -468,6 +522,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode() {
+  // cuTensorMapEncodeTiled needs a current context: autograd worker threads may reach here before any runtime call bound
+  // the primary context to them (CUDA_ERROR_INVALID_CONTEXT otherwise)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -495,15 +553,17 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
                                           (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
   return 0;
 }
-// rank-4 bf16 map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1]
+// rank-4 bf16 map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1] pixels taken every (sh, sw)-th
+// row / column (TMA element strides: the box spans TW*sw x TH*sh input pixels and lands compacted in shared memory)
 int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
-                         uint32_t TW, uint32_t TH) {
+                  uint32_t TW, uint32_t TH, uint32_t sw, uint32_t sh) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  if (TW * sw > 256 || TH * sh > 256) return set_error("make_map_nhwc: box %ux%u with strides %ux%u exceeds 256", TW, TH, sw, sh);
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {ldp * 2, W * ldp * 2, H * W * ldp * 2};
-  cuuint32_t box[4] = {64, TW, TH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, TW * sw, TH * sh, 1};
+  cuuint32_t estr[4] = {1, sw, sh, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -597,6 +657,7 @@ using namespace lsn;
 extern "C" int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc,
                                int M, int N, int K, const float* bias, int relu, int out_fp32, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(bias) % 16) return set_error("lsnet_gemm_bf16: bias must be 16-byte aligned");
   if ((N % 16) || (K % 8) || (lda % 8) || (ldb % 8) || (ldc % (out_fp32 ? 4 : 8)))
     return set_error("lsnet_gemm_bf16: need N%%16==0, K%%8==0 and 16-byte aligned pitches (N=%d K=%d lda=%lld ldb=%lld ldc=%lld)",
                      N, K, lda, ldb, ldc);
@@ -605,6 +666,24 @@ extern "C" int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, lon
   GemmArgs a{};
   a.M = M; a.N = N; a.num_k_iters = (K + BK - 1) / BK; a.m_tiles = (M + BM - 1) / BM;
   a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  return dispatch_kmajor(tmA, Bw, N, K, ldb, a, static_cast<cudaStream_t>(stream));
+}
+
+// lsnet_gemm_bf16 with the full epilogue: v = acc + bias + resid[row, :];  ReLU;  v = mask[row, :] > 0 ? v : 0
+extern "C" int lsnet_gemm_ex_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc,
+                                  int M, int N, int K, const float* bias, const void* resid, long long ldr,
+                                  const void* mask, long long ldm, int relu, int out_fp32, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(bias) % 16) return set_error("lsnet_gemm_ex_bf16: bias must be 16-byte aligned");
+  if ((N % 16) || (K % 8) || (lda % 8) || (ldb % 8) || (ldc % (out_fp32 ? 4 : 8)) || (ldr % 8) || (ldm % 8))
+    return set_error("lsnet_gemm_ex_bf16: need N%%16==0, K%%8==0 and 16-byte aligned pitches (N=%d K=%d)", N, K);
+  CUtensorMap tmA;
+  if (int rc = make_map_2d(&tmA, A, M, K, lda, 64, BM)) return rc;
+  GemmArgs a{};
+  a.M = M; a.N = N; a.num_k_iters = (K + BK - 1) / BK; a.m_tiles = (M + BM - 1) / BM;
+  a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  a.resid = static_cast<const __nv_bfloat16*>(resid); a.ldr = ldr;
+  a.mask = static_cast<const __nv_bfloat16*>(mask); a.ldm = ldm;
   return dispatch_kmajor(tmA, Bw, N, K, ldb, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -623,28 +702,80 @@ extern "C" int lsnet_gemm_blockdiag_bf16(const void* A, long long lda, const voi
   return launch_kmajor<64>(tmA, tmB, a, static_cast<cudaStream_t>(stream));
 }
 
+// The generalised implicit-GEMM correlation behind every convolution entry point:
+//   out[b, ho*osh + ooh, wo*osw + oow, n] = sum_t sum_c x[b, ho*ish + tap_dy[t], wo*isw + tap_dx[t], c] * Wt[n, t*Cpad + c]
+//                                           (+ bias[n]) (+ resid) (ReLU) (zeroed where mask <= 0),   ho < Ho, wo < Wo
+extern "C" int lsnet_conv2d_taps_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt, int N,
+                                      int ntaps, const int* tap_dy, const int* tap_dx, const int* tap_kblk, int wt_taps,
+                                      int ish, int isw, int Ho, int Wo,
+                                      void* out, long long ldc, int osh, int osw, int ooh, int oow, int OH, int OW,
+                                      const float* bias, const void* resid, long long ldr, const void* mask,
+                                      long long ldm, int relu, int out_fp32, void* stream) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(bias) % 16) return set_error("lsnet_conv2d_taps_bf16: bias must be 16-byte aligned");
+  if ((C % 8) || (N % 16) || (ldp % 8) || (ldc % (out_fp32 ? 4 : 8)) || (ldr % 8) || (ldm % 8))
+    return set_error("lsnet_conv2d_taps_bf16: need C%%8==0, N%%16==0, aligned pitches (C=%d N=%d)", C, N);
+  if (wt_taps < 1 || wt_taps > 127) return set_error("lsnet_conv2d_taps_bf16: weight pack of 1..127 taps");
+  if (ntaps < 1 || ntaps > kMaxTaps || ish < 1 || isw < 1 || ish > 8 || isw > 8 || osh < 1 || osw < 1)
+    return set_error("lsnet_conv2d_taps_bf16: 1..%d taps, input strides 1..8 (ntaps=%d ish=%d isw=%d)", kMaxTaps, ntaps, ish, isw);
+  const int cblks = (C + 63) / 64;   // weights are packed with C padded to 64 per tap; A's channel tail is TMA zero-fill
+  int TH = 8, TW = 16;
+  pick_patch(Ho, Wo, BM, &TH, &TW);
+  while (TW * isw > 256) { TW /= 2; TH *= 2; }
+  while (TH * ish > 256) { TH /= 2; TW *= 2; }
+  CUtensorMap tmA;
+  if (int rc = make_map_nhwc(&tmA, x, B, H, W, C, ldp, TW, TH, isw, ish)) return rc;
+  GemmArgs a{};
+  a.conv = 1; a.Ho = Ho; a.Wo = Wo; a.TH = TH; a.TW = TW;
+  a.tw_shift = 0;
+  while ((1 << a.tw_shift) < TW) ++a.tw_shift;
+  a.tiles_h = (Ho + TH - 1) / TH; a.tiles_w = (Wo + TW - 1) / TW;
+  a.cblks = cblks; a.ish = ish; a.isw = isw; a.osh = osh; a.osw = osw; a.ooh = ooh; a.oow = oow; a.OH = OH; a.OW = OW;
+  for (int t = 0; t < ntaps; ++t) {
+    if (tap_dy[t] < -128 || tap_dy[t] > 127 || tap_dx[t] < -128 || tap_dx[t] > 127)
+      return set_error("lsnet_conv2d_taps_bf16: tap offset out of range");
+    a.tap_dy[t] = static_cast<signed char>(tap_dy[t]);
+    a.tap_dx[t] = static_cast<signed char>(tap_dx[t]);
+    const int kb = tap_kblk ? tap_kblk[t] : t;
+    if (kb < 0 || kb >= wt_taps) return set_error("lsnet_conv2d_taps_bf16: weight block %d outside the %d-tap pack", kb, wt_taps);
+    a.tap_kb[t] = static_cast<signed char>(kb);
+  }
+  a.M = B * Ho * Wo; a.N = N; a.num_k_iters = ntaps * a.cblks; a.m_tiles = B * a.tiles_h * a.tiles_w;
+  a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  a.resid = static_cast<const __nv_bfloat16*>(resid); a.ldr = ldr;
+  a.mask = static_cast<const __nv_bfloat16*>(mask); a.ldm = ldm;
+  return dispatch_kmajor(tmA, Wt, N, wt_taps * cblks * 64, static_cast<long long>(wt_taps) * cblks * 64, a,
+                         static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int lsnet_conv2d_nhwc_bf16(const void* x, int B, int H, int W, int C, long long ldp, const void* Wt,
                                       int N, int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, void* out,
                                       long long ldc, const float* bias, int relu, int out_fp32, void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0) return 0;
-  if ((C % 8) || (N % 16) || (ldp % 8) || (ldc % (out_fp32 ? 4 : 8)))
-    return set_error("lsnet_conv2d_nhwc_bf16: need C%%8==0, N%%16==0, aligned pitches (C=%d N=%d)", C, N);
-  const int cblks = (C + 63) / 64;   // weights are packed with C padded to 64 per tap; A's channel tail is TMA zero-fill
   // "same" geometry only: output grid == input grid (stride 1, 2*pad == dil*(k-1))
   if (2 * pad_h != dil_h * (kh - 1) || 2 * pad_w != dil_w * (kw - 1))
     return set_error("lsnet_conv2d_nhwc_bf16: only stride-1 'same' convolutions are supported");
-  int TH = 8, TW = 16;
-  pick_patch(H, W, BM, &TH, &TW);
-  CUtensorMap tmA;
-  if (int rc = make_map_nhwc(&tmA, x, B, H, W, C, ldp, TW, TH)) return rc;
-  GemmArgs a{};
-  a.conv = 1; a.H = H; a.W = W; a.TH = TH; a.TW = TW;
-  a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
-  a.kw = kw; a.cblks = cblks; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h; a.dil_w = dil_w;
-  a.M = B * H * W; a.N = N; a.num_k_iters = kh * kw * a.cblks; a.m_tiles = B * a.tiles_h * a.tiles_w;
-  a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
-  return dispatch_kmajor(tmA, Wt, N, kh * kw * cblks * 64, static_cast<long long>(kh) * kw * cblks * 64, a,
-                         static_cast<cudaStream_t>(stream));
+  if (kh * kw > kMaxTaps) return set_error("lsnet_conv2d_nhwc_bf16: at most %d taps", kMaxTaps);
+  int tdy[kMaxTaps], tdx[kMaxTaps];
+  for (int t = 0; t < kh * kw; ++t) { tdy[t] = (t / kw) * dil_h - pad_h; tdx[t] = (t % kw) * dil_w - pad_w; }
+  return lsnet_conv2d_taps_bf16(x, B, H, W, C, ldp, Wt, N, kh * kw, tdy, tdx, nullptr, kh * kw, 1, 1, H, W, out, ldc, 1, 1, 0, 0, H, W,
+                                bias, nullptr, 0, nullptr, 0, relu, out_fp32, stream);
+}
+
+// Split-K factor of a pixel-reduction GEMM with `base` output tiles over `k_chunks` 64-pixel chunks: the persistent grid
+// runs ceil(base * s / SMs) rounds of ceil(k_chunks / s) chunks (+ an epilogue worth ~8 chunks of reds per round), so the
+// factor must be chosen on that product -- rounding the SM count UP to a multiple of `base` (r01: 18 tiles -> 9 splits ->
+// 162 items on 148 SMs) leaves a second round for a handful of CTAs and nearly doubles the kernel's time.
+int lsn::pick_splits(int base, int k_chunks) {
+  const int sms = num_sms();
+  long long best_cost = -1;
+  int best = 1;
+  const int smax = k_chunks < 4 * sms ? k_chunks : 4 * sms;
+  for (int s = 1; s <= smax; ++s) {
+    const long long rounds = (static_cast<long long>(base) * s + sms - 1) / sms;
+    const long long cost = rounds * ((k_chunks + s - 1) / s + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 template <int MT>
@@ -659,10 +790,8 @@ static int launch_wgrad_t(const CUtensorMap& tmA, const CUtensorMap& tmB, WgradA
   }
   const int m_groups = (a.m_tiles + MT - 1) / MT;
   int base = a.taps * m_groups * a.n_tiles;
-  int splits = (num_sms() + base - 1) / base;
-  if (splits > a.k_chunks) splits = a.k_chunks;
-  if (splits < 1) splits = 1;
-  a.splits = splits;
+  a.splits = pick_splits(base, a.k_chunks);
+  int splits = a.splits;
   int items = base * splits;
   int grid = items < num_sms() ? items : num_sms();
   const int th = timing_begin(TC_WGRAD, 2.0 * a.M * a.N * a.taps * a.k_chunks * BK, st);
@@ -697,21 +826,31 @@ extern "C" int lsnet_gemm_tn_bf16(const void* A, long long lda, const void* Bm, 
   return launch_wgrad(tmA, tmB, a, static_cast<cudaStream_t>(stream));
 }
 
-// dW[N_out, kh*kw, C] (fp32) += sum_pixels dY[p, n] * X[p + tap, c]     (stride-1 'same' conv weight gradient)
+// dW[N_out, kh*kw, C] (fp32) += sum_{output pixels p} dY[p, n] * X[p*stride - pad + tap*dil, c]   (dY on the Ho x Wo grid)
+extern "C" int lsnet_conv2d_wgrad_strided_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B,
+                                                    int H, int W, int C, int Ho, int Wo, int N, int kh, int kw,
+                                                    int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                                                    int dil_w, float* dw, void* stream) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  if ((C % 8) || (N % 8) || (ldy % 8) || (ldx % 8)) return set_error("lsnet_conv2d_wgrad_nhwc_bf16: alignment");
+  if (stride_h < 1 || stride_w < 1 || stride_h > 8 || stride_w > 8) return set_error("lsnet_conv2d_wgrad_nhwc_bf16: stride 1..8");
+  int TH = 4, TW = 16;
+  pick_patch(Ho, Wo, BK, &TH, &TW);
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_nhwc(&tmA, dy, B, Ho, Wo, N, ldy, TW, TH, 1, 1)) return rc;
+  if (int rc = make_map_nhwc(&tmB, x, B, H, W, C, ldx, TW, TH, stride_w, stride_h)) return rc;
+  WgradArgs a{};
+  a.M = N; a.N = C; a.m_tiles = (N + BM - 1) / BM; a.n_tiles = (C + BNW - 1) / BNW; a.taps = kh * kw;
+  a.conv = 1; a.TH = TH; a.TW = TW; a.tiles_h = (Ho + TH - 1) / TH; a.tiles_w = (Wo + TW - 1) / TW;
+  a.k_chunks = B * a.tiles_h * a.tiles_w; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h;
+  a.dil_w = dil_w; a.ish = stride_h; a.isw = stride_w; a.out = dw; a.ldc = static_cast<long long>(kh) * kw * C;
+  return launch_wgrad(tmA, tmB, a, static_cast<cudaStream_t>(stream));
+}
+
+// stride-1 'same' conv weight gradient
 extern "C" int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, long long ldx, int B, int H,
                                             int W, int C, int N, int kh, int kw, int pad_h, int pad_w, int dil_h,
                                             int dil_w, float* dw, void* stream) {
-  if (B <= 0 || H <= 0 || W <= 0) return 0;
-  if ((C % 8) || (N % 8) || (ldy % 8) || (ldx % 8)) return set_error("lsnet_conv2d_wgrad_nhwc_bf16: alignment");
-  int TH = 4, TW = 16;
-  pick_patch(H, W, BK, &TH, &TW);
-  CUtensorMap tmA, tmB;
-  if (int rc = make_map_nhwc(&tmA, dy, B, H, W, N, ldy, TW, TH)) return rc;
-  if (int rc = make_map_nhwc(&tmB, x, B, H, W, C, ldx, TW, TH)) return rc;
-  WgradArgs a{};
-  a.M = N; a.N = C; a.m_tiles = (N + BM - 1) / BM; a.n_tiles = (C + BNW - 1) / BNW; a.taps = kh * kw;
-  a.conv = 1; a.TH = TH; a.TW = TW; a.tiles_h = (H + TH - 1) / TH; a.tiles_w = (W + TW - 1) / TW;
-  a.k_chunks = B * a.tiles_h * a.tiles_w; a.kw = kw; a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dil_h;
-  a.dil_w = dil_w; a.out = dw; a.ldc = static_cast<long long>(kh) * kw * C;
-  return launch_wgrad(tmA, tmB, a, static_cast<cudaStream_t>(stream));
+  return lsnet_conv2d_wgrad_strided_nhwc_bf16(dy, ldy, x, ldx, B, H, W, C, H, W, N, kh, kw, 1, 1, pad_h, pad_w, dil_h,
+                                              dil_w, dw, stream);
 }

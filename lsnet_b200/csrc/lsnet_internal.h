@@ -21,7 +21,9 @@ int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, u
                 uint32_t box_rows);
 // rank-4 bf16 SWIZZLE_128B map over NHWC [B,H,W,C] (pixel pitch ldp elements); box = [64, TW, TH, 1]
 int make_map_nhwc(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldp,
-                  uint32_t TW, uint32_t TH);
+                  uint32_t TW, uint32_t TH, uint32_t sw = 1, uint32_t sh = 1);
+// split-K factor of a pixel-reduction GEMM: `base` output tiles, `k_chunks` 64-pixel chunks (cost model over SM rounds)
+int pick_splits(int base, int k_chunks);
 // rank-5 map over a [B*Ho*Wo, taps*C] bf16 matrix viewed as [B, Ho, Wo, taps, C]; box = [64, taps, PW, PH, 1]
 int make_map_col5d(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t Ho, uint64_t Wo, uint64_t taps, uint64_t C,
                    uint64_t ldcol, uint32_t PW, uint32_t PH);

@@ -2,6 +2,8 @@
 (mmdet/models/backbones/resnet.py:305-646, resnext.py:9-131).  The plain convolutions stay on cuDNN (bf16,
 channels_last) in this round — SURVEY.md §8 row f4 ("next"); the DCNv2 ``conv2`` sites (stage_with_dcn) are built
 through CONV_LAYERS and so land on the B200 deformable kernels (groups == 1 only for now)."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -106,9 +108,145 @@ def conv_bn_fold(conv, bn):
     return _BnFold.apply(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps))
 
 
-def conv_bn_act(x, conv, bn, z=None):
+class _BnFoldPacked(Function):
+    """(W, gamma, beta; frozen mean, var) -> the two bf16 GEMM operand packs of W*s ([O, taps*I] and [I, taps*O]) and the
+    folded bias, one kernel each way (lsnet_bn_fold2_fwd / _bwd).  The backward takes the weight gradient as the fp32
+    [O, taps*I] matrix the weight-gradient GEMM wrote and -- when the trainer exposes the parameters' gradient memory --
+    adds gW / ggamma / gbeta there directly."""
+
+    @staticmethod
+    def forward(ctx, W, gamma, beta, mean, var, eps, holder):
+        # ``holder``: dict shared with the consuming _ConvPacked, which leaves the fp32 weight gradient there (autograd
+        # would cast a gradient returned for the bf16 pack to bf16)
+        from .. import lib as L
+        ctx.holder = holder
+        O, I, kh, kw = W.shape
+        KK = kh * kw
+        Wd = W.detach()
+        tap_major = KK > 1 and Wd.stride(1) == 1 and Wd.stride(3) == I and Wd.stride(2) == kw * I
+        if not tap_major and not Wd.is_contiguous():
+            Wd = Wd.contiguous()
+        si, sk = (1, I) if tap_major else (KK, 1)
+        wb = torch.empty((O, KK * I), device=W.device, dtype=torch.bfloat16)
+        wt = torch.empty((I, KK * O), device=W.device, dtype=torch.bfloat16)
+        bias = torch.empty(O, device=W.device, dtype=torch.float32)
+        L.call('lsnet_bn_fold2_fwd', L.ptr(Wd), L.c_ll(si), L.c_ll(sk), L.ptr(gamma.detach()), L.ptr(beta.detach()),
+               L.ptr(mean), L.ptr(var), L.c_f(eps), L.c_int(O), L.c_int(I), L.c_int(KK), L.ptr(wb), L.ptr(wt),
+               L.ptr(bias), L.stream())
+        ctx.save_for_backward(Wd, gamma, mean, var)
+        ctx.cfg = (eps, si, sk, tap_major)
+        ctx.params = (W, gamma, beta)
+        ctx.mark_non_differentiable(wt)
+        return wb, wt, bias
+
+    @staticmethod
+    def backward(ctx, gwb, _gwt, gbias):
+        from .. import lib as L
+        from ..ops import gemm_ops as G
+        Wd, gamma, mean, var = ctx.saved_tensors
+        eps, si, sk, tap_major = ctx.cfg
+        O, I, kh, kw = Wd.shape
+        KK = kh * kw
+        gwb = ctx.holder.pop('gwb', None)
+        if gwb is None:
+            gwb = torch.zeros((O, KK * I), device=Wd.device, dtype=torch.float32)
+        gb = None if gbias is None else gbias.float().contiguous()
+        W, gm, bt = ctx.params
+        # straight into the parameters' gradient memory (GraphTrainer's flat buffer) when all three are exposed
+        tg, tb = G.direct_vec(gm), G.direct_vec(bt)
+        tw = None
+        if getattr(W, '_lsnet_direct_any', False) and W.grad is not None and W.grad.dtype == torch.float32 \
+                and W.grad.stride() == Wd.stride():
+            tw = W.grad
+        direct = tw is not None and tg is not None and tb is not None and all(ctx.needs_input_grad[:3])
+        if direct:
+            gW, gg, gbt = tw, tg, tb
+        else:
+            gW = torch.empty_strided(Wd.shape, Wd.stride(), device=Wd.device, dtype=torch.float32)
+            gg = torch.empty(O, device=Wd.device, dtype=torch.float32)
+            gbt = torch.empty(O, device=Wd.device, dtype=torch.float32)
+        L.call('lsnet_bn_fold2_bwd', L.ptr(gwb), L.ptr(gb), L.ptr(Wd), L.c_ll(si), L.c_ll(sk), L.ptr(gamma.detach()),
+               L.ptr(mean), L.ptr(var), L.c_f(eps), L.c_int(O), L.c_int(I), L.c_int(KK), L.ptr(gW), L.ptr(gg),
+               L.ptr(gbt), L.c_int(int(direct)), L.stream())
+        if direct:
+            return None, None, None, None, None, None, None
+        return gW, gg, gbt, None, None, None, None
+
+
+# 'own': trunk convolutions on the library's tcgen05 implicit-GEMM kernels (every groups == 1 conv whose input channels are
+# a multiple of 64: all of ResNet-50/101 but the 3-channel stem); 'cudnn': the cuDNN fused conv+bias(+add)+ReLU path.
+TRUNK = os.environ.get('LSNET_TRUNK', 'own')
+# fold every (conv, BN) pair of the trunk on a side stream at the start of the forward (they only depend on parameters):
+# 53 five-microsecond kernels leave the critical path, and so do their backward twins
+FOLD_SIDE = os.environ.get('LSNET_FOLD_SIDE', '1') == '1'
+STEM_OWN = os.environ.get('LSNET_STEM_OWN', '1') == '1'
+_FOLD_STREAM = {}
+_PREFOLD = {}
+
+
+def _own_ok(conv):
+    return (TRUNK == 'own' and isinstance(conv, nn.Conv2d) and conv.groups == 1 and conv.in_channels % 64 == 0
+            and conv.out_channels % 16 == 0 and conv.kernel_size[0] == conv.kernel_size[1]
+            and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+            and conv.dilation[0] == conv.dilation[1] and conv.bias is None)
+
+
+def _fold_apply(conv, bn):
+    holder = {}
+    return _BnFoldPacked.apply(conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps),
+                               holder) + (holder,)
+
+
+def fold_packed(conv, bn):
+    """(wb, wt, bias, holder) of a (conv, frozen BN) pair: from the side-stream prefold of this forward if there is one."""
+    hit = _PREFOLD.get(id(conv))
+    if hit is not None and hit[0] is conv:
+        return hit[1]
+    return _fold_apply(conv, bn)
+
+
+def join_fold_stream(device):
+    """After backward inside a stream capture: the fold backward nodes ran on the side stream -- rejoin it."""
+    side = _FOLD_STREAM.get(str(device))
+    if side is None:
+        return
+    with torch.cuda.stream(side):
+        busy = torch.cuda.is_current_stream_capturing()
+    if busy or not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream(device).wait_stream(side)
+
+
+def prefold(pairs, device):
+    """Run the folds of ``pairs`` [(conv, bn)] on a side stream; returns the stream the consumers wait on."""
+    cur = torch.cuda.current_stream(device)
+    key = str(device)
+    if key not in _FOLD_STREAM:
+        _FOLD_STREAM[key] = torch.cuda.Stream(device=device)
+    side = _FOLD_STREAM[key]
+    side.wait_stream(cur)
+    _PREFOLD.clear()
+    with torch.cuda.stream(side):
+        for conv, bn in pairs:
+            out = _fold_apply(conv, bn)
+            for t in out[:3]:
+                t.record_stream(cur)
+            _PREFOLD[id(conv)] = (conv, out)
+    return side
+
+
+def conv_bn_act(x, conv, bn, z=None, relu=True, extra_bias=None):
     """relu(BN_eval(conv(x)) (+ z)) with the BN folded into the conv (see above)."""
+    if _own_ok(conv):
+        from ..ops.conv import conv2d_packed
+        wb, wt, shift, holder = fold_packed(conv, bn)
+        if extra_bias is not None:
+            shift = shift + extra_bias
+        return conv2d_packed(x, wb, wt, shift, z, conv.kernel_size, conv.stride[0], conv.padding[0], conv.dilation[0], relu,
+                             wgrad_holder=holder)
     w, shift = conv_bn_fold(conv, bn)
+    if extra_bias is not None:
+        shift = shift + extra_bias
+    assert relu
     return _ConvBiasAct.apply(x, w, shift, z, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups)
 
 
@@ -139,6 +277,9 @@ class Bottleneck(nn.Module):
         self.bn3 = nn.BatchNorm2d(planes * self.expansion)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
+        for c in (self.conv1, self.conv2, self.conv3, None if downsample is None else downsample[0]):
+            if c is not None and _own_ok(c):
+                c.weight._lsnet_tapmajor = True      # GraphTrainer may keep it tap-major (see train.py)
 
     norm3 = property(lambda self: self.bn3)
 
@@ -151,9 +292,13 @@ class Bottleneck(nn.Module):
         out = conv_bn_act(out, self.conv2, self.bn2)
         if self.downsample is None:
             return conv_bn_act(out, self.conv3, self.bn3, z=x)
-        # identity branch: plain conv with the folded weight; its folded bias rides on conv3's bias
-        wd, bd = conv_bn_fold(self.downsample[0], self.downsample[1])
         dc = self.downsample[0]
+        if _own_ok(dc) and _own_ok(self.conv3):
+            # identity branch on the same kernels (bias in its own epilogue, no ReLU), added in conv3's epilogue
+            ident = conv_bn_act(x, dc, self.downsample[1], relu=False)
+            return conv_bn_act(out, self.conv3, self.bn3, z=ident)
+        # identity branch: plain conv with the folded weight; its folded bias rides on conv3's bias
+        wd, bd = conv_bn_fold(dc, self.downsample[1])
         ident = F.conv2d(x.to(torch.bfloat16), wd, None, dc.stride, dc.padding)
         w3, b3 = conv_bn_fold(self.conv3, self.bn3)
         return _ConvBiasAct.apply(out, w3, b3 + bd, ident, [1, 1], [0, 0], [1, 1], 1)
@@ -256,9 +401,41 @@ class ResNet(nn.Module):
                 if self.zero_init_residual:
                     nn.init.constant_(m.bn3.weight, 0)
 
+    def _own_stem(self, x):
+        """The frozen stem (frozen_stages >= 0: no gradient reaches conv1 / bn1) on the library's stem kernels."""
+        c, m = self.conv1, self.maxpool
+        return (TRUNK == 'own' and STEM_OWN and not x.requires_grad and not c.weight.requires_grad
+                and not self.bn1.weight.requires_grad and c.in_channels == 3 and c.out_channels == 64
+                and c.kernel_size == (7, 7) and c.stride == (2, 2) and c.padding == (3, 3) and c.bias is None
+                and m.kernel_size == 3 and m.stride == 2 and m.padding == 1 and x.dtype in (torch.float32, torch.bfloat16))
+
+    def _fold_pairs(self):
+        pairs = []
+        for m in self.modules():
+            if isinstance(m, Bottleneck) and not m.bn1.training:
+                cands = [(m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3)]
+                if m.downsample is not None:
+                    cands.append((m.downsample[0], m.downsample[1]))
+                pairs += [(c, b) for c, b in cands if _own_ok(c)]
+        return pairs
+
     def forward(self, x):
+        fold_ev = None
         if x.is_cuda and not self.bn1.training and _fused_available(x):
-            x = self.maxpool(conv_bn_act(x, self.conv1, self.bn1))
+            if FOLD_SIDE and TRUNK == 'own':
+                fold_side = prefold(self._fold_pairs(), x.device)
+                fold_ev = True
+            if self._own_stem(x):
+                from .. import ops
+                wp, shift = ops.gemm_ops.cached_pack(
+                    self.conv1.weight, 'stem', lambda t: ops.pack_stem_weight(
+                        t, self.bn1.weight.detach(), self.bn1.bias.detach(), self.bn1.running_mean, self.bn1.running_var,
+                        self.bn1.eps))
+                x = ops.maxpool3x3s2(ops.stem_conv(x, wp, shift))
+            else:
+                x = self.maxpool(conv_bn_act(x, self.conv1, self.bn1))
+            if fold_ev:
+                torch.cuda.current_stream(x.device).wait_stream(fold_side)
         else:
             x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
@@ -266,6 +443,7 @@ class ResNet(nn.Module):
             x = getattr(self, name)(x)
             if i in self.out_indices:
                 outs.append(x)
+        _PREFOLD.clear()
         return tuple(outs)
 
     def train(self, mode=True):        # resnet.py:636-646

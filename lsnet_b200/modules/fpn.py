@@ -18,7 +18,8 @@ class ConvNorm(nn.Module):
         self.with_norm = norm_cfg is not None
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=not self.with_norm)
         self.stride, self.padding, self.k, self.act = stride, padding, k, act
-        self.conv.weight._lsnet_tapmajor = stride == 1 and (k == 1 or padding == k // 2)   # see train.py
+        self.conv.weight._lsnet_tapmajor = (stride == 1 and (k == 1 or padding == k // 2)) or \
+            (cin % 64 == 0 and cout % 64 == 0)   # see train.py
         if self.with_norm:
             kind = norm_cfg.get('type', 'GN')
             if kind == 'GN':
@@ -38,6 +39,9 @@ class ConvNorm(nn.Module):
     def forward(self, x):
         if self.stride == 1 and x.is_cuda and (self.k == 1 or self.padding == self.k // 2):
             x = ops.conv2d_same(x, self.conv.weight, self.conv.bias, padding=self.padding)
+        elif x.is_cuda and self.conv.in_channels % 64 == 0 and self.conv.out_channels % 64 == 0 and self.conv.groups == 1:
+            # the stride-2 extra levels (fpn.py:203-211): strided TMA boxes forward, one implicit GEMM per output phase backward
+            x = ops.conv2d_strided(x, self.conv.weight, self.conv.bias, self.stride, self.padding)
         else:
             x = F.conv2d(x.to(torch.bfloat16), self.conv.weight.to(torch.bfloat16),
                          None if self.conv.bias is None else self.conv.bias.to(torch.bfloat16), self.stride, self.padding)

@@ -75,7 +75,8 @@ def cached_pack(w, kind, fn):
             cur = torch.cuda.current_stream(w.device)
             if cur != hit[4]:
                 cur.wait_event(hit[3])
-                hit[2].record_stream(cur)
+                for t in (hit[2] if isinstance(hit[2], (tuple, list)) else (hit[2],)):
+                    t.record_stream(cur)
         return hit[2]
     p = fn(w.detach())
     ev = st = None

@@ -168,6 +168,7 @@ class GraphTrainer:
                 p.grad = self.flat_g[o:o + k].view_as(p)
                 # biases / norm affines: the backward kernels add into this memory directly (ops.gemm_ops.direct_vec)
                 p._lsnet_direct_vec = DIRECT_VEC and p.dim() == 1
+            p._lsnet_direct_any = DIRECT_VEC
             o += (k + al - 1) // al * al
         # ---- captured steps, one per input canvas (H, W): multi-scale training (configs/lsnet/*mstrain*) replays the
         # graph of the batch's shape bucket; all graphs share ONE memory pool (they never run concurrently), so the
@@ -211,6 +212,8 @@ class GraphTrainer:
         losses = self.model(img=st.img, img_metas=st.metas, gt_bboxes=st.gt, gt_labels=None)
         loss, log_vars = parse_losses(losses)
         loss.backward()
+        from .modules.backbone import join_fold_stream
+        join_fold_stream(self.device)
         return loss, log_vars
 
     def _ensure_capacity(self, batch):

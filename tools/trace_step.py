@@ -70,4 +70,13 @@ with open('gpurun_out/trace_summary.md', 'w') as f:
     gaps.sort(reverse=True)
     f.write('\nlargest idle gaps (us, next kernel): ' + ', '.join(f'{g:.0f} ({n})' for g, n in gaps[:12]) + '\n')
 print(open('gpurun_out/trace_summary.md').read())
+# compact per-activity timeline for offline analysis: start us (relative), duration us, stream, grid, name
+with open('gpurun_out/trace_timeline.csv', 'w') as f:
+    f.write('start_us,dur_us,stream,grid,block,name\n')
+    for e in ev:
+        a = e['args']
+        g = a.get('grid'); b = a.get('block')
+        g = 'x'.join(str(v) for v in g) if isinstance(g, (list, tuple)) else str(g)
+        b = 'x'.join(str(v) for v in b) if isinstance(b, (list, tuple)) else str(b)
+        f.write(f"{e['ts'] - t0:.1f},{e['dur']:.1f},{a.get('stream', -1)},{g},{b},\"{e['name'][:90]}\"\n")
 os.remove('gpurun_out/trace_step.json')
