@@ -29,7 +29,8 @@ unsigned long long lsnet_launch_count(void);    /* kernels launched by this libr
 int lsnet_abi_version(void);
 int lsnet_require_sm100(void);                  /* 0 iff the current CUDA device is compute capability 10.x */
 
-/* Optional device timing per kernel class (0 tcgen05 GEMM/conv, 1 weight-gradient GEMM, 2 DCN gather, 3 DCN scatter):
+/* Optional device timing per kernel class (0 tcgen05 GEMM/conv, 1 weight-gradient GEMM, 2 DCN gather, 3 DCN scatter,
+ * 4-6 fused DCN forward / weight gradient / backward data, 7 GEMM launches below the FLOP/byte ridge, accounted in bytes):
  * when enabled every launch of the class is bracketed by CUDA events on its own stream; collect() returns the summed
  * elapsed ms, the launch count and the summed algorithmic work (FLOPs for 0/1, bytes for 2/3) since the last reset. */
 void lsnet_timing_enable(int on);

@@ -213,53 +213,88 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t* stg = staging + (warp - 2) * (32 * 20);
 #pragma unroll 1
       for (int c = col_begin; c < col_begin + Cfg::kColsPerWarp; c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= p.N) continue;     // warp-uniform (this warp neither reads the accumulator columns nor stores them)
+        // every global operand of the epilogue is requested BEFORE the accumulator is awaited, as independent loads: issued
+        // one by one next to their uses they cost eight serial L1/L2 round trips per 32-column block (ncu: 40 % of the
+        // warp-stall samples of a K = 64 layer sat on the bias adds)
+        float4 bv[8];
+        uint4 rv[4], mv[4];
+        if (p.bias) {      // N % 16 == 0 and the bias vector is 16-byte aligned (host-checked): whole float4 groups
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            bv[j] = (col0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // resid / mask: requested in the COALESCED pattern of the write-out (8 rows x 64 contiguous bytes per warp
+        // instruction) and transposed to row-per-thread through the warp's staging buffer below -- one thread reading
+        // its own 64-byte row piece touches 32 different lines per instruction and doubled the kernel's time
+        const int seg_l = lane & 3;
+        if (p.resid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rv[i] = (sok[i] && col0 + seg_l * 8 < p.N)
+                        ? __ldg(reinterpret_cast<const uint4*>(p.resid + srow[i] * p.ldr + col0 + seg_l * 8))
+                        : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (p.mask) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            mv[i] = (sok[i] && col0 + seg_l * 8 < p.N)
+                        ? __ldg(reinterpret_cast<const uint4*>(p.mask + srow[i] * p.ldm + col0 + seg_l * 8))
+                        : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        }
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (col0 >= p.N) continue;     // warp-uniform
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {      // N % 16 == 0 and the bias vector is 16-byte aligned (host-checked): whole float4 groups
+        if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (col0 + j < p.N) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
-            }
+          for (int j = 0; j < 8; ++j) {
+            f[4 * j] += bv[j].x; f[4 * j + 1] += bv[j].y; f[4 * j + 2] += bv[j].z; f[4 * j + 3] += bv[j].w;
+          }
         }
-        if (p.resid && valid) {
-          const __nv_bfloat16* rp = p.resid + row * p.ldr + col0;
+        if (p.resid) {
+          // transpose: (row (lane>>2)+8i, 16-byte segment lane&3) -> this thread's row, segments 0..3
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + 8 * j < p.N) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + j);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * 20 + seg_l * 4) = rv[i];
+          __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[8 * j + 2 * i] += __uint_as_float(rw[i] << 16);
-                f[8 * j + 2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
-              }
+          for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(stg + lane * 20 + j * 4);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t rw[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              f[8 * j + 2 * i] += __uint_as_float(rw[i] << 16);
+              f[8 * j + 2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
             }
+          }
         }
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (p.mask && valid) {
-          const __nv_bfloat16* mp = p.mask + row * p.ldm + col0;
+        if (p.mask) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col0 + 8 * j < p.N) {
-              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mp) + j);
-              const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * 20 + seg_l * 4) = mv[i];
+          __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {      // bf16 > 0  <=>  sign clear and not (+)zero
-                if (!((mw[i] & 0xffffu) - 1u < 0x7fffu)) f[8 * j + 2 * i] = 0.f;
-                if (!((mw[i] >> 16) - 1u < 0x7fffu)) f[8 * j + 2 * i + 1] = 0.f;
-              }
+          for (int j = 0; j < 4; ++j) mv[j] = *reinterpret_cast<const uint4*>(stg + lane * 20 + j * 4);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t mw[4] = {mv[j].x, mv[j].y, mv[j].z, mv[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {      // bf16 > 0  <=>  sign clear and not (+)zero
+              if (!((mw[i] & 0xffffu) - 1u < 0x7fffu)) f[8 * j + 2 * i] = 0.f;
+              if (!((mw[i] >> 16) - 1u < 0x7fffu)) f[8 * j + 2 * i + 1] = 0.f;
             }
+          }
         }
         if (p.out_fp32) {
           if (valid) {
@@ -622,7 +657,15 @@ static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   }
   int tiles = a.m_tiles * a.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  const int th = timing_begin(TC_GEMM, 2.0 * a.M * a.N * a.num_k_iters * BK, st);
+  // roofline class of this launch: algorithmic FLOPs vs algorithmic bytes (input read once, weights, output, epilogue
+  // operands) against the ridge of the machine
+  const double flops = 2.0 * a.M * a.N * a.num_k_iters * BK;
+  const double k_in = a.conv ? static_cast<double>(a.cblks) * BK * ((a.num_k_iters > a.cblks) ? a.ish * a.isw : 1)
+                             : static_cast<double>(a.num_k_iters) * BK;
+  const double bytes = 2.0 * a.M * k_in + 2.0 * a.N * a.num_k_iters * BK + static_cast<double>(a.M) * a.N * (a.out_fp32 ? 4 : 2) +
+                       (a.resid ? 2.0 * a.M * a.N : 0.0) + (a.mask ? 2.0 * a.M * a.N : 0.0);
+  const bool hbm_bound = flops < 200.0 * bytes;
+  const int th = timing_begin(hbm_bound ? TC_GEMM_HBM : TC_GEMM, hbm_bound ? bytes : flops, st);
   gemm_kmajor_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
   timing_end(th, st);
   cudaError_t e = cudaGetLastError();
@@ -633,12 +676,26 @@ static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
 
 static int dispatch_kmajor(const CUtensorMap& tmA, const void* Bw, int N, int K, long long ldb, GemmArgs& a,
                            cudaStream_t st) {
-  int BN = N >= 256 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-  // Small problems (the upper pyramid levels: 3..33 M tiles) leave most of the 148 SMs idle with 256-wide tiles, and
-  // one CTA streams its K loop at only ~80 GB/s: narrow the N tile until the grid covers the machine.
+  // N tile: the widest that fits, narrowed when that saves whole rounds of the persistent grid.  A K step of a
+  // 128 x BN tile costs max(BN/2 tensor cycles, (128+BN)/4 cycles of shared-memory operand reads) = 128 / 64 / 48 / 40
+  // cycles for BN = 256 / 128 / 64 / 32; a launch costs rounds(BN) times that.  Level-0 / level-1 head GEMMs keep 256
+  // (ties go to the wider tile: fewer weight re-reads); the trunk's 3x3 convs on 50x84 maps (168 tiles -> two rounds at 57 %)
+  // and the small pyramid levels get narrower tiles.  LSNET_GEMM_ADAPT_BN=0 restores the fixed choice.
+  const int bn_max = N >= 256 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  int BN = bn_max;
   static int adapt = -1;
-  if (adapt < 0) { const char* e = getenv("LSNET_GEMM_ADAPT_BN"); adapt = e ? atoi(e) : 0; }   // measured in-step: 7.50 ms with, 7.36 ms without -> opt-in
-  while (adapt && BN > 32 && static_cast<long long>(a.m_tiles) * ((N + BN - 1) / BN) < num_sms()) BN /= 2;
+  if (adapt < 0) { const char* e = getenv("LSNET_GEMM_ADAPT_BN"); adapt = e ? atoi(e) : 1; }
+  // launches that do not fill one round keep the wide tile: in the training step they run beside other streams' kernels,
+  // and more, narrower CTAs only take SMs away from those (measured in-step: 22.9 ms with, 22.5 ms without)
+  if (adapt && static_cast<long long>(a.m_tiles) * ((N + bn_max - 1) / bn_max) > num_sms()) {
+    const int sms = num_sms();
+    long long best = -1;
+    for (int bn = bn_max; bn >= 32; bn /= 2) {
+      const long long tiles = static_cast<long long>(a.m_tiles) * ((N + bn - 1) / bn);
+      const long long cost = ((tiles + sms - 1) / sms) * (bn == 256 ? 128 : bn == 128 ? 64 : bn == 64 ? 48 : 40);
+      if (best < 0 || cost < best) { best = cost; BN = bn; }
+    }
+  }
   a.n_tiles = (N + BN - 1) / BN;
   CUtensorMap tmB;
   if (int rc = make_map_2d(&tmB, Bw, N, K, ldb, 64, BN)) return rc;

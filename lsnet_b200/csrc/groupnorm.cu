@@ -49,7 +49,29 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const int total = (p1 - p0) * vpp;
   float s = 0.f, ss = 0.f;
   int my_v = -1;
-  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+  int i_begin = threadIdx.x;
+  if (GN_THREADS % vpp == 0 && !x2) {
+    // every thread keeps ONE vector column and walks the pixels with a fixed stride: four independent 16-byte loads in
+    // flight per thread (the one-load-per-iteration loop below left the memory pipe idle: 1.9 TB/s at the level-0 shape)
+    const int v = threadIdx.x % vpp, step = GN_THREADS / vpp;
+    const __nv_bfloat16* base = x + static_cast<long long>(b) * a.HW * a.ldx + v * 8;
+    int p = p0 + threadIdx.x / vpp;
+    for (; p + 3 * step < p1; p += 4 * step) {
+      float f0[8], f1[8], f2[8], f3[8];
+      ld8(base + static_cast<long long>(p) * a.ldx, f0);
+      ld8(base + static_cast<long long>(p + step) * a.ldx, f1);
+      ld8(base + static_cast<long long>(p + 2 * step) * a.ldx, f2);
+      ld8(base + static_cast<long long>(p + 3 * step) * a.ldx, f3);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s += (f0[e] + f1[e]) + (f2[e] + f3[e]);
+        ss += (f0[e] * f0[e] + f1[e] * f1[e]) + (f2[e] * f2[e] + f3[e] * f3[e]);
+      }
+    }
+    my_v = v;
+    i_begin = (p - p0) * vpp + v;       // the remaining pixels of this column go through the generic loop
+  }
+  for (int i = i_begin; i < total; i += GN_THREADS) {
     const int v = i % vpp, p = p0 + i / vpp;
     if (my_v >= 0 && v != my_v) {   // only when GN_THREADS % vpp != 0: flush and switch column
       atomicAdd(&sm[2 * my_v], s); atomicAdd(&sm[2 * my_v + 1], ss); s = ss = 0.f;
@@ -168,7 +190,51 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     for (int e = 0; e < 8; ++e) { atomicAdd(&sm_dg[my_v * 8 + e], dg[e]); atomicAdd(&sm_db[my_v * 8 + e], db[e]); dg[e] = db[e] = 0.f; }
     atomicAdd(&sm_s[2 * my_v], s1); atomicAdd(&sm_s[2 * my_v + 1], s2); s1 = s2 = 0.f;
   };
-  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+  int i_begin = threadIdx.x;
+  if (GN_THREADS % vpp == 0) {
+    // fixed vector column per thread: group statistics / affine parameters are loaded once, and the x / dy vectors of
+    // two pixels are requested together (4-6 independent 16-byte loads in flight per thread)
+    const int v = threadIdx.x % vpp, step = GN_THREADS / vpp;
+    float mean, rstd;
+    mean_rstd(stats, b, v / cpg8, a, &mean, &rstd);
+    load8f(gamma + v * 8, gmr);
+    load8f(beta + v * 8, btr);
+    loaded_v = v;
+    int p = p0 + threadIdx.x / vpp;
+    for (; p + step < p1; p += 2 * step) {
+      const long long pa = static_cast<long long>(b) * a.HW + p, pb = pa + step;
+      float fa[8], fb[8], da[8], db2[8];
+      ld8(x + pa * a.ldx + v * 8, fa);
+      ld8(x + pb * a.ldx + v * 8, fb);
+      ld8(dy + pa * lddy + v * 8, da);
+      ld8(dy + pb * lddy + v * 8, db2);
+      if (x2) {
+        float ga[8], gb[8];
+        ld8(x2 + pa * a.ldx2 + v * 8, ga);
+        ld8(x2 + pb * a.ldx2 + v * 8, gb);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          fa[e] = __bfloat162float(__float2bfloat16(fa[e] + ga[e]));
+          fb[e] = __bfloat162float(__float2bfloat16(fb[e] + gb[e]));
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float gm = gmr[e];
+        const float xa = (fa[e] - mean) * rstd, xb = (fb[e] - mean) * rstd;
+        float ya = da[e], yb = db2[e];
+        if (a.relu && !(xa * gm + btr[e] > 0.f)) ya = 0.f;
+        if (a.relu && !(xb * gm + btr[e] > 0.f)) yb = 0.f;
+        dg[e] += ya * xa + yb * xb;
+        db[e] += ya + yb;
+        s1 += (ya + yb) * gm;
+        s2 += (ya * xa + yb * xb) * gm;
+      }
+    }
+    my_v = v;
+    i_begin = (p - p0) * vpp + v;
+  }
+  for (int i = i_begin; i < total; i += GN_THREADS) {
     const int v = i % vpp, p = p0 + i / vpp;
     if (my_v >= 0 && v != my_v) flush();
     my_v = v;

@@ -11,8 +11,10 @@ int set_error(const char* fmt, ...);
 void count_launch();
 int check_launch(const char* what);
 // kernel classes for the optional device timing (api.cu)
+// TC_GEMM_HBM: gemm_kmajor launches whose arithmetic intensity (FLOPs / algorithmic bytes) is below the machine's ridge
+// (measured 1346.8 TFLOP/s / 6.54 TB/s ~ 200 FLOP/B): bounded by HBM, so their work is accounted in bytes
 enum { TC_GEMM = 0, TC_WGRAD = 1, TC_IM2COL = 2, TC_COL2IM = 3, TC_DCN_FWD = 4, TC_DCN_WGRAD = 5, TC_DCN_BWD = 6,
-       TC_NUM = 7 };
+       TC_GEMM_HBM = 7, TC_NUM = 8 };
 int timing_begin(int cls, double work, cudaStream_t st);
 void timing_end(int handle, cudaStream_t st);
 // host helpers of the tcgen05 GEMM family (gemm_tcgen05.cu)

@@ -120,6 +120,7 @@ class _BnFoldPacked(Function):
         # would cast a gradient returned for the bf16 pack to bf16)
         from .. import lib as L
         ctx.holder = holder
+        ctx.set_materialize_grads(False)     # no zero tensors for the packs' (absent) gradients
         O, I, kh, kw = W.shape
         KK = kh * kw
         Wd = W.detach()
@@ -180,6 +181,8 @@ TRUNK = os.environ.get('LSNET_TRUNK', 'own')
 # 53 five-microsecond kernels leave the critical path, and so do their backward twins
 FOLD_SIDE = os.environ.get('LSNET_FOLD_SIDE', '1') == '1'
 STEM_OWN = os.environ.get('LSNET_STEM_OWN', '1') == '1'
+# ReLU masks / identity-path sums of the trunk's backward inside the input-gradient GEMM epilogues (ops/conv.py::_ConvPacked)
+BWD_FUSE = os.environ.get('LSNET_TRUNK_BWD_FUSE', '1') == '1'
 _FOLD_STREAM = {}
 _PREFOLD = {}
 
@@ -234,7 +237,7 @@ def prefold(pairs, device):
     return side
 
 
-def conv_bn_act(x, conv, bn, z=None, relu=True, extra_bias=None):
+def conv_bn_act(x, conv, bn, z=None, relu=True, extra_bias=None, opts=None):
     """relu(BN_eval(conv(x)) (+ z)) with the BN folded into the conv (see above)."""
     if _own_ok(conv):
         from ..ops.conv import conv2d_packed
@@ -242,7 +245,7 @@ def conv_bn_act(x, conv, bn, z=None, relu=True, extra_bias=None):
         if extra_bias is not None:
             shift = shift + extra_bias
         return conv2d_packed(x, wb, wt, shift, z, conv.kernel_size, conv.stride[0], conv.padding[0], conv.dilation[0], relu,
-                             wgrad_holder=holder)
+                             wgrad_holder=holder, opts=opts if BWD_FUSE else None)
     w, shift = conv_bn_fold(conv, bn)
     if extra_bias is not None:
         shift = shift + extra_bias
@@ -288,6 +291,27 @@ class Bottleneck(nn.Module):
                 and isinstance(self.conv2, nn.Conv2d) and _fused_available(x))
 
     def _inner_fused(self, x):
+        own = _own_ok(self.conv1) and _own_ok(self.conv2) and _own_ok(self.conv3) and \
+            (self.downsample is None or _own_ok(self.downsample[0]))
+        if own:
+            # Backward fusion (exact, see _ConvPacked): inside the block every ReLU output has ONE consumer, so the
+            # consumer's input-gradient GEMM applies the mask and the producer only sums its bias columns; the block input
+            # is read by conv1 and the identity path (or the downsample conv) -- they share a gradient sink.
+            # in_relu: x is the (ReLU) output of the previous Bottleneck; out_premasked: every consumer of this block's
+            # output masks by it (the next Bottleneck of the stage) -- both set by ResNet.
+            # the sink needs EVERY consumer of x inside this block (autograd may sum an outside gradient with the first
+            # one before the second is added in place): true for all but a stage's first block, whose input also feeds
+            # the neck / is the previous stage's output
+            sink = {} if getattr(self, 'in_exclusive', False) else None
+            in_mask = getattr(self, 'in_relu', False)
+            out = conv_bn_act(x, self.conv1, self.bn1, opts=dict(mask_input=in_mask, premasked=True, x_sink=sink))
+            out = conv_bn_act(out, self.conv2, self.bn2, opts=dict(mask_input=True, premasked=True))
+            o3 = dict(mask_input=True, premasked=getattr(self, 'out_premasked', False))
+            if self.downsample is None:
+                return conv_bn_act(out, self.conv3, self.bn3, z=x, opts=dict(o3, z_sink=sink))
+            ident = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False,
+                                opts=dict(mask_input=in_mask, x_sink=sink))
+            return conv_bn_act(out, self.conv3, self.bn3, z=ident, opts=o3)
         out = conv_bn_act(x, self.conv1, self.bn1)
         out = conv_bn_act(out, self.conv2, self.bn2)
         if self.downsample is None:
@@ -355,6 +379,16 @@ class ResNet(nn.Module):
                 layers.append(block(inplanes, planes, stride, dilations[i], down, style, with_cp,
                                     dcn if stage_with_dcn[i] else None, groups, base_width, base_channels))
                 inplanes = planes * block.expansion
+            # backward-fusion topology (Bottleneck._inner_fused): a block's input is the previous block's ReLU output
+            # (the first block of stage 1 reads the max-pool instead); the output of every block but the stage's last has
+            # the next block as its only consumer (stage outputs also feed the neck)
+            def all_own(b):
+                cs = [b.conv1, b.conv2, b.conv3] + ([] if b.downsample is None else [b.downsample[0]])
+                return all(_own_ok(c) for c in cs)
+            for j, blk in enumerate(layers):
+                blk.in_relu = not (i == 0 and j == 0)
+                blk.in_exclusive = j > 0
+                blk.out_premasked = j + 1 < nblocks and not with_cp and all_own(layers[j + 1])
             name = f'layer{i + 1}'
             self.add_module(name, nn.Sequential(*layers))
             self.res_layers.append(name)

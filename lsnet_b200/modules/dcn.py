@@ -14,6 +14,7 @@ from ..registry import CONV_LAYERS
 
 import os
 
+GX_SINK = os.environ.get('LSNET_GX_SINK', '1') == '1'
 PACKED_OFFSET_MASK = os.environ.get('LSNET_DCN_PACKED_OM', '1') == '1'
 
 
@@ -97,11 +98,12 @@ class ModulatedDeformConv(_DeformBase):
                                          self.dilation, self.groups, self.deformable_groups)
 
 
-def _offset_conv(m, x):
+def _offset_conv(m, x, gx_sink=None):
     """conv_offset through the tcgen05 implicit-GEMM kernel when it is a stride-1 'same' conv, else cuDNN."""
     k, s, p, d = m.kernel_size, m.stride, m.padding, m.dilation
     if s == (1, 1) and k[0] == k[1] and p[0] == p[1] and d[0] == d[1] and 2 * p[0] == d[0] * (k[0] - 1) and x.is_cuda:
-        return ops.conv2d_same(x, m.conv_offset.weight, m.conv_offset.bias, padding=p[0], dilation=d[0], out_fp32=True)
+        return ops.conv2d_same(x, m.conv_offset.weight, m.conv_offset.bias, padding=p[0], dilation=d[0], out_fp32=True,
+                               gx_sink=gx_sink)
     return m.conv_offset(x)
 
 
@@ -122,13 +124,20 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
         self.conv_offset.weight.data.zero_()
         self.conv_offset.bias.data.zero_()
 
-    def forward(self, x):
-        out = _offset_conv(self, x)
+    def forward(self, x, exclusive=False):
+        """``exclusive``: the caller guarantees that this module is the ONLY consumer of ``x`` in the autograd graph (a
+        tower layer fed by the previous layer).  Then the two internal consumers of x share a gradient sink: the sampling
+        op's backward runs first (conv_offset's output feeds it) and the conv_offset backward adds its input gradient into
+        that tensor inside its GEMM epilogue.  With other consumers autograd may already have summed the first gradient
+        into a new tensor when the second arrives, so the in-place sum would be lost -- hence the explicit promise."""
         n = self.deformable_groups * self.kernel_size[0] * self.kernel_size[1]
         if PACKED_OFFSET_MASK and x.is_cuda:
             # one op: the sampling kernels split offsets / mask logits and apply the sigmoid (and its derivative)
+            sink = {} if (GX_SINK and exclusive and x.requires_grad and x.dtype == torch.bfloat16) else None
+            out = _offset_conv(self, x, sink)
             return ops.modulated_deform_conv_packed(x, out[:, :3 * n], self.weight, self.bias, self.stride, self.padding,
-                                                    self.dilation, self.groups, self.deformable_groups)
+                                                    self.dilation, self.groups, self.deformable_groups, gx_sink=sink)
+        out = _offset_conv(self, x)
         # chunk(3) + cat(o1, o2) keeps the channel order (deform_conv.py:528-531): offsets = first 2n channels
         offset, mask = out[:, :2 * n], torch.sigmoid(out[:, 2 * n:3 * n])
         return ops.modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding,

@@ -62,8 +62,10 @@ class DCNConvModule(nn.Module):
         self.bn = nn.GroupNorm(num_groups, out_channels)
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, x):
-        return ops.group_norm_nhwc(self.conv(x), self.bn.num_groups, self.bn.weight, self.bn.bias, self.bn.eps, relu=True)
+    def forward(self, x, exclusive=False):
+        """``exclusive``: x has no other consumer (see ModulatedDeformConvPack.forward)."""
+        return ops.group_norm_nhwc(self.conv(x, exclusive=exclusive), self.bn.num_groups, self.bn.weight, self.bn.bias,
+                                   self.bn.eps, relu=True)
 
 
 class NormConvModule(nn.Module):
@@ -74,7 +76,7 @@ class NormConvModule(nn.Module):
         self.conv = B200Conv2d(cin, cout, 3, 1, 1, bias=False)
         self.gn = nn.GroupNorm(num_groups, cout)
 
-    def forward(self, x):
+    def forward(self, x, exclusive=False):
         return ops.group_norm_nhwc(self.conv(x), self.gn.num_groups, self.gn.weight, self.gn.bias, self.gn.eps, relu=True)
 
 
@@ -299,13 +301,13 @@ class LSHead(nn.Module):
         """lsnet_head.py:502-598 for one level: towers + init regression -> (cls_feat, {br: (feat, init_sp, dcn_off)})."""
         cls_feat = x if with_cls else None
         if with_cls:
-            for m in self.cls_convs:
-                cls_feat = m(cls_feat)
+            for i, m in enumerate(self.cls_convs):
+                cls_feat = m(cls_feat, exclusive=i > 0)      # layer i > 0 is the only reader of layer i-1's output
         out = {}
         for br in BRANCHES[self.task]:
             feat = x
-            for m in getattr(self, f'{br}_convs'):
-                feat = m(feat)
+            for i, m in enumerate(getattr(self, f'{br}_convs')):
+                feat = m(feat, exclusive=i > 0)
             hid = getattr(self, f'pts_{br}_init_conv')(feat, relu=True)
             o = getattr(self, f'pts_{br}_init_out')(hid, out_fp32=True)
             if HEAD_GLUE and o.is_cuda:
@@ -346,8 +348,8 @@ class LSHead(nn.Module):
             with torch.cuda.stream(s_cls):
                 for l in lv:
                     c = feats[l]
-                    for m in self.cls_convs:
-                        c = m(c)
+                    for i, m in enumerate(self.cls_convs):
+                        c = m(c, exclusive=i > 0)
                     cls_feats[l] = c
             with torch.cuda.stream(s_reg):
                 for l in lv:

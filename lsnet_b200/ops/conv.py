@@ -12,7 +12,11 @@ from . import gemm_ops as G
 class _ConvSame(Function):
 
     @staticmethod
-    def forward(ctx, x, weight, bias, pad, dil, relu, out_fp32):
+    def forward(ctx, x, weight, bias, pad, dil, relu, out_fp32, gx_sink=None):
+        # gx_sink: dict shared with ANOTHER consumer of x on the same stream whose backward runs first and leaves its input
+        # gradient there under 'dx' ([B,H,W,C] bf16): this op then adds its own input gradient into that tensor in the
+        # GEMM epilogue and returns none (the DCN + conv_offset pair: no separate gradient-sum kernel)
+        ctx.gx_sink = gx_sink
         co, ci, kh, kw = weight.shape
         x = G.as_nhwc(x, torch.bfloat16)
         if x.shape[1] % 8:
@@ -43,7 +47,14 @@ class _ConvSame(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             wt = G.cached_pack(weight, 'bwd', lambda t: G.pack_conv_weight(t, flip_transpose=True))
-            gx = G.conv2d_nhwc(gyp, wt, kh, kw, pad, dil, None, False, torch.bfloat16, n_valid=ci)
+            acc = ctx.gx_sink.pop('dx', None) if ctx.gx_sink is not None else None
+            B_, _, H_, W_ = gyp.shape
+            if acc is not None and acc.shape == (B_, H_, W_, wt.shape[0]) and acc.dtype == torch.bfloat16 \
+                    and acc.is_contiguous() and wt.shape[0] == ci:
+                taps = [(ky * dil - pad, kx * dil - pad, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+                conv2d_taps(gyp, wt, taps, H_, W_, out=acc, resid=acc.permute(0, 3, 1, 2))     # acc += dgrad, in place
+            else:
+                gx = G.conv2d_nhwc(gyp, wt, kh, kw, pad, dil, None, False, torch.bfloat16, n_valid=ci)
         if ctx.needs_input_grad[1]:
             direct = ctx.grad2d
             if direct is not None and tuple(direct.shape) != (gyp.shape[1], kh * kw * x.shape[1]):
@@ -55,13 +66,13 @@ class _ConvSame(Function):
                 gw = dw[:co, :, :ci].reshape(co, kh, kw, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if has_bias and ctx.needs_input_grad[2]:
             gb = colsum
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
-def conv2d_same(x, weight, bias=None, padding=1, dilation=1, relu=False, out_fp32=False):
+def conv2d_same(x, weight, bias=None, padding=1, dilation=1, relu=False, out_fp32=False, gx_sink=None):
     """nn.Conv2d(stride=1, padding=dilation*(k-1)/2) semantics on (B,C,H,W) tensors (any layout; converted to
     channels_last bf16).  Returns a (B,Cout,H,W) channels_last view."""
-    return _ConvSame.apply(x, weight, bias, padding, dilation, relu, out_fp32)
+    return _ConvSame.apply(x, weight, bias, padding, dilation, relu, out_fp32, gx_sink)
 
 
 def linear_nhwc(x, weight, bias=None, relu=False, out_fp32=False):
@@ -133,11 +144,25 @@ def dgrad_phases(kh, kw, stride, pad, dil):
 class _ConvPacked(Function):
     """y = relu?(conv(x; wb) + bias (+ z)) with wb / wt the two bf16 GEMM packs of the SAME weight ([O, taps*I] and
     [I, taps*O]); the gradient w.r.t. the weight is returned for wb as fp32 [O, taps*I] (the layout the weight-gradient
-    GEMM writes), wt gets none."""
+    GEMM writes), wt gets none.
+
+    Backward fusion flags (``opts``; all default off, every combination is exact):
+      mask_input  x is the output of a ReLU whose backward masks by (x > 0) anyway: the input-gradient GEMM applies that
+                  mask in its epilogue (the producer then only needs its bias column sums)
+      premasked   the incoming gradient is already masked by (y > 0) (its producers all set mask_input): no mask pass
+      x_sink      dict shared by the consumers of x that run on ONE stream: the first backward to run leaves its input
+                  gradient there, the others add theirs into that tensor inside the GEMM epilogue and return none
+      z_sink      the x_sink of the tensor passed as z: the identity-path gradient (returned to autograd as usual) is
+                  registered there so that the other consumers of that tensor accumulate into it"""
 
     @staticmethod
-    def forward(ctx, x, wb, wt, bias, z, kh, kw, stride, pad, dil, relu, holder):
+    def forward(ctx, x, wb, wt, bias, z, kh, kw, stride, pad, dil, relu, holder, opts):
         ctx.holder = holder
+        ctx.opts = dict(opts or {})
+        if x.dtype != torch.bfloat16 or (z is not None and z.dtype != torch.bfloat16):
+            # autograd would cast the returned gradient to the input's dtype (a copy): in-place sums would be lost
+            ctx.opts.pop('x_sink', None)
+            ctx.opts.pop('z_sink', None)
         x = G.as_nhwc(x, torch.bfloat16)
         B, C, H, W = x.shape
         O = wb.shape[0]
@@ -156,22 +181,35 @@ class _ConvPacked(Function):
     def backward(ctx, gy):
         x, wt, y = ctx.saved_tensors
         kh, kw, stride, pad, dil, relu, has_bias, has_z, O = ctx.cfg
+        opts = ctx.opts
         B, C, H, W = x.shape
         Ho, Wo = gy.shape[2:]
-        g, colsum = G.grad_prep(gy, y if relu else None, has_bias and ctx.needs_input_grad[3])
-        gx = gwb = None
+        want_bias = has_bias and ctx.needs_input_grad[3]
+        # premasked: the mask pass degenerates to the (read-only) column sums
+        g, colsum = G.grad_prep(gy, y if (relu and not opts.get('premasked')) else None, want_bias)
+        gx = gwb = gz = None
         if ctx.needs_input_grad[0]:
+            sink = opts.get('x_sink')
+            acc = sink.pop('dx', None) if sink is not None else None
+            if acc is not None and not (acc.shape == (B, H, W, C) and acc.dtype == torch.bfloat16 and acc.is_contiguous()):
+                sink['dx'] = acc
+                acc = None
             phases = dgrad_phases(kh, kw, stride, pad, dil)
             full = all(len(t) for _, _, t in phases)
-            buf = (torch.empty if full else torch.zeros)((B, H, W, C), device=x.device, dtype=torch.bfloat16)
+            buf = acc if acc is not None else (torch.empty if full else torch.zeros)((B, H, W, C), device=x.device,
+                                                                                     dtype=torch.bfloat16)
+            mask = x if opts.get('mask_input') else None
             for ph, pw, taps in phases:
                 if not taps:
                     continue
                 Hp, Wp = (H - ph + stride - 1) // stride, (W - pw + stride - 1) // stride
                 if Hp <= 0 or Wp <= 0:
                     continue
-                conv2d_taps(g, wt, taps, Hp, Wp, 1, 1, wt_taps=kh * kw, out=buf, out_map=(stride, stride, ph, pw, H, W))
-            gx = buf.permute(0, 3, 1, 2)
+                conv2d_taps(g, wt, taps, Hp, Wp, 1, 1, wt_taps=kh * kw, out=buf, out_map=(stride, stride, ph, pw, H, W),
+                            resid=None if acc is None else acc.permute(0, 3, 1, 2), mask=mask)
+            if sink is not None and acc is None:
+                sink['dx'] = buf           # later consumers of x accumulate into this tensor
+            gx = buf.permute(0, 3, 1, 2) if acc is None else None
         if ctx.needs_input_grad[1]:
             gwb = torch.zeros((O, kh * kw * C), device=x.device, dtype=torch.float32)
             _, _, _, _, ldy = G.nhwc_geom(g)
@@ -182,14 +220,20 @@ class _ConvPacked(Function):
         if gwb is not None and ctx.holder is not None:
             ctx.holder['gwb'] = gwb          # fp32, picked up by the fold's backward (see _BnFoldPacked)
             gwb = None
-        return gx, gwb, None, colsum, (g if has_z else None), None, None, None, None, None, None, None
+        if has_z and ctx.needs_input_grad[4]:
+            gz = g
+            zs = opts.get('z_sink')
+            gb = g.permute(0, 2, 3, 1)
+            if zs is not None and 'dx' not in zs and gb.is_contiguous() and g.dtype == torch.bfloat16:
+                zs['dx'] = gb               # the identity gradient: the other consumers of z's tensor add theirs into it
+        return gx, gwb, None, colsum, gz, None, None, None, None, None, None, None, None
 
 
 def conv2d_packed(x, wb, wt, bias=None, z=None, kernel=(1, 1), stride=1, padding=0, dilation=1, relu=False,
-                  wgrad_holder=None):
+                  wgrad_holder=None, opts=None):
     """``wgrad_holder``: dict that receives the fp32 weight gradient under 'gwb' instead of autograd (which would cast it
-    to the bf16 pack's dtype); the producer of the packs reads it in its own backward."""
-    return _ConvPacked.apply(x, wb, wt, bias, z, kernel[0], kernel[1], stride, padding, dilation, relu, wgrad_holder)
+    to the bf16 pack's dtype); the producer of the packs reads it in its own backward.  ``opts``: see _ConvPacked."""
+    return _ConvPacked.apply(x, wb, wt, bias, z, kernel[0], kernel[1], stride, padding, dilation, relu, wgrad_holder, opts)
 
 
 class _ConvStrided(Function):

@@ -263,7 +263,8 @@ class _DCN(Function):
 
     @staticmethod
     def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
-                out_slice=None, packed_om=False):
+                out_slice=None, packed_om=False, gx_sink=None):
+        ctx.gx_sink = gx_sink        # see ops/conv.py::_ConvSame: the conv_offset conv adds its input gradient into ours
         # packed_om: ``offset`` is the whole conv_offset output (B, 3*dg*taps, Ho, Wo) — offsets in the first 2/3 of the
         # channels, mask LOGITS behind them; ``mask`` is None and the kernels apply the sigmoid.
         co, cig, kh, kw = weight.shape
@@ -380,13 +381,17 @@ class _DCN(Function):
                                                 mask_logits=logits, packed_out=ctx.packed_om, groups=native)
             if gx is not None and gx.dtype != torch.bfloat16:
                 gx = gx.to(torch.bfloat16)
+            if gx is not None and ctx.gx_sink is not None:
+                base = gx.permute(0, 2, 3, 1)
+                if base.is_contiguous():
+                    ctx.gx_sink['dx'] = base
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         elif ctx.needs_input_grad[3]:
             gw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
-        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None, None
 
 
 def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
@@ -404,11 +409,11 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
 
 
 def modulated_deform_conv_packed(x, offset_mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                                 deformable_groups=1, out_fp32=False):
+                                 deformable_groups=1, out_fp32=False, gx_sink=None):
     """ModulatedDeformConvPack.forward after its conv_offset (deform_conv.py:528-533) as ONE op: ``offset_mask`` is the
     raw conv_offset output; chunk / cat / sigmoid and their backward happen inside the sampling kernels."""
     return _DCN.apply(x, offset_mask, None, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
-                      groups, deformable_groups, False, out_fp32, None, True)
+                      groups, deformable_groups, False, out_fp32, None, True, gx_sink)
 
 
 def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

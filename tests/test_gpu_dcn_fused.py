@@ -329,3 +329,55 @@ def test_grouped_dcn_native_vs_oracle(C, groups, stride):
         dcn_mod.grouped_native = saved
     assert _rel(out, out2) < 2e-3
     assert _rel(gg[3], gg2[3]) < 5e-3
+
+
+def test_dcn_pack_gradient_sink_matches_autograd_sum():
+    """ModulatedDeformConvPack: x feeds conv_offset AND the sampling op.  With the gradient sink the conv_offset backward
+    adds its input gradient into the sampling op's dX inside its GEMM epilogue (no separate sum); result must equal the
+    plain autograd sum of the two gradients up to one bf16 rounding of the partial sum."""
+    import torch
+    from lsnet_b200.modules import dcn as D
+    torch.manual_seed(3)
+    m = D.ModulatedDeformConvPack(256, 256, 3, 1, 1).cuda()
+    m.conv_offset.weight.data.normal_(0, 0.02)
+    m.conv_offset.bias.data.normal_(0, 0.1)
+    x0 = torch.randn(2, 256, 25, 42, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(2, 256, 25, 42, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for mode in (True, False):
+        D.GX_SINK = mode
+        try:
+            m.zero_grad()
+            x = x0.clone().requires_grad_(True)
+            m(x, exclusive=True).backward(gy)
+            torch.cuda.synchronize()
+            res[mode] = (x.grad.float().clone(), m.conv_offset.weight.grad.clone(), m.weight.grad.clone())
+        finally:
+            D.GX_SINK = True
+    scale = res[False][0].abs().max()
+    assert float((res[True][0] - res[False][0]).abs().max() / scale) < 1e-2
+    assert torch.allclose(res[True][1], res[False][1], rtol=1e-3, atol=1e-4 * float(res[False][1].abs().max()))
+    assert torch.allclose(res[True][2], res[False][2], rtol=1e-3, atol=1e-4 * float(res[False][2].abs().max()))
+
+
+def test_dcn_pack_default_is_safe_with_outside_consumers():
+    """Without the caller's ``exclusive`` promise the pack must not sum in place: x here also feeds an identity branch, so
+    autograd accumulates an outside gradient with the sampling op's dX before conv_offset's arrives."""
+    import torch
+    from lsnet_b200.modules import dcn as D
+    torch.manual_seed(5)
+    m = D.ModulatedDeformConvPack(64, 64, 3, 1, 1).cuda()
+    m.conv_offset.weight.data.normal_(0, 0.02)
+    x0 = torch.randn(2, 64, 13, 21, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(2, 64, 13, 21, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for mode in (True, False):
+        D.GX_SINK = mode
+        try:
+            x = x0.clone().requires_grad_(True)
+            (m(x) + x * 0.5).backward(gy)
+            torch.cuda.synchronize()
+            res[mode] = x.grad.float().clone()
+        finally:
+            D.GX_SINK = True
+    assert float((res[True] - res[False]).abs().max() / res[False].abs().max()) < 1e-2

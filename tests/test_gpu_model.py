@@ -53,23 +53,46 @@ def test_detector_vs_oracle_bbox():
         ref = torch.stack([x.detach() for x in ol[k]])
         assert torch.allclose(got, ref, rtol=1e-4, atol=1e-6), (k, got, ref)
     # ---- tier 2: whole network vs the fp32 oracle (bf16 tolerance) ----
-    sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k else v)
-           for k, v in sd.items()}
-    rl = O.detector_losses(sdp, d['img'], d['gt_bboxes'], d['gt_labels'], d['img_metas'], task='bbox',
-                           gt_extremes=d['gt_extremes'])
-    rtot, _ = O.parse_losses(rl)
-    rtot.backward()
-    tot, _ = model._parse_losses(losses)
-    tot.backward()
-    assert abs(float(tot) - float(rtot)) < 0.05 * abs(float(rtot)), (float(tot), float(rtot))
-    # gradient direction agreement on a few large parameters
-    for name in ['bbox_head.pts_cls_out.weight', 'bbox_head.cls_convs.0.conv.weight', 'neck.lateral_convs.0.conv.weight',
-                 'bbox_head.pts_bbox_refine_conv.weight', 'bbox_head.bbox_convs.2.conv.conv_offset.weight']:
-        g = dict(model.named_parameters())[name].grad.float().cpu().flatten()
-        r = sdp[name].grad.flatten()
-        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
-        print('COS', name, round(cos, 4), float(g.norm()), float(r.norm()))
-        assert cos > 0.95, (name, cos, float(g.norm()), float(r.norm()))
+    # Free-running: the fp32 oracle assigns on ITS OWN predictions.  At random initialisation every predicted box is a few
+    # pixels wide, so the ATSS IoU test is borderline for some candidates and bf16 noise in the features can flip an
+    # assignment; the cross-IOU gradient of such a tiny box is large, so ONE flipped positive rotates the gradient of
+    # every parameter the refine loss reaches (measured: cosine -0.75 on a tower conv_offset weight with one flip, 0.985
+    # without).  Gradients are therefore compared on the first batch on which both runs train on the SAME positives;
+    # the loss bound holds on every batch tried.
+    names = ['bbox_head.pts_cls_out.weight', 'bbox_head.cls_convs.0.conv.weight', 'neck.lateral_convs.0.conv.weight',
+             'bbox_head.pts_bbox_refine_conv.weight', 'bbox_head.bbox_convs.2.conv.conv_offset.weight']
+    compared = False
+    for seed in (101, 102, 103, 104, 105, 106):
+        if seed != 101:
+            d = synth.detector_batch('bbox', seed)
+            model.zero_grad(set_to_none=True)
+            feats = model.extract_feat(d['img'].cuda())
+            outs = model.bbox_head(feats)
+            losses, aux = model.bbox_head.loss(*outs, d['gt_bboxes'], d['gt_extremes'], None, None, d['gt_labels'],
+                                               d['img_metas'], return_aux=True)
+        sdp = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running_' not in k else v)
+               for k, v in sd.items()}
+        rl, raux = O.detector_losses(sdp, d['img'], d['gt_bboxes'], d['gt_labels'], d['img_metas'], task='bbox',
+                                     gt_extremes=d['gt_extremes'], return_aux=True)
+        rtot, _ = O.parse_losses(rl)
+        tot, _ = model._parse_losses(losses)
+        assert abs(float(tot) - float(rtot)) < 0.05 * abs(float(rtot)), (seed, float(tot), float(rtot))
+        flips = sum(int((aux[f'assign_{st}'][i].cpu().long() + 1 != raux['tg'][st][i]['assign']).sum())
+                    for st in ('init', 'refine') for i in range(len(d['gt_bboxes'])))
+        print('seed', seed, 'loss', float(tot), 'oracle', float(rtot), 'assignment flips', flips)
+        if flips:
+            continue
+        rtot.backward()
+        tot.backward()
+        for name in names:
+            g = dict(model.named_parameters())[name].grad.float().cpu().flatten()
+            r = sdp[name].grad.flatten()
+            cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+            print('COS', name, round(cos, 4), float(g.norm()), float(r.norm()))
+            assert cos > 0.95, (name, cos, float(g.norm()), float(r.norm()))
+        compared = True
+        break
+    assert compared, 'no batch without an assignment flip among 6 seeds'
 
 
 def test_train_steps_reduce_loss():

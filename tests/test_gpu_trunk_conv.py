@@ -205,3 +205,45 @@ def test_stem_conv_and_maxpool(B, H, W, nhwc, dtype):
     pooled = ops.maxpool3x3s2(y)
     refp = F.max_pool2d(y.float(), 3, 2, 1)
     assert pooled.shape == refp.shape and torch.equal(pooled.float(), refp)
+
+
+def test_backbone_backward_fusion_is_exact():
+    """The trunk's fused backward (ReLU masks and identity-path sums inside the input-gradient GEMM epilogues, shared
+    gradient sinks) against the plain per-op backward of the SAME kernels: identical math, so outputs are bit-equal and
+    gradients agree to bf16 rounding of the partial sums."""
+    import lsnet_b200 as L
+    from lsnet_b200.modules import backbone as bb
+    torch.manual_seed(1)
+    net = L.build_backbone(dict(type='ResNet', depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                                norm_cfg=dict(type='BN', requires_grad=True), norm_eval=True, style='pytorch'))
+    net.init_weights(None)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.1)
+    net.cuda().train()
+    x = torch.randn(2, 3, 200, 264, device='cuda')
+
+    def run(fuse):
+        old = bb.BWD_FUSE
+        bb.BWD_FUSE = fuse
+        try:
+            net.zero_grad()
+            outs = net(x)
+            loss = sum((o.float() ** 2).mean() for o in outs)
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            bb.BWD_FUSE = old
+        return [o.float().detach() for o in outs], {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    o1, g1 = run(True)
+    o0, g0 = run(False)
+    for a, b in zip(o1, o0):
+        assert torch.equal(a, b)
+    assert set(g1) == set(g0)
+    worst = 0.0
+    for k in g0:
+        n0 = float(g0[k].norm())
+        if n0 > 0:
+            worst = max(worst, float((g1[k] - g0[k]).norm()) / n0)
+    assert worst < 2e-2, worst

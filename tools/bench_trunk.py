@@ -12,14 +12,31 @@ dev = 'cuda'
 flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
 
-def timeit(fn, n=7):
-    ts = []
-    for _ in range(n + 2):
+def _queued(fn, n):
+    """GPU time of n back-to-back calls: a long spin kernel runs first so that the CPU enqueues everything (Python / ctypes
+    launch overhead of a call is ~50-100 us, more than most of these kernels take) before the first call starts."""
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(4e7))
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    a.record()
+    for _ in range(n):
         flush.zero_()
-        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    return sorted(ts[2:])[len(ts[2:]) // 2]
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+T_FLUSH = None
+
+
+def timeit(fn, n=10):
+    global T_FLUSH
+    if T_FLUSH is None:
+        _queued(lambda: None, n)
+        T_FLUSH = min(_queued(lambda: None, n) for _ in range(3))
+    fn()
+    return min(_queued(fn, n) for _ in range(3)) - T_FLUSH
 
 
 # (name, I, O, H, W, k, stride, count per step fwd, trainable)
@@ -35,6 +52,9 @@ SHAPES = [('l1 1x1 64>64', 64, 64, 200, 336, 1, 1, 1, False), ('l1 3x3 64>64', 6
           ('l4 1x1 1024>512 @50', 1024, 512, 50, 84, 1, 1, 1, True), ('l4 3x3s2 512', 512, 512, 50, 84, 3, 2, 1, True),
           ('l4 ds 1x1s2 1024>2048', 1024, 2048, 50, 84, 1, 2, 1, True), ('l4 1x1 512>2048', 512, 2048, 25, 42, 1, 1, 3, True),
           ('l4 1x1 2048>512', 2048, 512, 25, 42, 1, 1, 2, True), ('l4 3x3 512', 512, 512, 25, 42, 3, 1, 2, True)]
+only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None
+if only:
+    SHAPES = [s_ for s_ in SHAPES if s_[0] == only]
 rows = []
 tot = dict(own=0.0, lib=0.0)
 for name, I, O, H, W, k, s, cnt, train in SHAPES:
@@ -61,7 +81,7 @@ for name, I, O, H, W, k, s, cnt, train in SHAPES:
         y = conv2d_packed(xo, wbo, wt, None, None, (k, k), s, pad, 1, False, wgrad_holder=holder)
         # own: input gradient only / weight gradient only (autograd.grad on one input at a time)
         t_dg = timeit(lambda: torch.autograd.grad(y, xo, gy, retain_graph=True))
-        t_wg_both = timeit(lambda: torch.autograd.grad(y, (xo, wbo), gy, retain_graph=True, allow_unused=True))
+        t_wg_both = t_dg + timeit(lambda: torch.autograd.grad(y, wbo, gy, retain_graph=True, allow_unused=True))
         t_ldg = timeit(lambda: torch.ops.aten.convolution_backward(gy, x, wl, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [True, False, False]))
         t_lwg = timeit(lambda: torch.ops.aten.convolution_backward(gy, x, wl, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False]))
         r += [f'{t_dg:.3f}', f'{t_ldg:.3f}', f'{t_wg_both - t_dg:.3f}', f'{t_lwg:.3f}']
@@ -71,7 +91,7 @@ for name, I, O, H, W, k, s, cnt, train in SHAPES:
     r.append(str(cnt))
     rows.append(r)
     print(' | '.join(r), flush=True)
-out = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/trunk_layers.md'
+out = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith('--') else 'gpurun_out/trunk_layers.md'
 with open(out, 'w') as f:
     f.write('# ResNet-50 trunk convolutions, B=4 800x1344: own tcgen05 kernels vs cuDNN/cuBLAS (ms, CUDA events, L2 flushed)\n\n')
     f.write('| layer | GFLOP | own fwd | lib fwd | own dgrad | lib dgrad | own wgrad | lib wgrad | per step |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|\n')

@@ -1,0 +1,17 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_trunk_conv.py tests/test_gpu_kernels.py -q -x 2>&1 | tail -3
+timeout 900 python tools/bench_trunk.py gpurun_out/trunk_layers.md > gpurun_out/s17_trunk.log 2>&1; tail -28 gpurun_out/s17_trunk.log
+run() { name=$1; shift
+  env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/s17_bench_$name.json 2> gpurun_out/s17_bench_$name.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open('gpurun_out/s17_bench_$name.json').read().strip().splitlines()[-1])
+    print('$name', 'img/s', round(d['value'], 1), 'ms/step', round(d['ms_per_step'], 2), 'e2e img/s', round(d['e2e']['value'], 1), 'serial', round(d['roofline']['serialized_step_ms'], 2), 'launches', d['gpu_launches'])
+except Exception as e:
+    print('$name', 'FAILED', e); print(open('gpurun_out/s17_bench_$name.err').read()[-800:])
+PY
+}
+run own

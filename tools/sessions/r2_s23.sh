@@ -1,0 +1,20 @@
+#!/bin/bash
+cd /root/repo
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_model.py -x -q -k "detector_vs_oracle_bbox" -s 2>&1 | grep -v Warn | grep "COS\|Error\|error\|assert\|passed\|failed" | head -20
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6
+run() { name=$1; shift
+  env "$@" timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/s23_bench_$name.json 2> gpurun_out/s23_bench_$name.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open('gpurun_out/s23_bench_$name.json').read().strip().splitlines()[-1])
+    print('$name', 'img/s', round(d['value'], 1), 'ms/step', round(d['ms_per_step'], 2), 'e2e img/s', round(d['e2e']['value'], 1), 'serial', round(d['roofline']['serialized_step_ms'], 2), 'launches', d['gpu_launches'])
+except Exception as e:
+    print('$name', 'FAILED', e); print(open('gpurun_out/s23_bench_$name.err').read()[-800:])
+PY
+}
+run fused
+run nofuse LSNET_TRUNK_BWD_FUSE=0 LSNET_GX_SINK=0
+run fused2
+run nosink LSNET_GX_SINK=0

@@ -32,6 +32,8 @@ def cls(name):
     if 'lsn::' in short:
         short = short.split('lsn::')[-1]
         return re.sub(r'_kernel$', '', short)
+    if any(k in short for k in ('sgd_momentum', 'pred_reg_', 'add_softplus')):      # library kernels outside namespace lsn
+        return re.sub(r'_kernel$', '', short)
     if short.startswith('at::'):
         return 'torch elementwise / reductions'
     if 'nccl' in short.lower():
