@@ -102,8 +102,9 @@ int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, l
 
 /* ---- GroupNorm (+ residual add, + ReLU) over pixel-major bf16 maps: nn.GroupNorm(32, 256) sites of FPN / LSHead
  * (mmdet/models/necks/fpn.py:117-133; mmdet/models/dense_heads/lsnet_head.py:97-113, 700-708, 1843).
- * y = relu?(GN(x (+ x2))).  stats / ws_bstats: double [B, G, 3] workspaces (fp64 sums followed by an fp32 (mean, rstd) /
- * (s1, s2) table); stats is written by fwd and read by bwd.  (C/G) % 8 == 0. */
+ * y = relu?(GN(x (+ x2))).  stats / ws_bstats: workspaces of 3*B*G + 1 doubles (2*B*G fp64 sums, a ticket counter, then
+ * the fp32 (mean, rstd) / (s1, s2) table written by the last CTA of the statistics kernel); stats is written by fwd
+ * and read by bwd.  (C/G) % 8 == 0. */
 int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2, long long ldx2, int B, int HW, int C, int G,
                         const float* gamma, const float* beta, float eps, int relu, double* stats, void* y,
                         long long ldy, void* stream);

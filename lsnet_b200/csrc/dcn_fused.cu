@@ -185,7 +185,7 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
     const int r = q * 32 + lane;     // accumulator row = pixel of the patch handled by this thread
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t* stg = staging + (warp - F_EPI0) * (32 * 20);
+    const uint32_t stg_s = smem_u32(staging + (warp - F_EPI0) * (32 * 20));      // explicit ld/st.shared (not generic LD.E/ST.E)
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int tile, cb0, cb1;
       item_of(item, &tile, &cb0, &cb1);
@@ -235,9 +235,9 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
             // warp instruction instead of 32 rows x 16 bytes
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(stg + lane * 20 + j * 4) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              sts128(stg_s + (lane * 20 + j * 4) * 4,
+                     make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
             __syncwarp();
             const int seg = lane & 3;
 #pragma unroll
@@ -246,7 +246,7 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
               bool ok;
               const long long grow = row_of(q * 32 + rr, &ok);
               if (ok && c + seg * 8 < p.N) {
-                const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
+                const uint4 val = lds128(stg_s + (rr * 20 + seg * 4) * 4);
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + c + seg * 8) = val;
               }
             }

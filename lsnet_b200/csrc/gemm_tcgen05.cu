@@ -210,7 +210,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
-      uint32_t* stg = staging + (warp - 2) * (32 * 20);
+      // 32-bit shared-space address of this warp's staging rows (80-byte pitch): explicit ld/st.shared -- through a generic
+      // pointer these compile to LD.E / ST.E whose long-scoreboard latency sat on every store of the epilogue (ncu)
+      const uint32_t stg_s = smem_u32(staging + (warp - 2) * (32 * 20));
 #pragma unroll 1
       for (int c = col_begin; c < col_begin + Cfg::kColsPerWarp; c += 32) {
         const int col0 = n0 + c;
@@ -259,10 +261,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           // transpose: (row (lane>>2)+8i, 16-byte segment lane&3) -> this thread's row, segments 0..3
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * 20 + seg_l * 4) = rv[i];
+            sts128(stg_s + (((lane >> 2) + 8 * i) * 20 + seg_l * 4) * 4, rv[i]);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(stg + lane * 20 + j * 4);
+          for (int j = 0; j < 4; ++j) rv[j] = lds128(stg_s + (lane * 20 + j * 4) * 4);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -281,10 +283,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (p.mask) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(stg + ((lane >> 2) + 8 * i) * 20 + seg_l * 4) = mv[i];
+            sts128(stg_s + (((lane >> 2) + 8 * i) * 20 + seg_l * 4) * 4, mv[i]);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mv[j] = *reinterpret_cast<const uint4*>(stg + lane * 20 + j * 4);
+          for (int j = 0; j < 4; ++j) mv[j] = lds128(stg_s + (lane * 20 + j * 4) * 4);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -309,16 +311,16 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           // it with 8 rows x 64 contiguous bytes per warp instruction instead of 32 rows x 16 bytes
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * 20 + j * 4) =
-                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            sts128(stg_s + (lane * 20 + j * 4) * 4,
+                   make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
           __syncwarp();
           const int seg = lane & 3;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i;
             if (sok[i] && col0 + seg * 8 < p.N) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 20 + seg * 4);
+              const uint4 val = lds128(stg_s + (rr * 20 + seg * 4) * 4);
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + srow[i] * p.ldc + col0 + seg * 8) = val;
             }
           }

@@ -37,7 +37,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 // grid (ceil(HW / GN_PIX_PER_CTA), B).  stats[b][g] = {sum, sumsq} (double, pre-zeroed)
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2, const GnArgs a,
-                double* __restrict__ stats) {
+                double* __restrict__ stats, unsigned* __restrict__ ticket, float2* __restrict__ mr, double n_elem) {
   extern __shared__ float sm[];   // [vecs_per_pixel][2] partial per vector column
   const int vpp = a.C / 8;        // 16-byte vectors per pixel
   const int cpg8 = (a.C / a.G) / 8;
@@ -96,23 +96,24 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     atomicAdd(&stats[(static_cast<long long>(b) * a.G + g) * 2], static_cast<double>(gs));
     atomicAdd(&stats[(static_cast<long long>(b) * a.G + g) * 2 + 1], static_cast<double>(gss));
   }
+  // The LAST CTA to finish turns the fp64 sums into the fp32 (mean, rstd) table the streaming kernels read (a separate
+  // finalize launch sat on the critical chain of every GroupNorm: 96 two-microsecond kernels per step).
+  __shared__ bool last_cta;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (last_cta) {
+    __threadfence();
+    for (int i = threadIdx.x; i < a.B * a.G; i += GN_THREADS) {
+      const double m = __ldcg(&stats[2 * i]) / n_elem;
+      double var = __ldcg(&stats[2 * i + 1]) / n_elem - m * m;
+      var = var < 0.0 ? 0.0 : var;
+      mr[i] = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(a.eps))));
+    }
+  }
 }
 
-// (sum, sumsq) in fp64 -> (mean, rstd) in fp32, once per (sample, group); the streaming kernels then read two floats
-__global__ void gn_finalize_kernel(const double* __restrict__ stats, int BG, double n, float eps,
-                                   float2* __restrict__ mr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BG) return;
-  const double m = stats[2 * i] / n;
-  double var = stats[2 * i + 1] / n - m * m;
-  var = var < 0.0 ? 0.0 : var;
-  mr[i] = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
-}
-__global__ void gn_finalize_bwd_kernel(const double* __restrict__ bstats, int BG, float2* __restrict__ s12) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BG) return;
-  s12[i] = make_float2(static_cast<float>(bstats[2 * i]), static_cast<float>(bstats[2 * i + 1]));
-}
 __device__ __forceinline__ void mean_rstd(const float2* mr, int b, int g, const GnArgs& a, float* mean, float* rstd) {
   const float2 v = __ldg(mr + static_cast<long long>(b) * a.G + g);
   *mean = v.x;
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2,
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
                     const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    double* __restrict__ bstats, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    double* __restrict__ bstats, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    unsigned* __restrict__ ticket, float2* __restrict__ s12) {
   extern __shared__ float sm[];   // per channel: dgamma, dbeta [2*C]; per vector column: s1, s2 [2*vpp]
   const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
   float* sm_dg = sm;
@@ -275,6 +277,17 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
     atomicAdd(&bstats[(static_cast<long long>(b) * a.G + g) * 2], static_cast<double>(t1));
     atomicAdd(&bstats[(static_cast<long long>(b) * a.G + g) * 2 + 1], static_cast<double>(t2));
   }
+  // last CTA: fp64 sums -> fp32 (s1, s2) table (see gn_stats_kernel)
+  __shared__ bool last_cta;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (last_cta) {
+    __threadfence();
+    for (int i = threadIdx.x; i < a.B * a.G; i += GN_THREADS)
+      s12[i] = make_float2(static_cast<float>(__ldcg(&bstats[2 * i])), static_cast<float>(__ldcg(&bstats[2 * i + 1])));
+  }
 }
 
 // Backward pass 2: dx = rstd * (dy'*gamma - (s1 + xhat*s2)/n)
@@ -347,14 +360,14 @@ extern "C" int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2,
   if (int rc = gn_check("lsnet_groupnorm_fwd", C, G, ldx, ldy)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GnArgs a{B, HW, C, G, ldx, ldx2, ldy, eps, relu};
-  cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * G, st);
+  // workspace layout (3*B*G + 1 doubles): [2*B*G fp64 sums][ticket counter][B*G float2 (mean, rstd)]
+  cudaMemsetAsync(stats, 0, sizeof(double) * (2 * B * G + 1), st);
   dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
+  float2* mr = reinterpret_cast<float2*>(stats + 2 * B * G + 1);
   gn_stats_kernel<<<grid, GN_THREADS, sizeof(float) * 2 * (C / 8), st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats);
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, stats,
+      reinterpret_cast<unsigned*>(stats + 2 * B * G), mr, static_cast<double>(HW) * (C / G));
   if (int rc = check_launch("gn_stats")) return rc;
-  float2* mr = reinterpret_cast<float2*>(stats + 2 * B * G);     // (mean, rstd) table behind the fp64 sums
-  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(stats, B * G, static_cast<double>(HW) * (C / G), eps, mr);
-  if (int rc = check_launch("gn_finalize")) return rc;
   gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, mr, gamma, beta,
       static_cast<__nv_bfloat16*>(y));
@@ -370,20 +383,19 @@ static int groupnorm_bwd_impl(const void* x, long long ldx, const void* x2, long
   if (lddy % 8) return set_error("lsnet_groupnorm_bwd: dy pitch must be a multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GnArgs a{B, HW, C, G, ldx, ldx2, 0, eps, relu};
-  cudaMemsetAsync(ws_bstats, 0, sizeof(double) * 2 * B * G, st);
+  cudaMemsetAsync(ws_bstats, 0, sizeof(double) * (2 * B * G + 1), st);
   if (!accumulate) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
   }
   dim3 grid((HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA, B);
-  const float2* mr = reinterpret_cast<const float2*>(stats + 2 * B * G);
+  const float2* mr = reinterpret_cast<const float2*>(stats + 2 * B * G + 1);
+  float2* s12 = reinterpret_cast<float2*>(ws_bstats + 2 * B * G + 1);
   gn_bwd_stats_kernel<<<grid, GN_THREADS, sizeof(float) * (2 * C + 2 * (C / 8)), st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
-      static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, gamma, beta, ws_bstats, dgamma, dbeta);
+      static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, gamma, beta, ws_bstats, dgamma, dbeta,
+      reinterpret_cast<unsigned*>(ws_bstats + 2 * B * G), s12);
   if (int rc = check_launch("gn_bwd_stats")) return rc;
-  float2* s12 = reinterpret_cast<float2*>(ws_bstats + 2 * B * G);
-  gn_finalize_bwd_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(ws_bstats, B * G, s12);
-  if (int rc = check_launch("gn_finalize_bwd")) return rc;
   gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, s12, gamma, beta, static_cast<__nv_bfloat16*>(dx),

@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, 'liblsnet_sm100.so')
+_LIB_PATH = os.environ.get('LSNET_LIB_PATH') or os.path.join(_HERE, 'liblsnet_sm100.so')     # override: A/B builds
 _lib = None
 _checked_device = False
 

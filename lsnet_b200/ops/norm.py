@@ -18,7 +18,7 @@ class _GroupNorm(Function):
             x2 = G.as_nhwc(x2, torch.bfloat16)
             ldx2 = G.nhwc_geom(x2)[4]
         w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
-        stats = torch.empty((B, num_groups, 3), device=x.device, dtype=torch.float64)
+        stats = torch.empty(B * num_groups * 3 + 1, device=x.device, dtype=torch.float64)     # sums | ticket | (mean, rstd)
         y = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
         L.call('lsnet_groupnorm_fwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.c_int(B), L.c_int(H * W),
                L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats),
@@ -36,7 +36,7 @@ class _GroupNorm(Function):
         ldx2 = G.nhwc_geom(x2)[4] if x2 is not None else 0
         gy = G.as_nhwc(gy, torch.bfloat16)
         lddy = G.nhwc_geom(gy)[4]
-        bstats = torch.empty((B, num_groups, 3), device=x.device, dtype=torch.float64)
+        bstats = torch.empty(B * num_groups * 3 + 1, device=x.device, dtype=torch.float64)
         dx = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
         # affine gradients: added straight into the parameters' gradient memory when the trainer exposes it
         tg, tb = G.direct_vec(ctx.affine[0]), G.direct_vec(ctx.affine[1])

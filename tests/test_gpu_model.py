@@ -112,27 +112,51 @@ def test_train_steps_reduce_loss():
 
 
 def test_graph_trainer_matches_eager_trainer():
-    """The CUDA-graph step (flat buffers, captured fwd+bwd) must reproduce the eager step over 3 iterations from
-    identical initial weights.  Tolerance 6 %: at random initialisation every predicted box is a few pixels wide, so the
-    ATSS IoU threshold test is borderline for many candidates and last-bit differences (fp64 atomics order in the
-    GroupNorm statistics, bf16 red order in the DCN scatter) flip a few assignments between two runs of the SAME code;
-    the steps that do not flip agree to ~1e-3."""
+    """The CUDA-graph step (flat tap-major buffers, captured fwd+bwd with kernels that accumulate straight into the flat
+    gradient, fused clip + SGD) must reproduce the eager step (autograd accumulation, torch clip + SGD) from identical
+    weights on the same batch:
+      * the loss of the step (forward parity)                                     <= 1e-3 relative
+      * every parameter gradient, as ONE vector                                   <= 3 % relative L2, per tensor <= 12 %
+      * the parameter update of the optimizer step, as ONE vector                  <= 3 % relative L2
+    The bounds are the run-to-run noise of the SAME code (bf16 red order in the DCN scatter, fp32 atomics of the split-K
+    weight gradients: two replays of one graph differ by up to 11 % on the smallest tensors).  Losses of LATER steps are not
+    compared: from random initialisation one ATSS assignment that flips on such noise moves the next loss by several
+    percent in either trainer (measured: step 2 4.35 vs 4.55 with identical step-1 gradients)."""
     from lsnet_b200.data import MODEL_CFG, synthetic_batch, to_device
     from lsnet_b200.train import GraphTrainer, Trainer
-    batches = [synthetic_batch(s, batch=2, img_hw=(384, 512)) for s in range(3)]
+    b = synthetic_batch(0, batch=2, img_hw=(384, 512))
     torch.manual_seed(0)
     eager = Trainer(MODEL_CFG['bbox_r50'])
     sd = {k: v.clone() for k, v in eager.core.state_dict().items()}
     torch.manual_seed(0)
-    graph = GraphTrainer(MODEL_CFG['bbox_r50'], batches[0])
+    graph = GraphTrainer(MODEL_CFG['bbox_r50'], b)
     graph.core.load_state_dict(sd)
-    l_e, l_g = [], []
-    for b in batches:
-        eager.iter = graph.iter = 1000
-        l_e.append(float(eager.step(to_device(b, 'cuda'))[0]))
-        l_g.append(float(graph.step(b)[0]))
-    for a, c in zip(l_e, l_g):
-        assert abs(a - c) < 6e-2 * abs(a), (l_e, l_g)
+    names = [k for k, p in eager.core.named_parameters() if p.requires_grad]
+    before = {k: p.detach().float().clone() for k, p in eager.core.named_parameters() if p.requires_grad}
+    eager.iter = graph.iter = 1000            # past warm-up: full learning rate
+    le = float(eager.step(to_device(b, 'cuda'))[0])
+    ge = {k: p.grad.detach().float().clone() for k, p in eager.core.named_parameters() if p.requires_grad}
+    lg = float(graph.step(b)[0])
+    torch.cuda.synchronize()
+    assert abs(le - lg) < 1e-3 * abs(le), (le, lg)
+    # gradients: the graph's flat gradient buffer still holds this step's (averaged, unclipped) gradients
+    gg = {k: p.grad.detach().float().clone() for k, p in graph.core.named_parameters() if p.requires_grad}
+    # (torch's clip_grad_norm_ has already scaled the eager gradients in place, the fused SGD kernel applies the clip
+    # coefficient without touching the buffer: compare directions, the update below compares magnitudes)
+    ne = sum(float(ge[k].pow(2).sum()) for k in names) ** 0.5
+    ng = sum(float(gg[k].pow(2).sum()) for k in names) ** 0.5
+    num = sum(float((ge[k] / ne - gg[k] / ng).pow(2).sum()) for k in names)
+    assert num ** 0.5 < 3e-2, num ** 0.5
+    for k in names:
+        n = float(ge[k].norm()) / ne
+        if n > 1e-3:
+            assert float((ge[k] / ne - gg[k] / ng).norm()) / n < 0.12, k
+    # parameter update of the optimizer step
+    pe = dict(eager.core.named_parameters())
+    pg = dict(graph.core.named_parameters())
+    num = sum(float(((pe[k].detach().float() - before[k]) - (pg[k].detach().float() - before[k])).pow(2).sum()) for k in names)
+    den = sum(float((pe[k].detach().float() - before[k]).pow(2).sum()) for k in names)
+    assert den > 0 and (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
 
 
 def test_backbone_bn_fold_matches_unfused():
