@@ -184,6 +184,14 @@ int lsnet_stem_conv7x7s2_bf16(const void* x, int x_bf16, long long sb, long long
 /* y[B, (H-1)/2+1, (W-1)/2+1, C] = 3x3 / stride 2 / pad 1 max-pool of x NHWC bf16 (C % 8 == 0). */
 int lsnet_maxpool3x3s2_nhwc_bf16(const void* x, int B, int H, int W, int C, void* y, void* stream);
 
+/* FPN top-down pathway (mmdet/models/necks/fpn.py:180-192): out = fine + nearest-upsample(coarse) to fine's size
+ * (PyTorch 'nearest': source index min(floor(dst * in/out), in-1)); _bwd: gc = sum of g over the fine pixels of every
+ * coarse cell (the gradient w.r.t. `fine` is g itself).  Pixel-major bf16, C % 8 == 0. */
+int lsnet_upsample_add_nhwc_bf16(const void* fine, long long ldf, const void* coarse, long long ldc, int B, int Hf, int Wf,
+                                 int Hc, int Wc, int C, void* out, long long ldo, void* stream);
+int lsnet_upsample_add_bwd_nhwc_bf16(const void* g, long long ldg, int B, int Hf, int Wf, int Hc, int Wc, int C, void* gc,
+                                     long long ldgc, void* stream);
+
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel

@@ -542,3 +542,108 @@ extern "C" int lsnet_add_softplus(const float* t, long long ldt, const float* s,
   else add_softplus_kernel<false><<<ew_grid(P * C), 256, 0, st>>>(t, ldt, s, lds, nullptr, 0, P, C, out, ldout);
   return check_launch("add_softplus");
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// FPN top-down pathway (mmdet/models/necks/fpn.py:180-192): fine += F.interpolate(coarse, size=fine.shape, mode='nearest').
+// Pixel-major bf16 maps, 8 channels (16 bytes) per thread.  Source index of PyTorch's nearest mode:
+// min(floor(dst * (in / out)), in - 1) with the scale in fp32.  The adjoint sums the fine pixels of every coarse cell.
+// ---------------------------------------------------------------------------------------------------------------
+namespace lsn {
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+  const int s = static_cast<int>(floorf(static_cast<float>(dst) * scale));
+  return s < in_size - 1 ? s : in_size - 1;
+}
+__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {        // fp32 add, one rounding (what torch's bf16 add does)
+    const float2 x = __bfloat1622float2(pa[i]), y = __bfloat1622float2(pb[i]);
+    pr[i] = __floats2bfloat162_rn(x.x + y.x, x.y + y.y);
+  }
+  return r;
+}
+
+__global__ void upsample_add_kernel(const __nv_bfloat16* __restrict__ fine, long long ldf,
+                                    const __nv_bfloat16* __restrict__ coarse, long long ldc, int B, int Hf, int Wf, int Hc,
+                                    int Wc, int C, __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int vpp = C / 8;
+  const long long n = static_cast<long long>(B) * Hf * Wf * vpp;
+  const float sh = static_cast<float>(Hc) / static_cast<float>(Hf), sw = static_cast<float>(Wc) / static_cast<float>(Wf);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpp);
+    long long p = i / vpp;
+    const int w = static_cast<int>(p % Wf); p /= Wf;
+    const int h = static_cast<int>(p % Hf);
+    const int b = static_cast<int>(p / Hf);
+    const long long pf = (static_cast<long long>(b) * Hf + h) * Wf + w;
+    const long long pc = (static_cast<long long>(b) * Hc + nearest_src(h, sh, Hc)) * Wc + nearest_src(w, sw, Wc);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(fine + pf * ldf) + v);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(coarse + pc * ldc) + v);
+    reinterpret_cast<uint4*>(out + pf * ldo)[v] = add_bf16x8(a, c);
+  }
+}
+
+// gc[b, s_h, s_w, :] = sum of g over the fine pixels whose nearest source is (s_h, s_w)   (fp32 accumulation)
+__global__ void upsample_add_bwd_kernel(const __nv_bfloat16* __restrict__ g, long long ldg, int B, int Hf, int Wf, int Hc,
+                                        int Wc, int C, __nv_bfloat16* __restrict__ gc, long long ldgc) {
+  const int vpp = C / 8;
+  const long long n = static_cast<long long>(B) * Hc * Wc * vpp;
+  const float sh = static_cast<float>(Hc) / static_cast<float>(Hf), sw = static_cast<float>(Wc) / static_cast<float>(Wf);
+  const int rh = Hf / Hc + 2, rw = Wf / Wc + 2;      // a cell's fine pixels lie within this many rows / columns
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpp);
+    long long p = i / vpp;
+    const int cw = static_cast<int>(p % Wc); p /= Wc;
+    const int ch = static_cast<int>(p % Hc);
+    const int b = static_cast<int>(p / Hc);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int h0 = max(0, static_cast<int>(static_cast<float>(ch) / sh) - 1), w0 = max(0, static_cast<int>(static_cast<float>(cw) / sw) - 1);
+    for (int h = h0; h < min(Hf, h0 + rh + 2); ++h) {
+      if (nearest_src(h, sh, Hc) != ch) continue;
+      for (int w = w0; w < min(Wf, w0 + rw + 2); ++w) {
+        if (nearest_src(w, sw, Wc) != cw) continue;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(g + ((static_cast<long long>(b) * Hf + h) * Wf + w) * ldg) + v);
+        const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(e[k]);
+          acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(gc + ((static_cast<long long>(b) * Hc + ch) * Wc + cw) * ldgc)[v] =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                   pack_bf16x2(acc[6], acc[7]));
+  }
+}
+}  // namespace lsn
+
+extern "C" int lsnet_upsample_add_nhwc_bf16(const void* fine, long long ldf, const void* coarse, long long ldc, int B, int Hf,
+                                            int Wf, int Hc, int Wc, int C, void* out, long long ldo, void* stream) {
+  if (B <= 0 || Hf <= 0 || Wf <= 0) return 0;
+  if ((C % 8) || (ldf % 8) || (ldc % 8) || (ldo % 8) || Hc <= 0 || Wc <= 0)
+    return lsn::set_error("lsnet_upsample_add_nhwc_bf16: C %% 8 == 0 and 16-byte aligned pitches required");
+  const long long n = static_cast<long long>(B) * Hf * Wf * (C / 8);
+  const int grid = static_cast<int>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  lsn::upsample_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(fine), ldf, static_cast<const __nv_bfloat16*>(coarse), ldc, B, Hf, Wf, Hc, Wc, C,
+      static_cast<__nv_bfloat16*>(out), ldo);
+  return lsn::check_launch("upsample_add");
+}
+
+extern "C" int lsnet_upsample_add_bwd_nhwc_bf16(const void* g, long long ldg, int B, int Hf, int Wf, int Hc, int Wc, int C,
+                                                void* gc, long long ldgc, void* stream) {
+  if (B <= 0 || Hc <= 0 || Wc <= 0) return 0;
+  if ((C % 8) || (ldg % 8) || (ldgc % 8)) return lsn::set_error("lsnet_upsample_add_bwd_nhwc_bf16: alignment");
+  const long long n = static_cast<long long>(B) * Hc * Wc * (C / 8);
+  const int grid = static_cast<int>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  lsn::upsample_add_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(g), ldg, B, Hf, Wf, Hc, Wc, C, static_cast<__nv_bfloat16*>(gc), ldgc);
+  return lsn::check_launch("upsample_add_bwd");
+}

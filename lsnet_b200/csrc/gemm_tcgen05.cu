@@ -50,24 +50,29 @@ struct GemmArgs {
   int blockdiag;
 };
 
-template <int BN>
+// OCC = CTAs per SM.  OCC = 2 (BN <= 128: 2 x 2*BN TMEM columns, <= 113 KB of shared memory each, <= 102 registers per thread)
+// is for launches below the FLOP/byte ridge: their tiles have 1-4 K steps, so a CTA is mostly its epilogue -- a serial
+// latency chain per warp (ncu: 16 % warps active, 28 % issue slots with one CTA of 10 warps per SM) -- and a second
+// resident CTA hides it.
+template <int BN, int OCC = 1>
 struct KCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = OCC == 1 ? ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) : (BN == 128 ? 2 : (BN == 64 ? 3 : 4));
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kStagingBytes = 8 * 32 * 80;   // per epilogue warp: 32 rows x (64 B + 16 B pad)
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kEpiWarps = BN >= 64 ? 8 : 4;        // column halves only pay off from 64 columns up
   static constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
+  static_assert(OCC == 1 || (kSmemBytes <= 113 * 1024 && OCC * kTmemCols <= 512), "two CTAs per SM must fit");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmArgs p) {
-  using Cfg = KCfg<BN>;
+  using Cfg = KCfg<BN, OCC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -647,31 +652,38 @@ void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
   }
 }
 
-template <int BN>
-static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
-  using Cfg = KCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kmajor_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_kmajor<%d>): %s", BN, cudaGetErrorString(e));
-    attr_done = true;
-  }
-  int tiles = a.m_tiles * a.n_tiles;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  // roofline class of this launch: algorithmic FLOPs vs algorithmic bytes (input read once, weights, output, epilogue
-  // operands) against the ridge of the machine
+// FLOPs / algorithmic bytes (input read once, weights, output, epilogue operands) of a launch against the ridge of the
+// machine (measured 1346.8 TFLOP/s / 6.54 TB/s ~ 200 FLOP/B)
+static bool gemm_hbm_bound(const GemmArgs& a, double* flops_out, double* bytes_out) {
   const double flops = 2.0 * a.M * a.N * a.num_k_iters * BK;
   const double k_in = a.conv ? static_cast<double>(a.cblks) * BK * ((a.num_k_iters > a.cblks) ? a.ish * a.isw : 1)
                              : static_cast<double>(a.num_k_iters) * BK;
   const double bytes = 2.0 * a.M * k_in + 2.0 * a.N * a.num_k_iters * BK + static_cast<double>(a.M) * a.N * (a.out_fp32 ? 4 : 2) +
                        (a.resid ? 2.0 * a.M * a.N : 0.0) + (a.mask ? 2.0 * a.M * a.N : 0.0);
-  const bool hbm_bound = flops < 200.0 * bytes;
+  if (flops_out) *flops_out = flops;
+  if (bytes_out) *bytes_out = bytes;
+  return flops < 200.0 * bytes;
+}
+
+template <int BN, int OCC>
+static int launch_kmajor(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = KCfg<BN, OCC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kmajor_kernel<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm_kmajor<%d,%d>): %s", BN, OCC, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int tiles = a.m_tiles * a.n_tiles;
+  int grid = tiles < OCC * num_sms() ? tiles : OCC * num_sms();
+  double flops, bytes;
+  const bool hbm_bound = gemm_hbm_bound(a, &flops, &bytes);
   const int th = timing_begin(hbm_bound ? TC_GEMM_HBM : TC_GEMM, hbm_bound ? bytes : flops, st);
-  gemm_kmajor_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  gemm_kmajor_kernel<BN, OCC><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
   timing_end(th, st);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("gemm_kmajor<%d> launch: %s", BN, cudaGetErrorString(e));
+  if (e != cudaSuccess) return set_error("gemm_kmajor<%d,%d> launch: %s", BN, OCC, cudaGetErrorString(e));
   count_launch();
   return 0;
 }
@@ -689,7 +701,9 @@ static int dispatch_kmajor(const CUtensorMap& tmA, const void* Bw, int N, int K,
   if (adapt < 0) { const char* e = getenv("LSNET_GEMM_ADAPT_BN"); adapt = e ? atoi(e) : 1; }
   // launches that do not fill one round keep the wide tile: in the training step they run beside other streams' kernels,
   // and more, narrower CTAs only take SMs away from those (measured in-step: 22.9 ms with, 22.5 ms without)
-  if (adapt && static_cast<long long>(a.m_tiles) * ((N + bn_max - 1) / bn_max) > num_sms()) {
+  // (launches below the FLOP/byte ridge keep the wide tile too -- it reads the A operand once; LSNET_GEMM_ADAPT_BN=2 adapts them as well)
+  if (adapt && static_cast<long long>(a.m_tiles) * ((N + bn_max - 1) / bn_max) > num_sms() &&
+      (adapt == 2 || !gemm_hbm_bound(a, nullptr, nullptr))) {
     const int sms = num_sms();
     long long best = -1;
     for (int bn = bn_max; bn >= 32; bn /= 2) {
@@ -698,14 +712,23 @@ static int dispatch_kmajor(const CUtensorMap& tmA, const void* Bw, int N, int K,
       if (best < 0 || cost < best) { best = cost; BN = bn; }
     }
   }
+  // launches below the ridge with enough tiles for two CTAs per SM: 128- (or 64-) column tiles, two CTAs per SM
+  static int occ2 = -1;
+  if (occ2 < 0) { const char* e = getenv("LSNET_GEMM_OCC2"); occ2 = e ? atoi(e) : 0; }   // measured r02: l1 64->256 0.096 vs 0.063 ms, whole step 23.2 vs 22.35 ms -> opt-in
+  int OCC = 1;
+  if (occ2 && N >= 64 && gemm_hbm_bound(a, nullptr, nullptr)) {
+    const int bn2 = N > 64 ? 128 : 64;
+    if (static_cast<long long>(a.m_tiles) * ((N + bn2 - 1) / bn2) >= 2LL * num_sms()) { BN = bn2; OCC = 2; }
+  }
   a.n_tiles = (N + BN - 1) / BN;
   CUtensorMap tmB;
   if (int rc = make_map_2d(&tmB, Bw, N, K, ldb, 64, BN)) return rc;
+  if (OCC == 2) return BN == 128 ? launch_kmajor<128, 2>(tmA, tmB, a, st) : launch_kmajor<64, 2>(tmA, tmB, a, st);
   switch (BN) {
-    case 256: return launch_kmajor<256>(tmA, tmB, a, st);
-    case 128: return launch_kmajor<128>(tmA, tmB, a, st);
-    case 64: return launch_kmajor<64>(tmA, tmB, a, st);
-    default: return launch_kmajor<32>(tmA, tmB, a, st);
+    case 256: return launch_kmajor<256, 1>(tmA, tmB, a, st);
+    case 128: return launch_kmajor<128, 1>(tmA, tmB, a, st);
+    case 64: return launch_kmajor<64, 1>(tmA, tmB, a, st);
+    default: return launch_kmajor<32, 1>(tmA, tmB, a, st);
   }
 }
 
@@ -758,7 +781,7 @@ extern "C" int lsnet_gemm_blockdiag_bf16(const void* A, long long lda, const voi
   GemmArgs a{};
   a.M = M; a.N = N; a.num_k_iters = 1; a.m_tiles = (M + BM - 1) / BM; a.n_tiles = N / 64;
   a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = 0; a.relu = 0; a.bias = nullptr; a.blockdiag = cblks;
-  return launch_kmajor<64>(tmA, tmB, a, static_cast<cudaStream_t>(stream));
+  return launch_kmajor<64, 1>(tmA, tmB, a, static_cast<cudaStream_t>(stream));
 }
 
 // The generalised implicit-GEMM correlation behind every convolution entry point:

@@ -103,6 +103,9 @@ class FPN(nn.Module):
         for i in range(n - 1, 0, -1):
             if 'scale_factor' in self.upsample_cfg:
                 lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], **self.upsample_cfg)
+            elif lat[i].is_cuda and self.upsample_cfg.get('mode', 'nearest') == 'nearest' and lat[i].shape[1] % 8 == 0 \
+                    and len(self.upsample_cfg) == 1:
+                lat[i - 1] = ops.upsample_add(lat[i - 1], lat[i])       # one kernel each way instead of upsample + add
             else:
                 lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], **self.upsample_cfg)
         outs = [self.fpn_convs[i](lat[i]) for i in range(n)]

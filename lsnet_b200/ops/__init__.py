@@ -7,6 +7,6 @@ from .loss import (cross_iou_loss_rows, cross_iou_level_loss, sigmoid_focal_loss
                    directional_targets)
 from .assign import (Pyramid, centroid_assign, atss_assign, assign_targets, pred_boxes)  # noqa: F401
 from .norm import group_norm_nhwc  # noqa: F401
-from .headglue import pred_reg, pred_reg_table, add_softplus  # noqa: F401
+from .headglue import pred_reg, pred_reg_table, add_softplus, upsample_add  # noqa: F401
 from .nms import nms, batched_nms, multiclass_nms_lsvr  # noqa: F401
 from .stem import stem_conv, maxpool3x3s2, pack_stem_weight  # noqa: F401

@@ -108,3 +108,38 @@ class _AddSoftplus(Function):
 def add_softplus(t, s_detached):
     """softplus(t + s) with no gradient into s (refine = softplus(raw + init.detach()))."""
     return _AddSoftplus.apply(t, s_detached)
+
+
+class _UpsampleAdd(torch.autograd.Function):
+    """fine + F.interpolate(coarse, size=fine.shape[2:], mode='nearest') in ONE kernel each way (FPN top-down pathway,
+    mmdet/models/necks/fpn.py:180-192): lsnet_upsample_add_nhwc_bf16 / _bwd."""
+
+    @staticmethod
+    def forward(ctx, fine, coarse):
+        from . import gemm_ops as G
+        fine, coarse = G.as_nhwc(fine, torch.bfloat16), G.as_nhwc(coarse, torch.bfloat16)
+        B, Hf, Wf, C, ldf = G.nhwc_geom(fine)
+        _, Hc, Wc, Cc, ldc = G.nhwc_geom(coarse)
+        assert C == Cc and C % 8 == 0
+        out = torch.empty((B, Hf, Wf, C), device=fine.device, dtype=torch.bfloat16)
+        L.call('lsnet_upsample_add_nhwc_bf16', L.ptr(fine), L.c_ll(ldf), L.ptr(coarse), L.c_ll(ldc), L.c_int(B), L.c_int(Hf),
+               L.c_int(Wf), L.c_int(Hc), L.c_int(Wc), L.c_int(C), L.ptr(out), L.c_ll(C), L.stream())
+        ctx.geom = (B, Hf, Wf, Hc, Wc, C)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import gemm_ops as G
+        B, Hf, Wf, Hc, Wc, C = ctx.geom
+        g = G.as_nhwc(g, torch.bfloat16)
+        gc = None
+        if ctx.needs_input_grad[1]:
+            gc = torch.empty((B, Hc, Wc, C), device=g.device, dtype=torch.bfloat16)
+            L.call('lsnet_upsample_add_bwd_nhwc_bf16', L.ptr(g), L.c_ll(G.nhwc_geom(g)[4]), L.c_int(B), L.c_int(Hf), L.c_int(Wf),
+                   L.c_int(Hc), L.c_int(Wc), L.c_int(C), L.ptr(gc), L.c_ll(C), L.stream())
+            gc = gc.permute(0, 3, 1, 2)
+        return (g if ctx.needs_input_grad[0] else None), gc
+
+
+def upsample_add(fine, coarse):
+    return _UpsampleAdd.apply(fine, coarse)

@@ -499,3 +499,25 @@ def test_head_glue_kernels_vs_torch(branch, num_vectors, n_out):
     (yr * gsp).sum().backward()
     (yg * gsp).sum().backward()
     assert torch.allclose(tg.grad, tr.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('Hf,Wf,Hc,Wc', [(100, 168, 50, 84), (25, 42, 13, 21), (13, 21, 7, 11), (9, 9, 4, 5)])
+def test_upsample_add_matches_interpolate(Hf, Wf, Hc, Wc):
+    """FPN top-down step (necks/fpn.py:180-192): fine + F.interpolate(coarse, size=fine.shape, mode='nearest') and its
+    gradients -- bit-equal forward (one fp32 add, one rounding), gradient of the coarse map to bf16 rounding of the sum."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(Hf * Wf)
+    fine = _bf(torch.randn(2, 64, Hf, Wf, generator=g)).to(DEV)
+    coarse = _bf(torch.randn(2, 64, Hc, Wc, generator=g)).to(DEV)
+    gy = _bf(torch.randn(2, 64, Hf, Wf, generator=g)).to(DEV)
+    fr, cr = fine.clone().requires_grad_(True), coarse.clone().requires_grad_(True)
+    ref = fr + F.interpolate(cr, size=(Hf, Wf), mode='nearest')
+    ref.backward(gy)
+    fo = fine.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    co = coarse.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    out = ops.upsample_add(fo, co)
+    out.backward(gy.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    torch.cuda.synchronize()
+    assert torch.equal(out.float(), _bf(ref.detach()))
+    assert torch.equal(fo.grad.float(), gy)
+    assert _rel(co.grad.float(), cr.grad) < 8e-3
