@@ -108,6 +108,10 @@ int lsnet_conv2d_wgrad_nhwc_bf16(const void* dy, long long ldy, const void* x, l
 int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2, long long ldx2, int B, int HW, int C, int G,
                         const float* gamma, const float* beta, float eps, int relu, double* stats, void* y,
                         long long ldy, void* stream);
+/* lsnet_groupnorm_fwd whose statistics (the 2*B*G sums at the start of `stats`) were already accumulated by the producer's
+ * epilogue (lsnet_dcn_forward_gn): finalises them into the (mean, rstd) table and applies. */
+int lsnet_groupnorm_fwd_pre(const void* x, long long ldx, int B, int HW, int C, int G, const float* gamma, const float* beta,
+                            float eps, int relu, double* stats, void* y, long long ldy, void* stream);
 int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy, long long lddy,
                         int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
@@ -273,6 +277,15 @@ size_t lsnet_dcn_forward_workspace_size(const lsnet_dcn_desc* d, int N);
 int lsnet_dcn_forward(const lsnet_dcn_desc* d, const void* x, const float* offset, long long ldo, const float* mask,
                       long long ldm, const void* Wp, int N, const float* bias, int relu, void* out, long long ldc,
                       int out_fp32, void* col_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* lsnet_dcn_forward that also accumulates the GroupNorm statistics of its output (before ReLU) in the GEMM epilogue
+ * (DCNConvModule = conv -> GroupNorm -> ReLU, mmdet/models/dense_heads/lsnet_head.py:1830-1849): gn_sums is
+ * the first 2*B*G doubles of a lsnet_groupnorm_fwd workspace, ZEROED by the caller; the kernel adds (sum x, sum x^2) per
+ * (image, group).  lsnet_groupnorm_fwd_pre then normalises without its own statistics pass.  NULL = plain forward. */
+int lsnet_dcn_forward_gn(const lsnet_dcn_desc* d, const void* x, const float* offset, long long ldo, const float* mask,
+                         long long ldm, const void* Wp, int N, const float* bias, int relu, void* out, long long ldc,
+                         int out_fp32, void* col_out, void* workspace, size_t workspace_bytes, double* gn_sums,
+                         int gn_groups, void* stream);
 
 size_t lsnet_dcn_backward_data_workspace_size(const lsnet_dcn_desc* d, int N);
 /* dy: bf16 [B*Ho*Wo, ldy] (N channels, N % 8 == 0); Wt: bf16 [kh*kw*C, N] (= Wp^T).  dx (NHWC, ACCUMULATED: the caller

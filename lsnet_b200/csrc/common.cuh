@@ -213,6 +213,36 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// GroupNorm statistics from a GEMM epilogue: f = this thread's 32 consecutive output channels (first one
+// col0) of ONE pixel row of image b (valid: the row exists).  Per 8-channel piece the row sums (x, x^2) are folded over
+// the warp's 32 rows and lane 0 adds them to sums[(b*G + group)*2 + {0,1}] (fp64 atomics; cpg = channels per group,
+// a multiple of 8).  The rows of a warp may belong to two images (plain [pixels, C] GEMMs): [b_lo, b_hi] covers them.
+__device__ __forceinline__ void gn_epilogue_sums(const float (&f)[32], bool valid, int b, int b_lo, int b_hi, int col0, int N,
+                                                 int cpg, int G, double* sums, int lane) {
+  for (int bb = b_lo; bb <= b_hi; ++bb) {
+    const bool mine = valid && b == bb;
+#pragma unroll
+    for (int g0 = 0; g0 < 32; g0 += 8) {
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = mine ? f[g0 + j] : 0.f;
+        s += v;
+        ss += v * v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      }
+      if (lane == 0 && col0 + g0 < N) {
+        double* dst = sums + (static_cast<long long>(bb) * G + (col0 + g0) / cpg) * 2;
+        atomicAdd(dst, static_cast<double>(s));
+        atomicAdd(dst + 1, static_cast<double>(ss));
+      }
+    }
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

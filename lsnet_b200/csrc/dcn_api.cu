@@ -19,7 +19,9 @@ bool dcn_fused_supported(int C, int N, int kh, int kw, int dg, long long ldx, lo
                          long long Ho, long long Wo);
 int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, const float* mask, const void* Wp, int N,
                       const float* bias, int relu, void* out, long long ldc, int out_fp32, void* col, cudaStream_t st,
-                      int grouped);
+                      int grouped, double* gn_sums, int gn_G);
+int gemm_bf16_gn(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M, int N, int K,
+                 const float* bias, int relu, int out_fp32, double* gn_sums, int gn_G, long long gn_hw, cudaStream_t st);
 size_t dcn_fused_wgrad_partial_bytes(const DcnGeom& g, int M, long long ldw, int diag);
 int dcn_fused_wgrad(const DcnGeom& g, const void* dy, long long ldy, int M, const void* x, const float* offset,
                     const float* mask, float* dW, long long ldw, float* partial, cudaStream_t st, int diag);
@@ -97,7 +99,17 @@ extern "C" int lsnet_dcn_forward(const lsnet_dcn_desc* d, const void* x, const f
                                  const float* mask, long long ldm, const void* Wp, int N, const float* bias, int relu,
                                  void* out, long long ldc, int out_fp32, void* col_out, void* workspace,
                                  size_t workspace_bytes, void* stream) {
+  return lsnet_dcn_forward_gn(d, x, offset, ldo, mask, ldm, Wp, N, bias, relu, out, ldc, out_fp32, col_out, workspace,
+                              workspace_bytes, nullptr, 0, stream);
+}
+
+extern "C" int lsnet_dcn_forward_gn(const lsnet_dcn_desc* d, const void* x, const float* offset, long long ldo,
+                                    const float* mask, long long ldm, const void* Wp, int N, const float* bias, int relu,
+                                    void* out, long long ldc, int out_fp32, void* col_out, void* workspace,
+                                    size_t workspace_bytes, double* gn_sums, int gn_groups, void* stream) {
   if (int rc = check_desc("lsnet_dcn_forward", d)) return rc;
+  if (gn_sums && (d->groups > 1 || gn_groups < 1 || N % gn_groups || (N / gn_groups) % 8))
+    return set_error("lsnet_dcn_forward_gn: GroupNorm statistics need groups == 1, N %% G == 0, (N / G) %% 8 == 0 (N=%d G=%d)", N, gn_groups);
   if (d->B == 0 || d->Ho == 0 || d->Wo == 0) return 0;
   if (N <= 0 || N % 16) return set_error("lsnet_dcn_forward: N (= rows of the packed weight) must be a positive multiple of 16, got %d", N);
   if (ldc % (out_fp32 ? 4 : 8)) return set_error("lsnet_dcn_forward: output pitch must be 16-byte aligned");
@@ -107,11 +119,11 @@ extern "C" int lsnet_dcn_forward(const lsnet_dcn_desc* d, const void* x, const f
   if (d->groups > 1) {
     if (col_out) return set_error("lsnet_dcn_forward: the grouped kernel has no column side output");
     const DcnGeom g = geom_of(d, ldo, ldm, K, mask);
-    return dcn_fused_forward(g, x, offset, mask, Wp, N, bias, relu, out, ldc, out_fp32, nullptr, st, 1);
+    return dcn_fused_forward(g, x, offset, mask, Wp, N, bias, relu, out, ldc, out_fp32, nullptr, st, 1, nullptr, 0);
   }
   if (dcn_fused_supported(d->C, N, d->kh, d->kw, d->deformable_groups, d->ldx, d->B, d->H, d->W, d->Ho, d->Wo)) {
     const DcnGeom g = geom_of(d, ldo, ldm, K, mask);
-    return dcn_fused_forward(g, x, offset, mask, Wp, N, bias, relu, out, ldc, out_fp32, col_out, st, 0);
+    return dcn_fused_forward(g, x, offset, mask, Wp, N, bias, relu, out, ldc, out_fp32, col_out, st, 0, gn_sums, gn_groups);
   }
   void* col = col_out ? col_out : workspace;
   if (!col || (!col_out && workspace_bytes < col_bytes(d)))
@@ -121,8 +133,8 @@ extern "C" int lsnet_dcn_forward(const lsnet_dcn_desc* d, const void* x, const f
                                      d->kw, d->stride_h, d->stride_w, d->pad_h, d->pad_w, d->dil_h, d->dil_w,
                                      d->scale_h, d->scale_w, d->deformable_groups, col, K, d->mask_logits, stream))
     return rc;
-  return lsnet_gemm_bf16(col, K, Wp, K, out, ldc, d->B * d->Ho * d->Wo, N, static_cast<int>(K), bias, relu, out_fp32,
-                         stream);
+  return gemm_bf16_gn(col, K, Wp, K, out, ldc, d->B * d->Ho * d->Wo, N, static_cast<int>(K), bias, relu, out_fp32, gn_sums,
+                      gn_groups, static_cast<long long>(d->Ho) * d->Wo, st);
 }
 
 extern "C" size_t lsnet_dcn_backward_data_workspace_size(const lsnet_dcn_desc* d, int N) {

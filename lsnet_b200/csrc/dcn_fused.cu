@@ -57,6 +57,8 @@ struct FusedFwdArgs {
   int out_fp32, relu;
   const float* bias;
   __nv_bfloat16* col;                 // optional side output: the bf16 column matrix [pixels, taps*C] (or null)
+  double* gn_sums;                    // optional: GroupNorm statistics of the output (before ReLU), [B, G, 2] fp64, pre-zeroed
+  int gn_cpg, gn_G;
 };
 
 template <int BN, int STAGES>
@@ -219,6 +221,7 @@ dcn_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmB, const FusedFwdArgs
             for (int j = 0; j < 32; ++j)
               if (c + j < p.N) f[j] += __ldg(p.bias + c + j);
           }
+          if (p.gn_sums) gn_epilogue_sums(f, valid, b, b, b, c, p.N, p.gn_cpg, p.gn_G, p.gn_sums, lane);
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -762,8 +765,9 @@ static int dispatch_fused_fwd(const CUtensorMap& tmB, const FusedFwdArgs& a, cud
 // grouped != 0: Wp is the block-diagonal pack [N = C, taps * 64] (see lsnet_dcn_forward)
 int dcn_fused_forward(const DcnGeom& g, const void* x, const float* offset, const float* mask, const void* Wp, int N,
                       const float* bias, int relu, void* out, long long ldc, int out_fp32, void* col, cudaStream_t st,
-                      int grouped) {
+                      int grouped, double* gn_sums, int gn_G) {
   FusedFwdArgs a{};
+  a.gn_sums = gn_sums; a.gn_G = gn_G; a.gn_cpg = gn_sums ? N / gn_G : 0;
   a.grouped = grouped ? 1 : 0;
   a.g = g;
   a.x = static_cast<const __nv_bfloat16*>(x);

@@ -45,6 +45,11 @@ struct GemmArgs {
   long long ldr;
   const __nv_bfloat16* mask;
   long long ldm;
+  // GroupNorm statistics of the output (before ReLU), accumulated by the epilogue: sums [B, G, 2] fp64 (pre-zeroed), gn_cpg
+  // channels per group, gn_hw pixels per image (row -> image in plain mode); null = off
+  double* gn_sums;
+  int gn_cpg, gn_G;
+  long long gn_hw;
   // block-diagonal mode (grouped DCN dCol): ONE K block per tile; the N tile nt (64 columns) multiplies the 64-column
   // block (nt % blockdiag) of A with B[n0 .. n0+63, 0..63]; 0 = off
   int blockdiag;
@@ -280,6 +285,17 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               f[8 * j + 2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
             }
           }
+        }
+        if (p.gn_sums) {
+          int b = tb, b_lo = tb, b_hi = tb;
+          if (!p.conv) {      // plain [pixels, C] rows: the 32 rows of this warp may straddle an image boundary
+            const long long r0 = static_cast<long long>(mt) * BM + q * 32;
+            const long long rl = (r0 + 31 < p.M ? r0 + 31 : p.M - 1);
+            b = static_cast<int>(row / p.gn_hw);
+            b_lo = static_cast<int>(r0 / p.gn_hw);
+            b_hi = static_cast<int>(rl / p.gn_hw);
+          }
+          gn_epilogue_sums(f, valid, b, b_lo, b_hi, col0, p.N, p.gn_cpg, p.gn_G, p.gn_sums, lane);
         }
         if (p.relu) {
 #pragma unroll
@@ -750,6 +766,26 @@ extern "C" int lsnet_gemm_bf16(const void* A, long long lda, const void* Bw, lon
   a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
   return dispatch_kmajor(tmA, Bw, N, K, ldb, a, static_cast<cudaStream_t>(stream));
 }
+
+// internal: lsnet_gemm_bf16 + GroupNorm statistics of the output in the epilogue (dcn_api.cu, column-matrix forward path)
+namespace lsn {
+int gemm_bf16_gn(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc, int M, int N, int K,
+                 const float* bias, int relu, int out_fp32, double* gn_sums, int gn_G, long long gn_hw, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(bias) % 16) return set_error("gemm_bf16_gn: bias must be 16-byte aligned");
+  if ((N % 16) || (K % 8) || (lda % 8) || (ldb % 8) || (ldc % (out_fp32 ? 4 : 8)))
+    return set_error("gemm_bf16_gn: need N%%16==0, K%%8==0 and 16-byte aligned pitches (N=%d K=%d)", N, K);
+  if (gn_sums && (gn_G < 1 || N % gn_G || (N / gn_G) % 8 || gn_hw < 1))
+    return set_error("gemm_bf16_gn: GroupNorm epilogue needs N %% G == 0 and (N / G) %% 8 == 0 (N=%d G=%d)", N, gn_G);
+  CUtensorMap tmA;
+  if (int rc = make_map_2d(&tmA, A, M, K, lda, 64, BM)) return rc;
+  GemmArgs a{};
+  a.M = M; a.N = N; a.num_k_iters = (K + BK - 1) / BK; a.m_tiles = (M + BM - 1) / BM;
+  a.conv = 0; a.out = out; a.ldc = ldc; a.out_fp32 = out_fp32; a.relu = relu; a.bias = bias;
+  a.gn_sums = gn_sums; a.gn_G = gn_G; a.gn_cpg = gn_sums ? N / gn_G : 0; a.gn_hw = gn_hw;
+  return dispatch_kmajor(tmA, Bw, N, K, ldb, a, st);
+}
+}  // namespace lsn
 
 // lsnet_gemm_bf16 with the full epilogue: v = acc + bias + resid[row, :];  ReLU;  v = mask[row, :] > 0 ? v : 0
 extern "C" int lsnet_gemm_ex_bf16(const void* A, long long lda, const void* Bw, long long ldb, void* out, long long ldc,

@@ -114,6 +114,15 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
 }
 
+// (sum, sumsq) in fp64 -> (mean, rstd) in fp32 for statistics that a producer's epilogue accumulated
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, int BG, double n, float eps, float2* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  const double m = stats[2 * i] / n;
+  double var = stats[2 * i + 1] / n - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mr[i] = make_float2(static_cast<float>(m), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
 __device__ __forceinline__ void mean_rstd(const float2* mr, int b, int g, const GnArgs& a, float* mean, float* rstd) {
   const float2 v = __ldg(mr + static_cast<long long>(b) * a.G + g);
   *mean = v.x;
@@ -371,6 +380,21 @@ extern "C" int lsnet_groupnorm_fwd(const void* x, long long ldx, const void* x2,
   gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2), a, mr, gamma, beta,
       static_cast<__nv_bfloat16*>(y));
+  return check_launch("gn_apply");
+}
+
+extern "C" int lsnet_groupnorm_fwd_pre(const void* x, long long ldx, int B, int HW, int C, int G, const float* gamma,
+                                       const float* beta, float eps, int relu, double* stats, void* y, long long ldy,
+                                       void* stream) {
+  if (B <= 0 || HW <= 0) return 0;
+  if (int rc = gn_check("lsnet_groupnorm_fwd_pre", C, G, ldx, ldy)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GnArgs a{B, HW, C, G, ldx, 0, ldy, eps, relu};
+  float2* mr = reinterpret_cast<float2*>(stats + 2 * B * G + 1);
+  gn_finalize_kernel<<<(B * G + 127) / 128, 128, 0, st>>>(stats, B * G, static_cast<double>(HW) * (C / G), eps, mr);
+  if (int rc = check_launch("gn_finalize")) return rc;
+  gn_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), nullptr, a, mr, gamma, beta, static_cast<__nv_bfloat16*>(y));
   return check_launch("gn_apply");
 }
 

@@ -64,8 +64,11 @@ class DCNConvModule(nn.Module):
 
     def forward(self, x, exclusive=False):
         """``exclusive``: x has no other consumer (see ModulatedDeformConvPack.forward)."""
-        return ops.group_norm_nhwc(self.conv(x, exclusive=exclusive), self.bn.num_groups, self.bn.weight, self.bn.bias,
-                                   self.bn.eps, relu=True)
+        # SURVEY §8 f1: the GroupNorm statistics come out of the deformable convolution's GEMM epilogue
+        h = {} if (GN_EPILOGUE and x.is_cuda) else None
+        y = self.conv(x, exclusive=exclusive, gn_holder=h, gn_groups=self.bn.num_groups)
+        return ops.group_norm_nhwc(y, self.bn.num_groups, self.bn.weight, self.bn.bias, self.bn.eps, relu=True,
+                                   pre_sums=h.get('sums') if h else None)
 
 
 class NormConvModule(nn.Module):
@@ -103,6 +106,8 @@ class PackedGT:
             self.valid_hw.copy_(other.valid_hw, non_blocking=True)
 
 
+# GroupNorm statistics of the tower layers accumulated by the deformable convolution's GEMM epilogue
+GN_EPILOGUE = os.environ.get('LSNET_GN_EPILOGUE', '1') == '1'
 TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
 # Every pyramid level on its own streams: the kernels of the three small levels (6 % of the pixels, 3-44 CTAs, 15-20 us
 # each) run beside each other instead of one after the other.  Measured (1xB200, B=4): all levels in one chain 29.8 ms,

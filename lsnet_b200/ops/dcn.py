@@ -145,7 +145,7 @@ def _workspace(nbytes, device):
 
 
 def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, scales, dg, mask_logits=False,
-                out=None, out_dtype=torch.bfloat16, relu=False, save_col=False, groups=1):
+                out=None, out_dtype=torch.bfloat16, relu=False, save_col=False, groups=1, gn_sums=None, gn_groups=0):
     """Whole forward operator.  x (B,C,H,W) channels_last bf16; wp bf16 [Npad16, kh*kw*C]; returns (out2d [P, N], col or
     None).  ``out``: write into this [P, N] view (row pitch = out.stride(0))."""
     import ctypes
@@ -164,9 +164,11 @@ def dcn_forward(x, offset, mask, wp, bias, Ho, Wo, kh, kw, stride, pad, dil, sca
     col = torch.empty((P, kh * kw * C), device=x.device, dtype=torch.bfloat16) if save_col else None
     ws_bytes = 0 if save_col else L.load().lsnet_dcn_forward_workspace_size(ctypes.byref(d), L.c_int(N))
     ws = _workspace(ws_bytes, x.device)
-    L.call('lsnet_dcn_forward', ctypes.byref(d), L.ptr(x), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm),
+    # gn_sums: fp64 workspace of the GroupNorm that follows (zeroed); the epilogue adds the output's (sum, sum of squares)
+    L.call('lsnet_dcn_forward_gn', ctypes.byref(d), L.ptr(x), L.ptr(offset), L.c_ll(ldo), L.ptr(mask), L.c_ll(ldm),
            L.ptr(wp), L.c_int(N), L.ptr(bias), L.c_int(int(relu)), L.ptr(out), L.c_ll(out.stride(0)),
-           L.c_int(int(out.dtype == torch.float32)), L.ptr(col), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream())
+           L.c_int(int(out.dtype == torch.float32)), L.ptr(col), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.ptr(gn_sums),
+           L.c_int(gn_groups), L.stream())
     return out, col
 
 
@@ -263,8 +265,10 @@ class _DCN(Function):
 
     @staticmethod
     def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
-                out_slice=None, packed_om=False, gx_sink=None):
+                out_slice=None, packed_om=False, gx_sink=None, gn_holder=None, gn_groups=0):
         ctx.gx_sink = gx_sink        # see ops/conv.py::_ConvSame: the conv_offset conv adds its input gradient into ours
+        # gn_holder (dict) + gn_groups: a GroupNorm(gn_groups) follows; its statistics are accumulated by this op's GEMM
+        # epilogue into holder['sums'] (ops/norm.py picks them up instead of running its own statistics pass)
         # packed_om: ``offset`` is the whole conv_offset output (B, 3*dg*taps, Ho, Wo) — offsets in the first 2/3 of the
         # channels, mask LOGITS behind them; ``mask`` is None and the kernels apply the sigmoid.
         co, cig, kh, kw = weight.shape
@@ -309,8 +313,14 @@ class _DCN(Function):
             assert npad == co and buf.dtype == torch.bfloat16 and buf.shape[:3] == (B, Ho, Wo) and c0 % 8 == 0
             ld = buf.shape[3]
             out2d = torch.as_strided(buf, (B * Ho * Wo, co), (ld, 1), buf.storage_offset() + c0)
+        gn_sums = None
+        if gn_holder is not None and gn_groups > 0 and native == 1 and not out_fp32 and out_slice is None and npad == co \
+                and co % gn_groups == 0 and (co // gn_groups) % 8 == 0:
+            gn_sums = torch.zeros(3 * B * gn_groups + 1, device=x.device, dtype=torch.float64)
+            gn_holder['sums'] = gn_sums
         out2d, col = dcn_forward(x, off_v, mask_v, wp, b, *cfg, mask_logits=logits, out=out2d,
-                                 out_dtype=torch.float32 if out_fp32 else torch.bfloat16, save_col=save_col, groups=native)
+                                 out_dtype=torch.float32 if out_fp32 else torch.bfloat16, save_col=save_col, groups=native,
+                                 gn_sums=gn_sums, gn_groups=gn_groups)
         ctx.save_for_backward(x, offset, mask, weight, col)
         ctx.cfg, ctx.has_bias, ctx.groups = cfg, bias is not None, groups
         ctx.grad2d = G.direct_grad(weight) if groups == 1 else None
@@ -391,7 +401,7 @@ class _DCN(Function):
             gw = wgrad()
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = colsum
-        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None, None
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
@@ -409,11 +419,11 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
 
 
 def modulated_deform_conv_packed(x, offset_mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                                 deformable_groups=1, out_fp32=False, gx_sink=None):
+                                 deformable_groups=1, out_fp32=False, gx_sink=None, gn_holder=None, gn_groups=0):
     """ModulatedDeformConvPack.forward after its conv_offset (deform_conv.py:528-533) as ONE op: ``offset_mask`` is the
     raw conv_offset output; chunk / cat / sigmoid and their backward happen inside the sampling kernels."""
     return _DCN.apply(x, offset_mask, None, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
-                      groups, deformable_groups, False, out_fp32, None, True, gx_sink)
+                      groups, deformable_groups, False, out_fp32, None, True, gx_sink, gn_holder, gn_groups)
 
 
 def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

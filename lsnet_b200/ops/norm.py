@@ -10,7 +10,7 @@ from . import gemm_ops as G
 class _GroupNorm(Function):
 
     @staticmethod
-    def forward(ctx, x, x2, weight, bias, num_groups, eps, relu):
+    def forward(ctx, x, x2, weight, bias, num_groups, eps, relu, pre_sums=None):
         x = G.as_nhwc(x, torch.bfloat16)
         B, H, W, C, ldx = G.nhwc_geom(x)
         ldx2 = 0
@@ -18,11 +18,18 @@ class _GroupNorm(Function):
             x2 = G.as_nhwc(x2, torch.bfloat16)
             ldx2 = G.nhwc_geom(x2)[4]
         w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
-        stats = torch.empty(B * num_groups * 3 + 1, device=x.device, dtype=torch.float64)     # sums | ticket | (mean, rstd)
         y = torch.empty((B, H, W, C), device=x.device, dtype=torch.bfloat16)
-        L.call('lsnet_groupnorm_fwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.c_int(B), L.c_int(H * W),
-               L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats),
-               L.ptr(y), L.c_ll(C), L.stream())
+        if pre_sums is not None and x2 is None and pre_sums.numel() == B * num_groups * 3 + 1:
+            # the producer's GEMM epilogue already accumulated (sum, sum of squares) per (image, group)
+            stats = pre_sums
+            L.call('lsnet_groupnorm_fwd_pre', L.ptr(x), L.c_ll(ldx), L.c_int(B), L.c_int(H * W), L.c_int(C),
+                   L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats), L.ptr(y), L.c_ll(C),
+                   L.stream())
+        else:
+            stats = torch.empty(B * num_groups * 3 + 1, device=x.device, dtype=torch.float64)  # sums | ticket | (mean, rstd)
+            L.call('lsnet_groupnorm_fwd', L.ptr(x), L.c_ll(ldx), L.ptr(x2), L.c_ll(ldx2), L.c_int(B), L.c_int(H * W),
+                   L.c_int(C), L.c_int(num_groups), L.ptr(w), L.ptr(b), L.c_f(eps), L.c_int(int(relu)), L.ptr(stats),
+                   L.ptr(y), L.c_ll(C), L.stream())
         ctx.save_for_backward(x, x2, w, b, stats)
         ctx.cfg = (num_groups, eps, relu)
         ctx.affine = (weight, bias)
@@ -50,9 +57,10 @@ class _GroupNorm(Function):
         dxv = dx.permute(0, 3, 1, 2)
         if direct:
             dgamma = dbeta = None
-        return dxv, (dxv if x2 is not None else None), dgamma, dbeta, None, None, None
+        return dxv, (dxv if x2 is not None else None), dgamma, dbeta, None, None, None, None
 
 
-def group_norm_nhwc(x, num_groups, weight, bias, eps=1e-5, relu=False, residual=None):
-    """relu?(GroupNorm(x (+ residual))) -> (B,C,H,W) channels_last bf16."""
-    return _GroupNorm.apply(x, residual, weight, bias, int(num_groups), float(eps), bool(relu))
+def group_norm_nhwc(x, num_groups, weight, bias, eps=1e-5, relu=False, residual=None, pre_sums=None):
+    """relu?(GroupNorm(x (+ residual))) -> (B,C,H,W) channels_last bf16.  ``pre_sums``: fp64 statistics workspace whose sums
+    the producer of x accumulated in its GEMM epilogue (ops.dcn: gn_holder) -- the statistics pass is skipped."""
+    return _GroupNorm.apply(x, residual, weight, bias, int(num_groups), float(eps), bool(relu), pre_sums)

@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lsnet_b200.data import MODEL_CFG, synthetic_batch, to_device
 from lsnet_b200.train import GraphTrainer, Trainer, parse_losses
