@@ -116,11 +116,13 @@ int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2, long long 
                         int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
                         const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma, float* dbeta,
                         void* stream);
-/* _acc: dgamma / dbeta are ADDED to their targets (the parameters' gradient memory: no memset, no accumulate kernel). */
+/* _acc: dgamma / dbeta are ADDED to their targets (the parameters' gradient memory: no memset, no accumulate kernel).
+ * dx_colsum (optional, fp32 [C]): the per-channel sum of dx is ADDED there -- the bias gradient of a conv / DCN whose
+ * output is this norm's input (replaces that layer's own column-sum pass over dx). */
 int lsnet_groupnorm_bwd_acc(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy, long long lddy,
                             int B, int HW, int C, int G, const float* gamma, const float* beta, float eps, int relu,
                             const double* stats, double* ws_bstats, void* dx, long long lddx, float* dgamma,
-                            float* dbeta, void* stream);
+                            float* dbeta, float* dx_colsum, void* stream);
 
 /* LSHead element-wise glue.  pred_reg: o fp32 [P, ldo] = output of pts_*_init_out (n_out channels); sp[P, ldsp] =
  * softplus(o[:, :n_sp]) (nn.Softplus defaults, lsnet_head.py:96); off[P, ldoff] = the n_off DCN sampling offsets of

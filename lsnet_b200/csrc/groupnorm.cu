@@ -305,10 +305,19 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
                     const __nv_bfloat16* __restrict__ dy, long long lddy, const GnArgs a,
                     const float2* __restrict__ stats, const float2* __restrict__ bstats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ dx,
-                    long long lddx) {
+                    long long lddx, float* __restrict__ dx_colsum) {
+  // dx_colsum (optional, fp32 [C], ADDED to): per-channel sum of dx over all pixels = the bias gradient of the layer that
+  // produced x (a conv / DCN bias directly in front of this norm) -- this kernel holds every dx value in registers
+  // anyway, the separate read-only column-sum pass over dx disappears
+  extern __shared__ float sm_cs[];
   const int vpp = a.C / 8, cpg8 = (a.C / a.G) / 8;
   const float inv_n = 1.f / (static_cast<float>(a.HW) * (a.C / a.G));
   const long long total = static_cast<long long>(a.B) * a.HW * vpp;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (dx_colsum) {
+    for (int i = threadIdx.x; i < a.C; i += GN_THREADS) sm_cs[i] = 0.f;
+    __syncthreads();
+  }
   float gmr[8], btr[8];
   {
     const int v0 = static_cast<int>((static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x) % vpp);
@@ -340,8 +349,16 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
       float dd = d[e];
       if (a.relu && !(xh * gm + btr[e] > 0.f)) dd = 0.f;
       f[e] = rstd * (dd * gm - (s1 + xh * s2) * inv_n);
+      cs[e] += f[e];
     }
     st8(dx + px * lddx + v * 8, f);
+  }
+  if (dx_colsum) {      // the launcher keeps ONE vector column per thread: fold the block's threads of a column, then one atomic
+    const int v0 = static_cast<int>((static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x) % vpp);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sm_cs[v0 * 8 + e], cs[e]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.C; i += GN_THREADS) atomicAdd(&dx_colsum[i], sm_cs[i]);
   }
 }
 
@@ -401,7 +418,7 @@ extern "C" int lsnet_groupnorm_fwd_pre(const void* x, long long ldx, int B, int 
 static int groupnorm_bwd_impl(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
                               long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
                               float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
-                              float* dgamma, float* dbeta, int accumulate, void* stream) {
+                              float* dgamma, float* dbeta, int accumulate, float* dx_colsum, void* stream) {
   if (B <= 0 || HW <= 0) return 0;
   if (int rc = gn_check("lsnet_groupnorm_bwd", C, G, ldx, lddx)) return rc;
   if (lddy % 8) return set_error("lsnet_groupnorm_bwd: dy pitch must be a multiple of 8");
@@ -420,10 +437,11 @@ static int groupnorm_bwd_impl(const void* x, long long ldx, const void* x2, long
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, gamma, beta, ws_bstats, dgamma, dbeta,
       reinterpret_cast<unsigned*>(ws_bstats + 2 * B * G), s12);
   if (int rc = check_launch("gn_bwd_stats")) return rc;
-  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS, 0, st>>>(
+  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS,
+                        dx_colsum ? sizeof(float) * C : 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, s12, gamma, beta, static_cast<__nv_bfloat16*>(dx),
-      lddx);
+      lddx, dx_colsum);
   return check_launch("gn_bwd_apply");
 }
 
@@ -432,13 +450,13 @@ extern "C" int lsnet_groupnorm_bwd(const void* x, long long ldx, const void* x2,
                                    float eps, int relu, const double* stats, double* ws_bstats, void* dx, long long lddx,
                                    float* dgamma, float* dbeta, void* stream) {
   return groupnorm_bwd_impl(x, ldx, x2, ldx2, dy, lddy, B, HW, C, G, gamma, beta, eps, relu, stats, ws_bstats, dx, lddx,
-                            dgamma, dbeta, 0, stream);
+                            dgamma, dbeta, 0, nullptr, stream);
 }
 // same, but dgamma / dbeta are ADDED to (the affine parameters' gradient memory; no memset, no separate add kernel)
 extern "C" int lsnet_groupnorm_bwd_acc(const void* x, long long ldx, const void* x2, long long ldx2, const void* dy,
                                        long long lddy, int B, int HW, int C, int G, const float* gamma, const float* beta,
                                        float eps, int relu, const double* stats, double* ws_bstats, void* dx,
-                                       long long lddx, float* dgamma, float* dbeta, void* stream) {
+                                       long long lddx, float* dgamma, float* dbeta, float* dx_colsum, void* stream) {
   return groupnorm_bwd_impl(x, ldx, x2, ldx2, dy, lddy, B, HW, C, G, gamma, beta, eps, relu, stats, ws_bstats, dx, lddx,
-                            dgamma, dbeta, 1, stream);
+                            dgamma, dbeta, 1, dx_colsum, stream);
 }

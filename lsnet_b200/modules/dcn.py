@@ -124,7 +124,7 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
         self.conv_offset.weight.data.zero_()
         self.conv_offset.bias.data.zero_()
 
-    def forward(self, x, exclusive=False, gn_holder=None, gn_groups=0):
+    def forward(self, x, exclusive=False, gn_holder=None, gn_groups=0, skip_bias_grad=False):
         """``exclusive``: the caller guarantees that this module is the ONLY consumer of ``x`` in the autograd graph (a
         tower layer fed by the previous layer).  Then the two internal consumers of x share a gradient sink: the sampling
         op's backward runs first (conv_offset's output feeds it) and the conv_offset backward adds its input gradient into
@@ -138,7 +138,8 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
             # gn_holder / gn_groups: the GroupNorm that follows takes its statistics from this op's GEMM epilogue
             return ops.modulated_deform_conv_packed(x, out[:, :3 * n], self.weight, self.bias, self.stride, self.padding,
                                                     self.dilation, self.groups, self.deformable_groups, gx_sink=sink,
-                                                    gn_holder=gn_holder, gn_groups=gn_groups)
+                                                    gn_holder=gn_holder, gn_groups=gn_groups,
+                                                    skip_bias_grad=skip_bias_grad)
         out = _offset_conv(self, x)
         # chunk(3) + cat(o1, o2) keeps the channel order (deform_conv.py:528-531): offsets = first 2n channels
         offset, mask = out[:, :2 * n], torch.sigmoid(out[:, 2 * n:3 * n])

@@ -66,9 +66,11 @@ class DCNConvModule(nn.Module):
         """``exclusive``: x has no other consumer (see ModulatedDeformConvPack.forward)."""
         # SURVEY §8 f1: the GroupNorm statistics come out of the deformable convolution's GEMM epilogue
         h = {} if (GN_EPILOGUE and x.is_cuda) else None
-        y = self.conv(x, exclusive=exclusive, gn_holder=h, gn_groups=self.bn.num_groups)
+        # ... and the bias gradient of the convolution (= per-channel sum of the norm's dx) out of the norm's backward
+        ext = GN_EPILOGUE and x.is_cuda and ops.norm.bias_sink_ok(self.bn.weight, self.bn.bias, self.conv.bias)
+        y = self.conv(x, exclusive=exclusive, gn_holder=h, gn_groups=self.bn.num_groups, skip_bias_grad=ext)
         return ops.group_norm_nhwc(y, self.bn.num_groups, self.bn.weight, self.bn.bias, self.bn.eps, relu=True,
-                                   pre_sums=h.get('sums') if h else None)
+                                   pre_sums=h.get('sums') if h else None, bias_sink=self.conv.bias if ext else None)
 
 
 class NormConvModule(nn.Module):

@@ -265,7 +265,8 @@ class _DCN(Function):
 
     @staticmethod
     def forward(ctx, x, offset, mask, weight, bias, stride, pad, dil, scales, groups, dg, out_from_offset, out_fp32,
-                out_slice=None, packed_om=False, gx_sink=None, gn_holder=None, gn_groups=0):
+                out_slice=None, packed_om=False, gx_sink=None, gn_holder=None, gn_groups=0, skip_bias_grad=False):
+        ctx.skip_bias_grad = skip_bias_grad      # the GroupNorm behind this op adds the bias gradient (ops/norm.py bias_sink)
         ctx.gx_sink = gx_sink        # see ops/conv.py::_ConvSame: the conv_offset conv adds its input gradient into ours
         # gn_holder (dict) + gn_groups: a GroupNorm(gn_groups) follows; its statistics are accumulated by this op's GEMM
         # epilogue into holder['sums'] (ops/norm.py picks them up instead of running its own statistics pass)
@@ -344,7 +345,7 @@ class _DCN(Function):
                 d = d.view(groups, co // groups, kh, kw, groups, ci // groups)[idx, :, :, :, idx]
                 d = d.reshape(co, kh, kw, ci // groups)
             return d.permute(0, 3, 1, 2).to(weight.dtype)
-        gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4],
+        gyp, colsum = G.grad_prep(gy, None, ctx.has_bias and ctx.needs_input_grad[4] and not ctx.skip_bias_grad,
                                   colsum_into=G.direct_vec(ctx.bias_param))
         cop = gyp.shape[1]
         gy2 = torch.as_strided(gyp, (B * Ho * Wo, cop), (gyp.stride(3), 1))
@@ -399,9 +400,9 @@ class _DCN(Function):
             torch.cuda.current_stream().wait_stream(side)
         elif ctx.needs_input_grad[3]:
             gw = wgrad()
-        if ctx.has_bias and ctx.needs_input_grad[4]:
+        if ctx.has_bias and ctx.needs_input_grad[4] and not ctx.skip_bias_grad:
             gb = colsum
-        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None, None, None, None
+        return gx, goff, gmask, gw, gb, None, None, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64,
@@ -419,11 +420,12 @@ def modulated_deform_conv(x, offset, mask, weight, bias=None, stride=1, padding=
 
 
 def modulated_deform_conv_packed(x, offset_mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
-                                 deformable_groups=1, out_fp32=False, gx_sink=None, gn_holder=None, gn_groups=0):
+                                 deformable_groups=1, out_fp32=False, gx_sink=None, gn_holder=None, gn_groups=0,
+                                 skip_bias_grad=False):
     """ModulatedDeformConvPack.forward after its conv_offset (deform_conv.py:528-533) as ONE op: ``offset_mask`` is the
     raw conv_offset output; chunk / cat / sigmoid and their backward happen inside the sampling kernels."""
     return _DCN.apply(x, offset_mask, None, weight, bias, _pair(stride), _pair(padding), _pair(dilation), (1.0, 1.0),
-                      groups, deformable_groups, False, out_fp32, None, True, gx_sink, gn_holder, gn_groups)
+                      groups, deformable_groups, False, out_fp32, None, True, gx_sink, gn_holder, gn_groups, skip_bias_grad)
 
 
 def pyramid_deform_conv(x, offset, weight, scales=1, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,

@@ -418,7 +418,9 @@ def test_gn_statistics_from_the_dcn_epilogue(B, H, W):
     for name, a, b in zip(['y', 'dx', 'dgamma', 'dw'], res[True], res[False]):
         # dx is accumulated with bf16 reds whose order varies from run to run (two runs of the SAME mode differ by a few
         # per cent of max|dx| in single elements of a 27 M element map): compare it in the L2 norm
-        err = float((a - b).norm() / (b.norm() + 1e-30)) if name == 'dx' else float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        # (the weight gradient of a 7x11 map sums 231 pixels: the handful of outputs whose ReLU mask flips with the last
+        # bits of the statistics moves single entries by a few per cent -- gradients are compared in the L2 norm)
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-30)) if name == 'y' else float((a - b).norm() / (b.norm() + 1e-30))
         assert err < 2e-2, (name, err)
     # the statistics themselves: mean / variance of the normalised pre-activation are (beta, gamma^2) per group only in
     # expectation, so check against torch GroupNorm on the same DCN output instead
@@ -430,5 +432,44 @@ def test_gn_statistics_from_the_dcn_epilogue(B, H, W):
     assert float((y.float() - ref).abs().max() / ref.abs().max()) < 1.5e-2
     sums = h['sums'][:2 * B * 32].view(B, 32, 2).float().cpu()
     r = raw.float().view(B, 32, 8, H * W)
-    assert torch.allclose(sums[..., 0], r.sum((2, 3)).cpu(), rtol=2e-2, atol=2e-2 * float(r.abs().sum((2, 3)).max()))
-    assert torch.allclose(sums[..., 1], (r * r).sum((2, 3)).cpu(), rtol=1e-2)
+    # tight enough to see ONE missing pixel row of a group (8 of 8 * H*W values: 1.3 % of the sum of squares at 7x11);
+    # bf16 rounding of the reference values moves it by ~1e-4
+    ss_ref = (r * r).sum((2, 3)).cpu()
+    dev = float(((sums[..., 1] - ss_ref).abs() / ss_ref).max())
+    assert dev < 2e-3, dev
+    s_ref, s_abs = r.sum((2, 3)).cpu(), r.abs().sum((2, 3)).cpu()
+    dev = float(((sums[..., 0] - s_ref).abs() / s_abs).max())
+    assert dev < 2e-3, dev
+
+
+def test_dcn_bias_gradient_from_the_norm_backward():
+    """DCNConvModule under a trainer that exposes the parameters' gradient memory (GraphTrainer: ops.gemm_ops.direct_vec): the
+    bias gradient of the deformable convolution is the per-channel sum of the GroupNorm's dx and is added by the norm's
+    backward apply kernel; the convolution's own column-sum pass is skipped.  Same numbers as the autograd path."""
+    import torch
+    from lsnet_b200.modules import head as Hd
+    torch.manual_seed(12)
+    m = Hd.DCNConvModule(256, 256, 3, 1, 32, 1).cuda()
+    m.conv.conv_offset.weight.data.normal_(0, 0.02)
+    m.conv.bias.data.normal_(0, 0.5)
+    m.bn.weight.data.uniform_(0.5, 1.5)
+    x0 = torch.randn(2, 256, 25, 42, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(2, 256, 25, 42, device='cuda').to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    # reference: plain autograd accumulation
+    m.zero_grad()
+    m(x0.clone().requires_grad_(True)).backward(gy)
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    # direct mode: gradients of the 1-D parameters live in caller-owned memory the kernels add into
+    m.zero_grad()
+    for p in (m.bn.weight, m.bn.bias, m.conv.bias, m.conv.conv_offset.bias):
+        p.grad = torch.zeros_like(p)
+        p._lsnet_direct_vec = True
+    from lsnet_b200 import ops
+    assert ops.norm.bias_sink_ok(m.bn.weight, m.bn.bias, m.conv.bias)
+    m(x0.clone().requires_grad_(True)).backward(gy)
+    torch.cuda.synchronize()
+    for k in ('conv.bias', 'bn.weight', 'bn.bias', 'conv.conv_offset.bias', 'conv.weight'):
+        got, want = dict(m.named_parameters())[k].grad, ref[k]
+        assert float((got - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-2, k
+    for p in (m.bn.weight, m.bn.bias, m.conv.bias, m.conv.conv_offset.bias):
+        p._lsnet_direct_vec = False
