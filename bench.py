@@ -285,12 +285,19 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        gc.collect()             # a generation-2 collection inside the region would be timed as step time
+        # A cyclic-GC pass over this process's heap (modules, captured graphs, autograd records) takes 40-150 ms; in the
+        # e2e loop (one host synchronisation per step) a single automatic collection showed up as one 44 / 165 ms step among
+        # twenty 22.8 ms ones.  Collect before the region and keep the collector off inside it (as a training loop would).
+        gc.collect()
+        gc.disable()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for s in range(steps):
-            fn(s)
+        try:
+            for s in range(steps):
+                fn(s)
+        finally:
+            gc.enable()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

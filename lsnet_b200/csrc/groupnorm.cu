@@ -437,8 +437,14 @@ static int groupnorm_bwd_impl(const void* x, long long ldx, const void* x2, long
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, gamma, beta, ws_bstats, dgamma, dbeta,
       reinterpret_cast<unsigned*>(ws_bstats + 2 * B * G), s12);
   if (int rc = check_launch("gn_bwd_stats")) return rc;
-  gn_bwd_apply_kernel<<<gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8), GN_THREADS,
-                        dx_colsum ? sizeof(float) * C : 0, st>>>(
+  // with the column sums every block ends with C global reds onto the same C addresses: half the blocks (still four per
+  // SM) keep that tail short
+  int apply_grid = gn_grid(static_cast<long long>(B) * HW * (C / 8), C / 8);
+  if (dx_colsum && apply_grid > 148 * 4) {
+    apply_grid = 148 * 4;
+    while ((static_cast<long long>(apply_grid) * GN_THREADS) % (C / 8)) ++apply_grid;
+  }
+  gn_bwd_apply_kernel<<<apply_grid, GN_THREADS, dx_colsum ? sizeof(float) * C : 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(x2),
       static_cast<const __nv_bfloat16*>(dy), lddy, a, mr, s12, gamma, beta, static_cast<__nv_bfloat16*>(dx),
       lddx, dx_colsum);

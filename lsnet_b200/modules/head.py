@@ -67,7 +67,7 @@ class DCNConvModule(nn.Module):
         # the GroupNorm statistics come out of the deformable convolution's GEMM epilogue
         h = {} if (GN_EPILOGUE and x.is_cuda) else None
         # ... and the bias gradient of the convolution (= per-channel sum of the norm's dx) out of the norm's backward
-        ext = GN_EPILOGUE and x.is_cuda and ops.norm.bias_sink_ok(self.bn.weight, self.bn.bias, self.conv.bias)
+        ext = BIAS_SINK and x.is_cuda and ops.norm.bias_sink_ok(self.bn.weight, self.bn.bias, self.conv.bias)
         y = self.conv(x, exclusive=exclusive, gn_holder=h, gn_groups=self.bn.num_groups, skip_bias_grad=ext)
         return ops.group_norm_nhwc(y, self.bn.num_groups, self.bn.weight, self.bn.bias, self.bn.eps, relu=True,
                                    pre_sums=h.get('sums') if h else None, bias_sink=self.conv.bias if ext else None)
@@ -110,6 +110,8 @@ class PackedGT:
 
 # GroupNorm statistics of the tower layers accumulated by the deformable convolution's GEMM epilogue
 GN_EPILOGUE = os.environ.get('LSNET_GN_EPILOGUE', '1') == '1'
+# bias gradient of a tower convolution added by the backward apply kernel of the GroupNorm behind it
+BIAS_SINK = os.environ.get('LSNET_BIAS_SINK', '1') == '1'
 TOWER_STREAMS = os.environ.get('LSNET_TOWER_STREAMS', '1') == '1'
 # Every pyramid level on its own streams: the kernels of the three small levels (6 % of the pixels, 3-44 CTAs, 15-20 us
 # each) run beside each other instead of one after the other.  Measured (1xB200, B=4): all levels in one chain 29.8 ms,
