@@ -286,9 +286,14 @@ class Bottleneck(nn.Module):
 
     norm3 = property(lambda self: self.bn3)
 
+    def _all_own(self):
+        cs = [self.conv1, self.conv2, self.conv3] + ([] if self.downsample is None else [self.downsample[0]])
+        return all(_own_ok(c) for c in cs)
+
     def _fusable(self, x):
+        # (the cuDNN fused conv+bias+ReLU probe only matters for convs that are not on the library's kernels)
         return (x.is_cuda and not self.bn1.training and not self.bn2.training and not self.bn3.training
-                and isinstance(self.conv2, nn.Conv2d) and _fused_available(x))
+                and isinstance(self.conv2, nn.Conv2d) and (self._all_own() or _fused_available(x)))
 
     def _inner_fused(self, x):
         own = _own_ok(self.conv1) and _own_ok(self.conv2) and _own_ok(self.conv3) and \
@@ -306,7 +311,10 @@ class Bottleneck(nn.Module):
             in_mask = getattr(self, 'in_relu', False)
             out = conv_bn_act(x, self.conv1, self.bn1, opts=dict(mask_input=in_mask, premasked=True, x_sink=sink))
             out = conv_bn_act(out, self.conv2, self.bn2, opts=dict(mask_input=True, premasked=True))
-            o3 = dict(mask_input=True, premasked=getattr(self, 'out_premasked', False))
+            # (_rt_premasked: ResNet.forward re-checks the promise at run time -- it only holds while the NEXT block also
+            # takes this fused path)
+            o3 = dict(mask_input=True, premasked=bool(getattr(self, 'out_premasked', False) and
+                                                      getattr(self, '_rt_premasked', False)))
             if self.downsample is None:
                 return conv_bn_act(out, self.conv3, self.bn3, z=x, opts=dict(o3, z_sink=sink))
             ident = conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False,
@@ -455,7 +463,7 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         fold_ev = None
-        if x.is_cuda and not self.bn1.training and _fused_available(x):
+        if x.is_cuda and not self.bn1.training and (self._own_stem(x) or _fused_available(x)):
             if FOLD_SIDE and TRUNK == 'own':
                 fold_side = prefold(self._fold_pairs(), x.device)
                 fold_ev = True
@@ -473,6 +481,10 @@ class ResNet(nn.Module):
         else:
             x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         outs = []
+        for name in self.res_layers:      # run-time half of the backward-fusion topology (see __init__)
+            blocks = list(getattr(self, name))
+            for j, blk in enumerate(blocks):
+                blk._rt_premasked = j + 1 < len(blocks) and blocks[j + 1]._fusable(x) and not blocks[j + 1].with_cp
         for i, name in enumerate(self.res_layers):
             x = getattr(self, name)(x)
             if i in self.out_indices:
