@@ -339,7 +339,10 @@ def run_gpu(args, rank, world, local_rank):
     if not graph_mode:
         lib.lsnet_timing_reset()
     # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
-    h2d = sum(b['img'].numel() * 4 for b in host) // nb
+    if args.e2e_input == 'u8' and graph_mode:
+        host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True, task=task, multiscale=ms,
+                                canvas_multiple=128 if ms else None, u8=True) for s in range(nb)]
+    h2d = sum(b['img'].numel() * b['img'].element_size() for b in host) // nb
 
     e2e_wall = []
 
@@ -409,6 +412,8 @@ def run_gpu(args, rank, world, local_rank):
                 shapes=sorted({tuple(b['img'].shape[-2:]) for b in host}),
                 e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps,
+                         input=('uint8 HWC bytes, normalised + padded on the GPU (lsnet_image_prep_u8) inside the step'
+                                if host[0]['img'].dtype == torch.uint8 else 'normalised fp32 NCHW batch'),
                          # host wall clock of the individual steps (each ends with the loss read-back): spread of the region
                          step_wall_ms=dict(min=wall[0], median=wall[len(wall) // 2], max=wall[-1])),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, clocks=clk)
@@ -427,6 +432,9 @@ def main():
     ap.add_argument('--config', default='bbox_r50', choices=sorted(WORKLOADS),
                     help="bbox_r50 = BASELINE.json configs[1] (default, the metric's configuration); the others are "
                          'configs[2..4]')
+    ap.add_argument('--e2e-input', default='f32', choices=['f32', 'u8'],
+                    help='host image format of the e2e loop: f32 = normalised float batch (51.6 MB / step), u8 = decoded '
+                         'bytes, normalised + padded on the GPU by lsnet_image_prep_u8 inside the step (12.9 MB / step)')
     ap.add_argument('--eager', action='store_true', help='per-op eager step with torch DDP instead of the CUDA graph')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

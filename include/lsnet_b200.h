@@ -198,6 +198,17 @@ int lsnet_upsample_add_nhwc_bf16(const void* fine, long long ldf, const void* co
 int lsnet_upsample_add_bwd_nhwc_bf16(const void* g, long long ldg, int B, int Hf, int Wf, int Hc, int Wc, int C, void* gc,
                                      long long ldgc, void* stream);
 
+/* ---- input side -------------------------------------------------------------------------------------
+ * Normalize -> Pad(size_divisor) -> DefaultFormatBundle -> collate of the reference's train pipeline in one pass
+ * (mmdet/datasets/pipelines/transforms.py:463-570, formating.py:209-215, mmcv/mmcv/image/photometric.py:21-41,
+ * mmcv/mmcv/parallel/collate.py:39-60).  src: uint8 [B, H, W, 3] (decoded / resized / flipped BGR images, top-left
+ * aligned on a common canvas, W % 4 == 0); hw: device int32 [B][2] = each image's own (height, width);
+ * dst: fp32 [B, H, W, 3] (the NHWC memory of a channels_last [B, 3, H, W] tensor, what lsnet_stem_conv reads):
+ * dst[b,y,x,c] = float((double(src[b,y,x, to_rgb ? 2-c : c]) - mean[c]) * stdinv[c]) inside the image, 0 in the padding
+ * (double arithmetic, one rounding: bit-identical to the reference's cv2.subtract / cv2.multiply). */
+int lsnet_image_prep_u8(const void* src_u8, const int* hw, int B, int H, int W, double mean0, double mean1, double mean2,
+                        double stdinv0, double stdinv1, double stdinv2, int to_rgb, void* dst_f32, void* stream);
+
 /* ---- deformable convolution sampling ---------------------------------------------------------------------------
  * One family for DCNv1 (mask NULL), DCNv2 (mask) and LSNet's pyramid DCN (scale_h/scale_w, input extent (H,W)
  * decoupled from the sampling grid (Ho,Wo)).  x: NHWC bf16; offset: fp32 [B*Ho*Wo, ldo], channel

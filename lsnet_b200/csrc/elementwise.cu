@@ -647,3 +647,65 @@ extern "C" int lsnet_upsample_add_bwd_nhwc_bf16(const void* g, long long ldg, in
       static_cast<const __nv_bfloat16*>(g), ldg, B, Hf, Wf, Hc, Wc, C, static_cast<__nv_bfloat16*>(gc), ldgc);
   return lsn::check_launch("upsample_add_bwd");
 }
+
+// ---- input side: Normalize + Pad + to-tensor of the train pipeline in one pass ----------------------------------------
+namespace lsn {
+// Thread = 4 consecutive pixels of one row: 12 input bytes (3 aligned 32-bit loads, W % 4 == 0) -> 12 floats (3 float4
+// stores); a warp reads 384 and writes 1536 contiguous bytes.  Pixels beyond an image's own (h, w) are written as 0 —
+// the pad value of the normalised image — whatever the staging buffer holds there.
+__global__ void image_prep_u8_kernel(const uint32_t* __restrict__ src, const int* __restrict__ hw, int B, int H, int W,
+                                     double m0, double m1, double m2, double s0, double s1, double s2, int to_rgb,
+                                     float4* __restrict__ dst) {
+  const int qpr = W / 4;
+  const long long n = static_cast<long long>(B) * H * qpr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int q = static_cast<int>(i % qpr);
+    long long r = i / qpr;
+    const int y = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    const int h = __ldg(hw + 2 * b), w = __ldg(hw + 2 * b + 1);
+    float o[12];
+    if (y < h && 4 * q < w) {
+      const uint32_t a0 = __ldg(src + 3 * i), a1 = __ldg(src + 3 * i + 1), a2 = __ldg(src + 3 * i + 2);
+      float v[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = static_cast<float>((a0 >> (8 * k)) & 0xffu);
+        v[4 + k] = static_cast<float>((a1 >> (8 * k)) & 0xffu);
+        v[8 + k] = static_cast<float>((a2 >> (8 * k)) & 0xffu);
+      }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int px = k / 3, ch = k % 3;                       // output channel ch of pixel px
+        const float x = to_rgb ? v[px * 3 + 2 - ch] : v[px * 3 + ch];
+        const double m = ch == 0 ? m0 : (ch == 1 ? m1 : m2), s = ch == 0 ? s0 : (ch == 1 ? s1 : s2);
+        // double arithmetic, one rounding to float: bit-identical to cv2.subtract / cv2.multiply with float64 scalars
+        o[k] = (4 * q + px < w) ? static_cast<float>(__dmul_rn(__dsub_rn(static_cast<double>(x), m), s)) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) o[k] = 0.f;
+    }
+    float4* d = dst + 3 * i;
+    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    d[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+}
+}  // namespace lsn
+
+extern "C" int lsnet_image_prep_u8(const void* src_u8, const int* hw, int B, int H, int W, double mean0, double mean1,
+                                   double mean2, double stdinv0, double stdinv1, double stdinv2, int to_rgb,
+                                   void* dst_f32, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  if (W % 4) return lsn::set_error("lsnet_image_prep_u8: W %% 4 == 0 required (the canvas is padded to a multiple of 32)");
+  if ((reinterpret_cast<uintptr_t>(src_u8) & 3) || (reinterpret_cast<uintptr_t>(dst_f32) & 15))
+    return lsn::set_error("lsnet_image_prep_u8: 4-byte aligned source / 16-byte aligned destination required");
+  const long long n = static_cast<long long>(B) * H * (W / 4);
+  const int grid = static_cast<int>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  lsn::image_prep_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint32_t*>(src_u8), hw, B, H, W, mean0, mean1, mean2, stdinv0, stdinv1, stdinv2, to_rgb,
+      static_cast<float4*>(dst_f32));
+  return lsn::check_launch("image_prep_u8");
+}

@@ -123,14 +123,19 @@ def ms_size(rng, short_range=(480, 960), long_max=1333, aspect=4 / 3):
     return int(round(scale)), int(round(scale * aspect))
 
 
+#: img_norm_cfg of every LSNet config (configs/_base_/datasets/coco_lsvr.py:3-4)
+IMG_NORM_CFG = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
+
+
 def synthetic_batch(step, rank=0, batch=4, img_hw=(800, 1333), divisor=32, task='bbox', pin=False, multiscale=None,
-                    canvas_multiple=None):
+                    canvas_multiple=None, u8=False):
     """One per-GPU batch: dict(img [B,3,Hp,Wp] fp32, img_metas, gt_bboxes, gt_labels, + task ground truth:
     'bbox' gt_extremes (G,10); 'segm' gt_masks = (G,74) contour tables (LSHead.process_polygons accepts them) and
     gt_bboxes = contour extents; 'pose_bbox' gt_keypoints (G,51), labels 0).
     ``multiscale=(lo, hi)``: every image gets its own size (short side in [lo, hi], collate pads to the largest,
     mmcv/parallel/collate.py:39-60); ``canvas_multiple`` additionally rounds the canvas up (shape buckets of the CUDA-graph
-    cache)."""
+    cache).  ``u8``: the image is the uint8 [B, Hp, Wp, 3] byte batch of the device-prep pipeline
+    (datasets.loader.collate) with ``img_hw`` / ``img_norm_cfg``; the trainer normalises it on the GPU."""
     rng = np.random.RandomState(1234 + 8 * step + rank)
     sizes = [ms_size(rng, multiscale) if multiscale else tuple(img_hw) for _ in range(batch)]
     pads = [((h + divisor - 1) // divisor * divisor, (w + divisor - 1) // divisor * divisor) for h, w in sizes]
@@ -138,7 +143,7 @@ def synthetic_batch(step, rank=0, batch=4, img_hw=(800, 1333), divisor=32, task=
     if canvas_multiple:
         Hp = (Hp + canvas_multiple - 1) // canvas_multiple * canvas_multiple
         Wp = (Wp + canvas_multiple - 1) // canvas_multiple * canvas_multiple
-    img = np.zeros((batch, 3, Hp, Wp), np.float32)
+    img = np.zeros((batch, Hp, Wp, 3), np.uint8) if u8 else np.zeros((batch, 3, Hp, Wp), np.float32)
     out = dict(gt_bboxes=[], gt_labels=[])
     if task == 'bbox':
         out['gt_extremes'] = []
@@ -149,7 +154,10 @@ def synthetic_batch(step, rank=0, batch=4, img_hw=(800, 1333), divisor=32, task=
     else:
         raise ValueError(task)
     for i, (H, W) in enumerate(sizes):
-        img[i, :, :H, :W] = rng.rand(3, H, W).astype(np.float32)
+        if u8:
+            img[i, :H, :W] = rng.randint(0, 256, (H, W, 3), dtype=np.uint8)
+        else:
+            img[i, :, :H, :W] = rng.rand(3, H, W).astype(np.float32)
         b = _boxes(rng, rng.randint(1, 16), H, W)
         labels = rng.randint(0, 80, len(b)).astype(np.int64)
         if task == 'bbox':
@@ -168,6 +176,11 @@ def synthetic_batch(step, rank=0, batch=4, img_hw=(800, 1333), divisor=32, task=
     out['img'] = img
     out['img_metas'] = [dict(img_shape=(H, W, 3), pad_shape=(ph, pw, 3), scale_factor=1.0, flip=False)
                         for (H, W), (ph, pw) in zip(sizes, pads)]
+    if u8:
+        out['img_hw'] = torch.tensor([[H, W] for H, W in sizes], dtype=torch.int32)
+        out['img_norm_cfg'] = IMG_NORM_CFG
+        if pin:
+            out['img_hw'] = out['img_hw'].pin_memory()
     return out
 
 

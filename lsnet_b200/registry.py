@@ -90,6 +90,8 @@ DETECTORS = Registry('detector')
 BBOX_ASSIGNERS = Registry('bbox_assigner')
 BBOX_SAMPLERS = Registry('bbox_sampler')
 CONV_LAYERS = Registry('conv layer')
+DATASETS = Registry('dataset')          # mmdet/datasets/builder.py:10-11
+PIPELINES = Registry('pipeline')
 
 
 def build(cfg, registry, default_args=None):

@@ -203,6 +203,33 @@ class GraphTrainer:
     def launches_per_step(self):
         return self.cur.launches
 
+    @staticmethod
+    def _canvas(batch):
+        """Shape key of a batch: [B, 3, H, W] for float images and for the uint8 [B, H, W, 3] batches of the
+        device-prep pipeline (datasets.loader.collate) alike."""
+        im = batch['img']
+        if im.dtype == torch.uint8:
+            return (im.shape[0], 3, im.shape[1], im.shape[2])
+        return tuple(im.shape)
+
+    def _stage_image(self, st, batch, src=None, hw=None):
+        """Refresh the static input image of ``st``: float batches are copied; uint8 batches are uploaded as bytes and
+        normalised / zero-padded by ``lsnet_image_prep_u8`` straight into the static buffer (``src`` / ``hw``: device
+        staging tensors a prefetch already filled)."""
+        im = batch['img']
+        if im.dtype != torch.uint8:
+            st.img.copy_(im if src is None else src, non_blocking=True)
+            return
+        if src is None:
+            if getattr(st, 'u8', None) is None:
+                st.u8 = torch.empty(im.shape, device=self.device, dtype=torch.uint8)
+                st.hw = torch.empty((im.shape[0], 2), device=self.device, dtype=torch.int32)
+            st.u8.copy_(im, non_blocking=True)
+            st.hw.copy_(batch['img_hw'], non_blocking=True)
+            src, hw = st.u8, st.hw
+        from .datasets.loader import DevicePrep
+        DevicePrep(self.device).run(src, hw, batch['img_norm_cfg'], out=st.img)
+
     def _gt_kwargs(self, batch):
         return dict(gt_extremes=batch.get('gt_extremes'), gt_keypoints_vs=batch.get('gt_keypoints'),
                     gt_masks=batch.get('gt_masks'))
@@ -231,7 +258,7 @@ class GraphTrainer:
 
     def _entry(self, batch):
         self._ensure_capacity(batch)
-        key = tuple(batch['img'].shape)
+        key = self._canvas(batch)
         st = self.steps.get(key)
         if st is None:
             if len(self.steps) >= self.max_graphs:          # drop the least recently used shape
@@ -245,12 +272,13 @@ class GraphTrainer:
     def _capture(self, batch):
         from .ops import gemm_ops
         st = GraphTrainer._Step()
+        st.img = torch.empty(self._canvas(batch), device=self.device, dtype=torch.float32).contiguous(
+            memory_format=torch.channels_last)
+        self._stage_image(st, batch)
         with torch.no_grad():          # pyramid geometry of this input size
-            feats = self.core.extract_feat(batch['img'][:1].to(self.device))
+            feats = self.core.extract_feat(st.img[:1])
         st.sizes = [tuple(f.shape[-2:]) for f in feats]
         del feats
-        st.img = torch.empty_like(batch['img'], device=self.device).contiguous(memory_format=torch.channels_last)
-        st.img.copy_(batch['img'].to(self.device))
         st.metas = batch['img_metas']
         head = self.core.bbox_head
         st.gt = head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes, self.device,
@@ -320,7 +348,7 @@ class GraphTrainer:
         cudaHostAlloc), guarded by an event each."""
         st = self.cur = self._entry(batch)
         head = self.core.bbox_head
-        st.img.copy_(batch['img'], non_blocking=True)
+        self._stage_image(st, batch)
         if st.stage is None:
             st.stage, st.stage_ev, st.stage_i = [], [], 0
             for _ in range(2):
@@ -345,8 +373,12 @@ class GraphTrainer:
         st = self._entry(batch)
         if not hasattr(self, '_copy_stream'):
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        if getattr(st, 'pre_img', None) is None:
-            st.pre_img = torch.empty_like(st.img)
+        u8 = batch['img'].dtype == torch.uint8
+        if getattr(st, 'pre_img', None) is None or (st.pre_img.dtype == torch.uint8) != u8:
+            # float batches stage the image itself, uint8 batches the bytes + extents (normalised on arrival)
+            st.pre_img = torch.empty(batch['img'].shape, device=self.device, dtype=torch.uint8) if u8 else \
+                torch.empty_like(st.img)
+            st.pre_hw = torch.empty((batch['img'].shape[0], 2), device=self.device, dtype=torch.int32) if u8 else None
             st.pre_gt = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes,
                                                     self.device, capacity=self.capacity, **self._gt_kwargs(batch))
             st.pre_pin = self.core.bbox_head.pack_gt(batch['gt_bboxes'], batch['gt_labels'], batch['img_metas'], st.sizes,
@@ -361,6 +393,8 @@ class GraphTrainer:
         cs = self._copy_stream                # (pre_done above already guarantees nobody still reads the staging buffers)
         with torch.cuda.stream(cs):
             st.pre_img.copy_(batch['img'], non_blocking=True)
+            if u8:
+                st.pre_hw.copy_(batch['img_hw'], non_blocking=True)
             st.pre_gt.copy_from(st.pre_pin)
             st.pre_ev.record(cs)
         st.pre_batch = batch
@@ -368,13 +402,13 @@ class GraphTrainer:
     def step(self, batch=None, sync_log=False, next_batch=None):
         """One training iteration.  ``next_batch``: prefetch it (host -> device on a copy stream) while this step runs."""
         if batch is not None:
-            st = self.steps.get(tuple(batch['img'].shape))
+            st = self.steps.get(self._canvas(batch))
             if st is not None and getattr(st, 'pre_batch', None) is batch:
                 # prefetched: wait for the copy stream, staging -> static inputs on the device
                 self.cur = st
                 st.last_use = self.iter
                 torch.cuda.current_stream(self.device).wait_event(st.pre_ev)
-                st.img.copy_(st.pre_img, non_blocking=True)
+                self._stage_image(st, batch, src=st.pre_img, hw=st.pre_hw)
                 st.gt.copy_from(st.pre_gt)
                 st.pre_done.record()
                 st.pre_batch = None

@@ -1,0 +1,100 @@
+"""GPU half of the input side: ``lsnet_image_prep_u8`` through the C ABI against (a) the recorded output
+of the reference's Normalize -> Pad -> DefaultFormatBundle -> collate (tests/golden/datapath.npz) and (b) its numpy
+restatement on mixed-size batches; then uint8 batches through ``GraphTrainer`` (direct and prefetched)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+
+pytestmark = pytest.mark.gpu
+
+
+def _numpy_prep(u8, hw, cfg):
+    from lsnet_b200.datasets import DevicePrep
+    mean, stdinv = DevicePrep.constants(cfg)
+    x = u8[..., ::-1] if cfg.get('to_rgb', True) else u8
+    out = ((x.astype(np.float64) - np.array(mean)) * np.array(stdinv)).astype(np.float32)
+    for k, (h, w) in enumerate(hw):
+        out[k, h:] = 0
+        out[k, :, w:] = 0
+    return out
+
+
+def test_image_prep_matches_reference_pipeline_bit_exact():
+    import synth_coco as S
+    import test_datasets_host as T
+    from lsnet_b200.datasets import DevicePrep, loader
+    dev_ds = T._dataset('bbox', True, pipe=loader.device_prep_pipeline(S.pipeline('bbox', True)))
+    prep = DevicePrep('cuda')
+    for ids in ([0, 3], [1, 4, 2], [5]):
+        batch = loader.collate([T._run(dev_ds, i, 1) for i in ids])
+        out = prep(batch)
+        img = out['img']
+        assert img.is_cuda and img.dtype == torch.float32 and img.is_contiguous(memory_format=torch.channels_last)
+        got = img.cpu().numpy()                                   # logical [B, 3, H, W]
+        for k, i in enumerate(ids):
+            ref = T.G[f'pipe_bbox_1_{i}_img']                     # reference: normalised, padded to 32, CHW
+            assert np.array_equal(got[k, :, :ref.shape[1], :ref.shape[2]], ref)
+            assert not got[k, :, ref.shape[1]:].any() and not got[k, :, :, ref.shape[2]:].any()
+
+
+@pytest.mark.parametrize('to_rgb', [True, False])
+def test_image_prep_mixed_sizes_ignores_staging_garbage(to_rgb):
+    from lsnet_b200.datasets import DevicePrep
+    rng = np.random.RandomState(0)
+    B, H, W = 3, 96, 160
+    u8 = rng.randint(0, 256, (B, H, W, 3), dtype=np.uint8)        # bytes everywhere: the padding must still come out 0
+    hw = [[96, 160], [70, 131], [1, 3]]
+    cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=to_rgb)
+    out = DevicePrep('cuda').run(torch.from_numpy(u8).cuda(), torch.tensor(hw, dtype=torch.int32).cuda(), cfg)
+    got = out.permute(0, 2, 3, 1).cpu().numpy()
+    assert np.array_equal(got, _numpy_prep(u8, hw, cfg))
+
+
+def test_image_prep_rejects_unaligned_width():
+    from lsnet_b200 import lib as L
+    from lsnet_b200.datasets import DevicePrep
+    with pytest.raises(L.LsnetError):
+        DevicePrep('cuda').run(torch.zeros((1, 8, 6, 3), dtype=torch.uint8).cuda(),
+                               torch.tensor([[8, 6]], dtype=torch.int32).cuda(),
+                               dict(mean=[0, 0, 0], std=[1, 1, 1], to_rgb=False))
+
+
+def test_graph_trainer_takes_uint8_batches():
+    """A uint8 batch and the float batch the reference pipeline would have made of it give the same static input image
+    and the same loss; the prefetched route stages bytes and normalises on arrival."""
+    from lsnet_b200.data import MODEL_CFG, synthetic_batch
+    from lsnet_b200.train import GraphTrainer
+    bu = [synthetic_batch(s, batch=2, img_hw=(320, 416), u8=True, pin=True) for s in range(3)]
+    bf = []
+    for b in bu:
+        f = dict(b)
+        img = _numpy_prep(b['img'].numpy(), b['img_hw'].tolist(), b['img_norm_cfg'])
+        f['img'] = torch.from_numpy(np.ascontiguousarray(img.transpose(0, 3, 1, 2)))
+        f.pop('img_hw'); f.pop('img_norm_cfg')
+        bf.append(f)
+    torch.manual_seed(0)
+    tr = GraphTrainer(MODEL_CFG['bbox_r50'], bu[0])
+    sd = {k: v.clone() for k, v in tr.core.state_dict().items()}
+
+    def run(batch, nxt=None):
+        tr.core.load_state_dict(sd)
+        tr.flat_m.zero_()
+        loss = float(tr.step(batch, next_batch=nxt)[0])
+        torch.cuda.synchronize()
+        return loss, tr.cur.img.clone()
+    lu, iu = run(bu[0])
+    lf, i_f = run(bf[0])
+    assert torch.equal(iu, i_f)                      # the kernel wrote exactly the reference pipeline's image
+    assert abs(lu - lf) < 2e-3 * abs(lf), (lu, lf)   # same input; the forward's own run-to-run noise (atomics) remains
+    # prefetched: step(b0, next=b1) uploads b1's bytes on the copy stream; step(b1) normalises them from the staging buffer
+    run(bu[0], nxt=bu[1])
+    assert tr.steps[tr._canvas(bu[1])].pre_batch is bu[1]
+    lp, ip = run(bu[1])
+    _, i1 = run(bf[1])
+    assert torch.equal(ip, i1) and np.isfinite(lp)
