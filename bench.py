@@ -340,8 +340,9 @@ def run_gpu(args, rank, world, local_rank):
         lib.lsnet_timing_reset()
     # ---- e2e: host (pinned) inputs -> H2D every step, loss read back every step ----
     if args.e2e_input == 'u8' and graph_mode:
-        host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True, task=task, multiscale=ms,
-                                canvas_multiple=128 if ms else None, u8=True) for s in range(nb)]
+        mscale = WORKLOADS[cfg_name]['multiscale']
+        host = [synthetic_batch(s, rank, BATCH, IMG_HW, pin=True, task=task, multiscale=mscale,
+                                canvas_multiple=128 if mscale else None, u8=True) for s in range(nb)]
     h2d = sum(b['img'].numel() * b['img'].element_size() for b in host) // nb
 
     e2e_wall = []
@@ -432,7 +433,7 @@ def main():
     ap.add_argument('--config', default='bbox_r50', choices=sorted(WORKLOADS),
                     help="bbox_r50 = BASELINE.json configs[1] (default, the metric's configuration); the others are "
                          'configs[2..4]')
-    ap.add_argument('--e2e-input', default='f32', choices=['f32', 'u8'],
+    ap.add_argument('--e2e-input', default='u8', choices=['f32', 'u8'],
                     help='host image format of the e2e loop: f32 = normalised float batch (51.6 MB / step), u8 = decoded '
                          'bytes, normalised + padded on the GPU by lsnet_image_prep_u8 inside the step (12.9 MB / step)')
     ap.add_argument('--eager', action='store_true', help='per-op eager step with torch DDP instead of the CUDA graph')
