@@ -150,7 +150,7 @@ def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist
                      rank=None, world_size=None, pin=False, **kwargs):
     """builder.py:68-127.  One process per GPU: ``dist=True`` gives this rank's share through
     ``DistributedGroupSampler``; ``num_gpus`` other than 1 (the reference's single-process DataParallel mode) is not
-    supported."""
+    supported.  ``rank`` / ``world_size`` default to the initialised process group (mmcv ``get_dist_info``)."""
     if rank is None or world_size is None:
         import torch.distributed as td
         on = td.is_available() and td.is_initialized()
@@ -166,8 +166,11 @@ def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist
     else:
         sampler = GroupSampler(dataset, samples_per_gpu) if shuffle else None
     init = partial(worker_init_fn, num_workers=workers_per_gpu, rank=rank, seed=seed) if seed is not None else None
+    # pin=True: the DataLoader's pin thread of THIS process page-locks the collated tensors (the workers must not touch
+    # CUDA), which is what lets GraphTrainer.prefetch copy the next batch asynchronously; the reference keeps
+    # pin_memory=False and copies synchronously in scatter (mmcv/parallel/scatter_gather.py)
     return DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, num_workers=workers_per_gpu,
-                      collate_fn=partial(collate, pin=pin), pin_memory=False, worker_init_fn=init, **kwargs)
+                      collate_fn=collate, pin_memory=bool(pin), worker_init_fn=init, **kwargs)
 
 
 class DevicePrep:

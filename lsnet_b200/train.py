@@ -441,3 +441,40 @@ class GraphTrainer:
                 dist.all_reduce(flat.div_(dist.get_world_size()))
             log = dict(zip(log.keys(), flat.tolist()))
         return loss, log
+
+
+def train_epochs(trainer, loader, epochs=1, start_epoch=0, on_step=None):
+    """The inner loops of the reference's ``EpochBasedRunner.run`` / ``train`` (mmcv/mmcv/runner/epoch_based_runner.py:
+    25-44, 62-100) for a ``GraphTrainer`` (or ``Trainer``) fed by ``datasets.build_dataloader``: per epoch
+    ``sampler.set_epoch`` (DistSamplerSeedHook, mmcv/runner/hooks/sampler_seed.py), then one step per batch.  With a
+    GraphTrainer every step also starts the upload of the FOLLOWING batch on the copy stream (one batch of look-ahead),
+    so the host-to-device copy of step i+1 overlaps the compute of step i.  ``on_step(epoch, i, loss, log_vars)`` is
+    the logging hook; returns the number of steps run."""
+    graph = hasattr(trainer, 'prefetch')
+    n = 0
+    for epoch in range(start_epoch, start_epoch + epochs):
+        sampler = getattr(loader, 'sampler', None)
+        if hasattr(sampler, 'set_epoch'):
+            sampler.set_epoch(epoch)
+        it = iter(loader)
+        cur = next(it, None)
+        i = 0
+        while cur is not None:
+            nxt = next(it, None)
+            if graph:
+                loss, log = trainer.step(cur, next_batch=nxt)
+            else:
+                b = dict(cur)
+                if b['img'].dtype == torch.uint8:       # device-prep batches: normalise + pad on the GPU
+                    from .datasets.loader import DevicePrep
+                    b = DevicePrep(trainer.device)(b)
+                    b.pop('img_hw'), b.pop('img_norm_cfg')
+                else:
+                    b['img'] = b['img'].to(trainer.device, non_blocking=True)
+                loss, log = trainer.step(b)
+            if on_step is not None:
+                on_step(epoch, i, loss, log)
+            cur = nxt
+            i += 1
+            n += 1
+    return n

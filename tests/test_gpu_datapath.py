@@ -102,3 +102,42 @@ def test_graph_trainer_takes_uint8_batches():
     lp, ip = run(bu[1])
     _, i1 = run(bf[1])
     assert torch.equal(ip, i1) and np.isfinite(lp)
+
+
+@pytest.mark.parametrize('task,device_prep', [('segm', False), ('pose_bbox', True)])
+def test_files_to_training_steps(tmp_path, task, device_prep):
+    """Image files + a COCO json -> DataLoader (reference pipeline, or its device-prep rewrite) -> ``train_epochs`` ->
+    GraphTrainer steps with one batch of look-ahead: every step's loss is finite and the parameters move."""
+    import cv2
+    import synth_coco as S
+    from lsnet_b200 import datasets as D
+    from lsnet_b200.data import MODEL_CFG
+    from lsnet_b200.registry import DATASETS
+    from lsnet_b200.train import GraphTrainer, train_epochs
+    for i in range(len(S.SIZES)):
+        cv2.imwrite(str(tmp_path / f'img_{i}.png'), S.image(i))
+    pipe = [dict(type='LoadImageFromFile')] + S.pipeline(task, multiscale=False)
+    for t in pipe:
+        if t['type'] == 'Resize':
+            t['img_scale'] = (640, 384)
+    if device_prep:
+        pipe = D.device_prep_pipeline(pipe)
+    pose = task == 'pose_bbox'
+    ds = DATASETS.get('CocoPoseDataset' if pose else 'CocoDataset')(
+        ann_file=S.coco_dict(pose), pipeline=pipe, img_prefix=str(tmp_path))
+    dl = D.build_dataloader(ds, samples_per_gpu=3, workers_per_gpu=2, dist=False, seed=1, pin=True)
+    cfg = MODEL_CFG[{'bbox': 'bbox_r50', 'segm': 'segm_r50', 'pose_bbox': 'pose_x101dcn'}[task]]
+    if pose:        # the R50 trunk keeps the test short; the pose head is what the keypoint batches exercise
+        cfg = dict(cfg, model=dict(cfg['model'], backbone=MODEL_CFG['bbox_r50']['model']['backbone']))
+    np.random.seed(0)
+    first = next(iter(dl))
+    assert first['img'].is_pinned() and (first['img'].dtype == torch.uint8) == device_prep
+    torch.manual_seed(0)
+    tr = GraphTrainer(cfg, first, capacity=16)
+    before = tr.flat_p.clone()
+    losses = []
+    n = train_epochs(tr, dl, epochs=1, on_step=lambda e, i, loss, log: losses.append(loss.clone()))
+    torch.cuda.synchronize()
+    assert n == len(dl) == 2 and all(bool(torch.isfinite(l)) for l in losses)      # one batch per aspect-ratio group
+    assert float((tr.flat_p - before).abs().max()) > 0
+    assert len(tr.steps) == 2                     # a landscape and a portrait canvas: one captured step each
