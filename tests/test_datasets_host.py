@@ -228,3 +228,30 @@ def test_dataloader_end_to_end(tmp_path):
                           gt_masks=batch['gt_masks'])
         assert gt.tables['segm'].shape == (2, 16, 74) and gt.count.tolist() == [len(b) for b in batch['gt_bboxes']]
     assert n == 4            # 3 landscape + 3 portrait/square images, each group padded to whole batches
+
+
+REF_CFGS = '/root/reference/code/configs/lsnet'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFGS), reason='reference tree not present')
+def test_reference_configs_resolve_their_train_pipelines():
+    """``cfg.data.train`` of every LSNet config (the two CPV variants use RepPointsV2 loaders: out of scope)
+    names a registered dataset and a pipeline that builds unchanged — and its device-prep rewrite too."""
+    import glob
+    from lsnet_b200 import Config
+    n = 0
+    for f in sorted(glob.glob(os.path.join(REF_CFGS, '*.py'))):
+        cfg = Config.fromfile(f)
+        if cfg.model.bbox_head.type != 'LSHead':
+            continue
+        tr = cfg.data.train
+        assert tr.type in DATASETS, (f, tr.type)
+        pipe = D.Compose(tr.pipeline)
+        assert [type(t).__name__ for t in pipe.transforms] == [t['type'] for t in tr.pipeline]
+        dev = D.Compose(D.device_prep_pipeline(tr.pipeline))
+        assert type(dev.transforms[-2]).__name__ == 'DeviceFormatBundle'
+        if 'mstrain' in f:
+            rs = [t for t in pipe.transforms if isinstance(t, D.Resize)][0]
+            assert len(rs.img_scale) == 2 and rs.multiscale_mode == 'range'
+        n += 1
+    assert n == 15
