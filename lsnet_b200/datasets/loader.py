@@ -89,16 +89,22 @@ class DistributedGroupSampler(Sampler):
         self.epoch = epoch
 
 
-def collate(samples, pin=False):
+def collate(samples, pin=False, canvas_multiple=None):
     """collate.py:39-60 for one GPU's samples.  ``img`` CHW float tensors are zero-padded bottom/right to the batch
     maximum and stacked -> [B, 3, H, W]; uint8 HWC images of the device-prep pipeline are padded the same way ->
     [B, H, W, 3] with their valid extents in ``img_hw`` (the canvas is then the padded extents' maximum, exactly the
-    stack of per-image ``Pad(size_divisor)`` results).  Everything else is a per-image list."""
+    stack of per-image ``Pad(size_divisor)`` results).  Everything else is a per-image list.
+    ``canvas_multiple`` (not in the reference) rounds the batch canvas up to that multiple: with real COCO aspect
+    ratios every multiple of 32 occurs as a canvas side, and ``GraphTrainer`` captures one CUDA graph per canvas —
+    buckets of 128 keep that to a handful; each image's valid extent stays exact in ``img_metas['pad_shape']``, which
+    is what the head's point validity uses (lsnet_head.py:770-779)."""
+    def up(v):
+        return v if not canvas_multiple else -(-v // canvas_multiple) * canvas_multiple
     out = {k: [s[k] for s in samples] for k in samples[0] if k != 'img'}
     imgs = [s['img'] for s in samples]
     if imgs[0].dtype == torch.uint8:
         pads = [m['pad_shape'] for m in out['img_metas']]
-        H, W = max(p[0] for p in pads), max(p[1] for p in pads)
+        H, W = up(max(p[0] for p in pads)), up(max(p[1] for p in pads))
         batch = torch.zeros((len(imgs), H, W, 3), dtype=torch.uint8)
         for i, im in enumerate(imgs):
             batch[i, :im.shape[0], :im.shape[1]] = im
@@ -106,7 +112,7 @@ def collate(samples, pin=False):
         cfg = out['img_metas'][0]['img_norm_cfg']
         out['img_norm_cfg'] = cfg
     else:
-        H, W = max(im.shape[-2] for im in imgs), max(im.shape[-1] for im in imgs)
+        H, W = up(max(im.shape[-2] for im in imgs)), up(max(im.shape[-1] for im in imgs))
         batch = imgs[0].new_zeros((len(imgs), imgs[0].shape[0], H, W))
         for i, im in enumerate(imgs):
             batch[i, :, :im.shape[-2], :im.shape[-1]] = im
@@ -147,10 +153,11 @@ def device_prep_pipeline(pipeline):
 
 
 def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist=True, shuffle=True, seed=None,
-                     rank=None, world_size=None, pin=False, **kwargs):
+                     rank=None, world_size=None, pin=False, canvas_multiple=None, **kwargs):
     """builder.py:68-127.  One process per GPU: ``dist=True`` gives this rank's share through
     ``DistributedGroupSampler``; ``num_gpus`` other than 1 (the reference's single-process DataParallel mode) is not
-    supported.  ``rank`` / ``world_size`` default to the initialised process group (mmcv ``get_dist_info``)."""
+    supported.  ``rank`` / ``world_size`` default to the initialised process group (mmcv ``get_dist_info``);
+    ``canvas_multiple``: see ``collate``."""
     if rank is None or world_size is None:
         import torch.distributed as td
         on = td.is_available() and td.is_initialized()
@@ -170,7 +177,8 @@ def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist
     # CUDA), which is what lets GraphTrainer.prefetch copy the next batch asynchronously; the reference keeps
     # pin_memory=False and copies synchronously in scatter (mmcv/parallel/scatter_gather.py)
     return DataLoader(dataset, batch_size=samples_per_gpu, sampler=sampler, num_workers=workers_per_gpu,
-                      collate_fn=collate, pin_memory=bool(pin), worker_init_fn=init, **kwargs)
+                      collate_fn=partial(collate, canvas_multiple=canvas_multiple), pin_memory=bool(pin),
+                      worker_init_fn=init, **kwargs)
 
 
 class DevicePrep:

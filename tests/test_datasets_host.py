@@ -149,6 +149,21 @@ def test_collate_matches_reference():
         assert len(b['gt_bboxes']) == len(ids) and len(b['img_metas']) == len(ids)
 
 
+def test_collate_canvas_buckets_keep_valid_extents():
+    ds = _dataset('bbox', True)
+    dev = _dataset('bbox', True, pipe=loader.device_prep_pipeline(S.pipeline('bbox', True)))
+    for d in (ds, dev):
+        plain = loader.collate([_run(d, i, 1) for i in (1, 4, 2)])
+        b = loader.collate([_run(d, i, 1) for i in (1, 4, 2)], canvas_multiple=128)
+        hw = (b['img'].shape[1:3] if b['img'].dtype == torch.uint8 else b['img'].shape[2:])
+        assert hw[0] % 128 == 0 and hw[1] % 128 == 0
+        assert [m['pad_shape'] for m in b['img_metas']] == [m['pad_shape'] for m in plain['img_metas']]
+        ph, pw = (plain['img'].shape[1:3] if plain['img'].dtype == torch.uint8 else plain['img'].shape[2:])
+        crop = b['img'][:, :ph, :pw] if b['img'].dtype == torch.uint8 else b['img'][:, :, :ph, :pw]
+        assert torch.equal(crop, plain['img'])
+        assert int((b['img'] != 0).sum()) == int((plain['img'] != 0).sum())          # the extra canvas is zero
+
+
 def test_group_samplers_match_reference():
     flag = np.array([1, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 1, 0], np.uint8)
     ds = types.SimpleNamespace(flag=flag)
