@@ -27,6 +27,10 @@
 
 namespace lsn {
 
+#ifndef LSN_FHFMA
+#define LSN_FHFMA 1      // dOffset / dMask dot products on FHFMA.BF16 (0: unpack + FFMA2, the A/B build)
+#endif
+
 constexpr int ADJ_THREADS = 256;
 constexpr int ADJ_GROUPS = ADJ_THREADS / 8;     // 32 lane groups of 8
 constexpr int ADJ_TAPS = 9;
@@ -227,16 +231,25 @@ dcn_adjoint_tma_kernel(const __grid_constant__ CUtensorMap tmCol, const __nv_bfl
     xs[2] = ldg128_at(xc, c_.z, ldxb);                                                \
     xs[3] = ldg128_at(xc, c_.w, ldxb);                                                \
   }
-      // 4 dot products of 8 channels each, folded over the 8 lanes of the group with 4 shuffles (transposed butterfly:
-      // lanes 0-1 end with corner 0, 2-3 with corner 1, ...), then one lane per corner adds into the shared table
-#define LSN_ADJ_DOT(dc, xs, t)                                                        \
+#if LSN_FHFMA
+#define LSN_ADJ_DOT4(dc, xs, d_) \
+  _Pragma("unroll") for (int q_ = 0; q_ < 4; ++q_) d_[q_] = dot8_bf16(dc, xs[q_]);
+#else
+#define LSN_ADJ_DOT4(dc, xs, d_)                                                      \
   {                                                                                   \
     const float2 ga_[4] = {bf16x2_f2(dc.x), bf16x2_f2(dc.y), bf16x2_f2(dc.z), bf16x2_f2(dc.w)}; \
-    float d_[4];                                                                      \
     _Pragma("unroll") for (int q_ = 0; q_ < 4; ++q_) {                                \
       const float2 t_ = dot_acc(ga_, xs[q_]);                                         \
       d_[q_] = t_.x + t_.y;                                                           \
     }                                                                                 \
+  }
+#endif
+      // 4 dot products of 8 channels each, folded over the 8 lanes of the group with 4 shuffles (transposed butterfly:
+      // lanes 0-1 end with corner 0, 2-3 with corner 1, ...), then one lane per corner adds into the shared table
+#define LSN_ADJ_DOT(dc, xs, t)                                                        \
+  {                                                                                   \
+    float d_[4];                                                                      \
+    LSN_ADJ_DOT4(dc, xs, d_)                                                          \
     const bool u4_ = sub & 4, u2_ = sub & 2;                                          \
     const float a0_ = (u4_ ? d_[2] : d_[0]) + __shfl_xor_sync(0xffffffffu, u4_ ? d_[0] : d_[2], 4); \
     const float a1_ = (u4_ ? d_[3] : d_[1]) + __shfl_xor_sync(0xffffffffu, u4_ ? d_[1] : d_[3], 4); \
@@ -270,6 +283,7 @@ dcn_adjoint_tma_kernel(const __grid_constant__ CUtensorMap tmCol, const __nv_bfl
       LSN_ADJ_DOT(dcA, xA, 8)
 #undef LSN_ADJ_LOAD
 #undef LSN_ADJ_DOT
+#undef LSN_ADJ_DOT4
     }
 
     if (want_dx) {

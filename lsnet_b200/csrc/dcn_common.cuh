@@ -115,12 +115,21 @@ __device__ __forceinline__ float2 bf16x2_f2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-// acc += <a, b> over 8 bf16 channels, accumulated pairwise with FFMA2 (sm_100 packed fp32x2; exact products)
-__device__ __forceinline__ float2 dot8(const float2 (&a)[4], const uint4& b, float2 acc) {
+// <a, b> over 8 bf16 channels on the mixed-precision FMA of sm_100 (PTX `fma.rn.f32.bf16` -> SASS `FHFMA.BF16 Rd, Ra.H0|H1,
+// Rb.H0|H1, Rc`: fp32 accumulator, both multiplicands taken straight from the halves of packed bf16x2 registers).  No
+// unpack instructions at all: 8 FHFMA in two independent chains instead of 8 + 8 shifts / masks and 4 FFMA2.  The
+// products are exact in fp32 either way, so the result differs from dot8 only by summation order.
+__device__ __forceinline__ float dot8_bf16(const uint4& a, const uint4& b) {
+  float lo = 0.f, hi = 0.f;
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
   const uint32_t* pb = reinterpret_cast<const uint32_t*>(&b);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc = __ffma2_rn(a[i], bf16x2_f2(pb[i]), acc);
-  return acc;
+  for (int i = 0; i < 4; ++i)
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %1, ah, bh, %1;\n\t}"
+        : "+f"(lo), "+f"(hi)
+        : "r"(pa[i]), "r"(pb[i]));
+  return lo + hi;
 }
 
 __device__ __forceinline__ void axpy8(float w, const uint4& a, float2 (&acc)[4]) {

@@ -409,11 +409,9 @@ dcn_col2im_binned_kernel(const __nv_bfloat16* __restrict__ gcol, const __nv_bflo
         const uint4 x1 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.y) * ldxb));
         const uint4 x2 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.z) * ldxb));
         const uint4 x3 = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(cq.w) * ldxb));
-        const float2 ga[4] = {bf16x2_f2(gc.x), bf16x2_f2(gc.y), bf16x2_f2(gc.z), bf16x2_f2(gc.w)};
-        const float2 zz = make_float2(0.f, 0.f);
-        const float2 d0 = dot8(ga, x0, zz), d1 = dot8(ga, x1, zz), d2 = dot8(ga, x2, zz), d3 = dot8(ga, x3, zz);
-        const float D0 = act ? d0.x + d0.y : 0.f, D1 = act ? d1.x + d1.y : 0.f;
-        const float D2 = act ? d2.x + d2.y : 0.f, D3 = act ? d3.x + d3.y : 0.f;
+        // bf16 x bf16 products accumulated in fp32 by FHFMA.BF16 (dcn_common.cuh::dot8_bf16): no operand unpacking
+        const float D0 = act ? dot8_bf16(gc, x0) : 0.f, D1 = act ? dot8_bf16(gc, x1) : 0.f;
+        const float D2 = act ? dot8_bf16(gc, x2) : 0.f, D3 = act ? dot8_bf16(gc, x3) : 0.f;
         const float4 kh = ah[pix * 9 + tap], kw = aw[pix * 9 + tap], km = am[pix * 9 + tap];
         v[2 * tap] += kh.x * D0 + kh.y * D1 + kh.z * D2 + kh.w * D3;
         v[2 * tap + 1] += kw.x * D0 + kw.y * D1 + kw.z * D2 + kw.w * D3;

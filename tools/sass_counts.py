@@ -12,7 +12,7 @@ lib = os.path.join(root, 'lsnet_b200', 'liblsnet_sm100.so')
 dst = sys.argv[1] if len(sys.argv) > 1 else os.path.join(root, 'profiles', 'r02_sass_counts.txt')
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 pat = ['UTCHMMA', 'UTCQMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'UTCBAR', 'SYNCS', 'HMMA', 'REDG', 'RED.', 'LDGSTS',
-       'FFMA2', 'FENCE.VIEW.ASYNC']
+       'FFMA2', 'FHFMA', 'FENCE.VIEW.ASYNC']
 cur, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in sass.splitlines():
     m = re.match(r'\s*Function : (\S+)', line)
@@ -31,7 +31,7 @@ for line in sass.splitlines():
 with open(dst, 'w') as f:
     f.write('# SASS evidence per kernel of liblsnet_sm100.so (cuobjdump -sass, sm_100a)\n')
     f.write('# UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld, UTMALDG = cp.async.bulk.tensor (TMA), UTCBAR = tcgen05.commit,\n')
-    f.write('# SYNCS = mbarrier, FFMA2 = packed fp32x2 FMA, REDG = red.global, FENCE.VIEW.ASYNC = fence.proxy.async\n\n')
+    f.write('# SYNCS = mbarrier, FFMA2 = packed fp32x2 FMA, FHFMA = fma.rn.f32.bf16 (fp32 += bf16 x bf16, operands from register halves), REDG = red.global, FENCE.VIEW.ASYNC = fence.proxy.async\n\n')
     for k, c in counts.items():
         tags = ' '.join(f'{p}={c[p]}' for p in pat if c[p])
         f.write(f'{k[:110]:110s} instr={c["instructions"]:6d}  {tags}\n')
