@@ -518,17 +518,22 @@ class LSHead(nn.Module):
             if torch.is_tensor(gm):
                 P = gm[:, :-2].reshape(gm.shape[0], -1, 2)
             else:
-                inst = []
+                # largest component per instance by shoelace area; strict '<' keeps the first maximum (:1728-1734).
+                # Single-component instances (the common case) skip the areas; one tensor per image, not per instance.
+                rows = []
                 for comps in gm.masks:
-                    areas = [0.5 * abs(float(np.dot(c.reshape(-1, 2)[:, 0], np.roll(c.reshape(-1, 2)[:, 1], 1)) -
-                                             np.dot(c.reshape(-1, 2)[:, 1], np.roll(c.reshape(-1, 2)[:, 0], 1))))
-                             for c in comps]
                     best = 0
-                    for ci in range(1, len(comps)):      # strict '<' keeps the first maximum (:1728-1734)
-                        if areas[best] < areas[ci]:
-                            best = ci
-                    inst.append(torch.as_tensor(np.asarray(comps[best]).reshape(-1, 2), dtype=torch.float32))
-                P = torch.stack(inst)
+                    if len(comps) > 1:
+                        areas = []
+                        for q in comps:
+                            q = np.asarray(q).reshape(-1, 2)
+                            areas.append(0.5 * abs(float(np.dot(q[:, 0], np.roll(q[:, 1], 1)) -
+                                                         np.dot(q[:, 1], np.roll(q[:, 0], 1)))))
+                        for ci in range(1, len(comps)):
+                            if areas[best] < areas[ci]:
+                                best = ci
+                    rows.append(np.asarray(comps[best], dtype=np.float64).reshape(-1, 2))
+                P = torch.from_numpy(np.stack(rows).astype(np.float32))
             xmin, ymin = P[:, :, 0].min(1)[0], P[:, :, 1].min(1)[0]
             xmax, ymax = P[:, :, 0].max(1)[0], P[:, :, 1].max(1)[0]
             ct = torch.stack([(xmin + xmax) / 2, (ymin + ymax) / 2], 1).unsqueeze(1)

@@ -104,6 +104,16 @@ def main():
                     rec[tag + '_mask_pts'] = np.concatenate([p for c in pm.masks for p in c]) if len(pm.masks) else \
                         np.zeros(0)
 
+    # ---- the head's host-side polygon step on pipeline output (lsnet_head.py:1717-1756) ----
+    import torch
+    from mmdet.models.dense_heads.lsnet_head import LSHead
+    stub = types.SimpleNamespace(component_polygon_area=lambda poly: LSHead.component_polygon_area(None, poly))
+    masks = [samples[('segm', 1, i)]['gt_masks'].data for i in range(len(S.SIZES))]
+    polys, boxes = LSHead.process_polygons(stub, masks, [torch.zeros(1)])
+    for i, (p, b) in enumerate(zip(polys, boxes)):
+        rec[f'headpoly_{i}_table'] = p.numpy()
+        rec[f'headpoly_{i}_boxes'] = b.numpy()
+
     # ---- collate (mmcv DataContainer semantics) of mixed-size samples ----
     for name, ids in (('a', [0, 3]), ('b', [1, 4, 2])):
         b = collate([samples[('bbox', 1, i)] for i in ids], samples_per_gpu=len(ids))

@@ -101,6 +101,20 @@ def test_pipeline_matches_reference(task, ms):
     assert 0 < flips < len(S.SIZES)              # the seeds exercise both branches
 
 
+def test_head_polygon_step_matches_reference():
+    """``LSHead.process_polygons`` (largest component, extent centre appended, extent boxes) on the segm pipeline's
+    output — multi-component instances included — against the reference head's own result."""
+    from lsnet_b200.modules.head import LSHead
+    ds = _dataset('segm', True)
+    masks = [_run(ds, i, 1)['gt_masks'] for i in range(len(S.SIZES))]
+    assert any(len(c) > 1 for m in masks for c in m.masks)
+    polys, boxes = LSHead.process_polygons(None, masks)
+    for i, (p, b) in enumerate(zip(polys, boxes)):
+        assert p.dtype == torch.float32 and p.shape[1] == 74
+        assert np.allclose(p.numpy(), G[f'headpoly_{i}_table'], atol=1e-4, rtol=0)
+        assert np.allclose(b.numpy(), G[f'headpoly_{i}_boxes'], atol=1e-4, rtol=0)
+
+
 def test_uniformsample_vectorised_equals_edge_loop():
     """The array formulation against the reference's per-edge loop (loading.py:311-375) written out for the test:
     random rings on both sides of the 360-point target, including repeated vertices (zero-length edges)."""
