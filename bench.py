@@ -410,7 +410,7 @@ def run_gpu(args, rank, world, local_rank):
     line = dict(metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
                 data='synthetic', config=bench_config(world, cfg_name), step_mode=mode,
-                shapes=sorted({tuple(b['img'].shape[-2:]) for b in host}),
+                shapes=sorted({tuple(b['img'].shape[-2:]) for b in resident}),
                 e2e=dict(value=e2e, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=ms_e2e / args.steps,
                          input=('uint8 HWC bytes, normalised + padded on the GPU (lsnet_image_prep_u8) inside the step'
