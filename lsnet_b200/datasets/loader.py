@@ -121,11 +121,19 @@ def collate(samples, pin=False, canvas_multiple=None):
 
 
 def worker_init_fn(worker_id, num_workers, rank, seed):
-    """builder.py:130-135."""
+    """builder.py:130-135 (seed of worker = num_workers * rank + worker_id + seed).  Additionally every worker runs
+    OpenCV single-threaded: the parallelism of the loader is its worker processes, and a forked child must not touch
+    the parent's OpenCV thread pool."""
     import random
-    s = num_workers * rank + worker_id + seed
-    np.random.seed(s)
-    random.seed(s)
+    try:
+        import cv2
+        cv2.setNumThreads(0)
+    except ImportError:
+        pass
+    if seed is not None:
+        s = num_workers * rank + worker_id + seed
+        np.random.seed(s)
+        random.seed(s)
 
 
 def device_prep_pipeline(pipeline):
@@ -172,7 +180,7 @@ def build_dataloader(dataset, samples_per_gpu, workers_per_gpu, num_gpus=1, dist
             sampler = DistributedSampler(dataset, world_size, rank, shuffle=False)
     else:
         sampler = GroupSampler(dataset, samples_per_gpu) if shuffle else None
-    init = partial(worker_init_fn, num_workers=workers_per_gpu, rank=rank, seed=seed) if seed is not None else None
+    init = partial(worker_init_fn, num_workers=workers_per_gpu, rank=rank, seed=seed)
     # pin=True: the DataLoader's pin thread of THIS process page-locks the collated tensors (the workers must not touch
     # CUDA), which is what lets GraphTrainer.prefetch copy the next batch asynchronously; the reference keeps
     # pin_memory=False and copies synchronously in scatter (mmcv/parallel/scatter_gather.py)

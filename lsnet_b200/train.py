@@ -150,8 +150,10 @@ class GraphTrainer:
         self.flat_g = torch.zeros(n, device=self.device, dtype=torch.float32)
         self.flat_m = torch.zeros(n, device=self.device, dtype=torch.float32)
         o = 0
+        self._slots = []                         # (offset, tap-major?) of every parameter inside the flat buffers
         for p in self.params:
             k = p.numel()
+            self._slots.append((o, bool(DIRECT_WGRAD and p.dim() == 4 and getattr(p, '_lsnet_tapmajor', False))))
             if DIRECT_WGRAD and p.dim() == 4 and getattr(p, '_lsnet_tapmajor', False):
                 # Weights of the tcgen05 conv / DCN kernels live tap-major ([Cout][kh][kw][Cin] memory, i.e.
                 # torch.channels_last strides on the OIHW parameter): the bf16 operand pack is then a plain cast and the
@@ -178,6 +180,18 @@ class GraphTrainer:
         self._pool = None
         self.recaptures = 0
         self.cur = self._entry(sample_batch)
+
+    def flat_views(self, flat):
+        """Per-parameter views of one of the flat buffers in the parameters' own (OIHW) shapes."""
+        out = []
+        for p, (o, tap) in zip(self.params, self._slots):
+            k = p.numel()
+            if tap:
+                co, ci, kh, kw = p.shape
+                out.append(flat[o:o + k].view(co, kh, kw, ci).permute(0, 3, 1, 2))
+            else:
+                out.append(flat[o:o + k].view_as(p))
+        return out
 
     # per-shape state: static image / GT buffers, the captured graph, its loss tensors, pinned GT staging
     class _Step:
@@ -441,6 +455,70 @@ class GraphTrainer:
                 dist.all_reduce(flat.div_(dist.get_world_size()))
             log = dict(zip(log.keys(), flat.tolist()))
         return loss, log
+
+
+def _momentum_views(trainer):
+    """{index among ALL parameters of the model (the reference builds its SGD over ``model.parameters()``, frozen ones
+    included: mmcv/runner/optimizer/default_constructor.py) -> momentum buffer or None} for either trainer."""
+    every = list(trainer.core.parameters())
+    pos = {id(p): i for i, p in enumerate(every)}
+    if hasattr(trainer, 'optimizer'):
+        return {pos[id(p)]: trainer.optimizer.state.get(p, {}).get('momentum_buffer') for p in trainer.params}, every
+    return {pos[id(p)]: m for p, m in zip(trainer.params, trainer.flat_views(trainer.flat_m))}, every
+
+
+def save_checkpoint(trainer, path, epoch=0, meta=None):
+    """The reference's checkpoint layout (mmcv/mmcv/runner/checkpoint.py:257-293, written by CheckpointHook every epoch):
+    ``{'meta', 'state_dict', 'optimizer'}`` with CPU tensors, parameter names and OIHW shapes of the reference modules and
+    the optimizer in ``torch.optim.SGD.state_dict()`` form over all model parameters -- so a file written here resumes
+    in the reference's runner and vice versa.  ``meta`` carries ``epoch`` / ``iter`` as ``BaseRunner.resume`` expects
+    (base_runner.py:289-307)."""
+    state = {k: v.detach().to('cpu', copy=True).contiguous() for k, v in trainer.core.state_dict().items()}
+    mom, every = _momentum_views(trainer)
+    opt = dict(state={i: dict(momentum_buffer=m.detach().to('cpu', copy=True).contiguous())
+                      for i, m in mom.items() if m is not None},
+               param_groups=[dict(lr=float(trainer.lr_at(trainer.iter)), momentum=_sgd(trainer, 'momentum'), dampening=0,
+                                  weight_decay=_sgd(trainer, 'weight_decay'), nesterov=False,
+                                  params=list(range(len(every))))])
+    ckpt = dict(meta=dict(meta or {}, epoch=int(epoch), iter=int(trainer.iter)), state_dict=state, optimizer=opt)
+    torch.save(ckpt, path)
+    return ckpt['meta']
+
+
+def _sgd(trainer, key):
+    if hasattr(trainer, 'optimizer'):
+        return trainer.optimizer.param_groups[0][key]
+    return trainer.momentum if key == 'momentum' else trainer.wd
+
+
+def resume(trainer, path, strict=True):
+    """``BaseRunner.resume`` (mmcv/mmcv/runner/base_runner.py:289-307): weights (``module.`` prefixes of a DataParallel
+    checkpoint stripped, checkpoint.py:204-240), momentum buffers, epoch and iteration.  Returns ``meta``."""
+    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    state = ckpt.get('state_dict', ckpt)
+    state = {(k[7:] if k.startswith('module.') else k): v for k, v in state.items()}
+    trainer.core.load_state_dict(state, strict=strict)          # copies INTO the (flat-buffer) parameter storage
+    opt = ckpt.get('optimizer')
+    if opt is not None:
+        mom, every = _momentum_views(trainer)
+        graph = not hasattr(trainer, 'optimizer')
+        if graph:
+            trainer.flat_m.zero_()
+        for i, st in opt['state'].items():
+            i = int(i)
+            if i not in mom:
+                raise ValueError(f'checkpoint holds a momentum buffer for parameter {i}, which is not trained here')
+            buf = st['momentum_buffer']
+            if graph:
+                mom[i].copy_(buf)
+            else:
+                trainer.optimizer.state[every[i]]['momentum_buffer'] = buf.to(every[i].device).clone()
+    meta = ckpt.get('meta', {})
+    trainer.iter = int(meta.get('iter', 0))
+    if not hasattr(trainer, 'optimizer'):
+        from .ops import gemm_ops
+        gemm_ops._PACK_CACHE.clear()                            # packs of the previous weights
+    return meta
 
 
 def train_epochs(trainer, loader, epochs=1, start_epoch=0, on_step=None):

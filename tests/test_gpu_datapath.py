@@ -141,3 +141,44 @@ def test_files_to_training_steps(tmp_path, task, device_prep):
     assert n == len(dl) == 2 and all(bool(torch.isfinite(l)) for l in losses)      # one batch per aspect-ratio group
     assert float((tr.flat_p - before).abs().max()) > 0
     assert len(tr.steps) == 2                     # a landscape and a portrait canvas: one captured step each
+
+
+def test_graph_trainer_checkpoint_resume(tmp_path):
+    """save_checkpoint / resume on the flat-buffer trainer: the file holds the reference's layout (OIHW weights and
+    momentum buffers by parameter index), restoring it reproduces the flat parameter / momentum buffers bit for bit
+    (tap-major storage included), and the same file resumes the eager trainer (plain parameters, torch SGD)."""
+    from lsnet_b200.data import MODEL_CFG, synthetic_batch
+    from lsnet_b200.train import GraphTrainer, Trainer, resume, save_checkpoint
+    b = [synthetic_batch(s, batch=2, img_hw=(320, 416)) for s in range(3)]
+    path = str(tmp_path / 'epoch_3.pth')
+    torch.manual_seed(0)
+    tr = GraphTrainer(MODEL_CFG['bbox_r50'], b[0])
+    tr.iter = 1000
+    tr.step(b[0])
+    tr.step(b[1])
+    meta = save_checkpoint(tr, path, epoch=3)
+    assert meta == dict(epoch=3, iter=1002)
+    p_saved, m_saved = tr.flat_p.clone(), tr.flat_m.clone()
+    assert float(m_saved.abs().max()) > 0
+    tr.step(b[2])
+    assert not torch.equal(tr.flat_p, p_saved)
+    assert resume(tr, path)['epoch'] == 3 and tr.iter == 1002
+    assert torch.equal(tr.flat_p, p_saved) and torch.equal(tr.flat_m, m_saved)
+    loss, _ = tr.step(b[2])                      # and it keeps training from there
+    assert bool(torch.isfinite(loss))
+    ck = torch.load(path, weights_only=False)
+    names = [k for k, p in tr.core.named_parameters()]
+    w = 'bbox_head.cls_convs.0.conv.weight'
+    assert tuple(ck['state_dict'][w].shape) == (256, 256, 3, 3) and ck['state_dict'][w].is_contiguous()
+    assert tuple(ck['optimizer']['state'][names.index(w)]['momentum_buffer'].shape) == (256, 256, 3, 3)
+    torch.manual_seed(5)
+    eager = Trainer(MODEL_CFG['bbox_r50'])
+    resume(eager, path)
+    assert eager.iter == 1002
+    for k, v in eager.core.state_dict().items():
+        assert torch.equal(v.detach().cpu(), ck['state_dict'][k]), k
+    every = list(eager.core.parameters())
+    for i, st in ck['optimizer']['state'].items():
+        assert torch.equal(eager.optimizer.state[every[i]]['momentum_buffer'].cpu(), st['momentum_buffer'])
+    loss, _ = eager.step({**b[2], 'img': b[2]['img'].cuda()})
+    assert bool(torch.isfinite(loss))

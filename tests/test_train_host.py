@@ -60,3 +60,46 @@ def test_keybox_ground_truth():
     assert torch.equal(boxes[0], torch.tensor([[10., 20., 30., 40.], [1., 2., 5., 6.]]))
     assert torch.equal(vs[0], torch.tensor([[2., 0., 1.], [2., 2., 2.]]))
     assert torch.equal(kps[0], torch.tensor([[10., 20., 50., 5., 30., 40., 20., 30.], [1., 2., 3., 4., 5., 6., 3., 4.]]))
+
+
+def test_checkpoint_resume_roundtrip(tmp_path):
+    """save_checkpoint / resume (mmcv checkpoint layout): a trainer resumed from a file continues exactly like the one
+    that wrote it -- weights, momentum, iteration (learning-rate schedule) -- and the file has the reference's keys."""
+    import torch
+    import torch.nn as nn
+    from lsnet_b200.train import Trainer, resume, save_checkpoint
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(6, 5)
+            self.frozen = nn.Linear(5, 5)
+            self.b = nn.Linear(5, 3)
+            for p in self.frozen.parameters():
+                p.requires_grad = False
+
+        def forward(self, x, y):
+            return {'loss_cls': ((self.b(self.frozen(torch.relu(self.a(x)))) - y) ** 2).mean()}
+    cfg = dict(optimizer=dict(lr=0.05, momentum=0.9, weight_decay=1e-4), grad_clip=dict(max_norm=0.5, norm_type=2),
+               lr_config=dict(policy='step', warmup='linear', warmup_iters=5, warmup_ratio=0.1, step=[1]))
+    g = torch.Generator().manual_seed(0)
+    data = [dict(x=torch.randn(4, 6, generator=g), y=torch.randn(4, 3, generator=g)) for _ in range(6)]
+    torch.manual_seed(1)
+    t1 = Trainer(cfg, device='cpu', model=Tiny(), iters_per_epoch=4)
+    for d in data[:3]:
+        t1.step(d)
+    meta = save_checkpoint(t1, str(tmp_path / 'e.pth'), epoch=0, meta=dict(note='x'))
+    assert meta == dict(note='x', epoch=0, iter=3)
+    ck = torch.load(str(tmp_path / 'e.pth'), weights_only=False)
+    assert set(ck) == {'meta', 'state_dict', 'optimizer'} and set(ck['state_dict']) == set(t1.core.state_dict())
+    # SGD state over ALL parameters (as the reference's optimizer): the frozen layer's two have no buffer
+    assert sorted(ck['optimizer']['state']) == [0, 1, 4, 5] and ck['optimizer']['param_groups'][0]['params'] == list(range(6))
+    torch.manual_seed(2)
+    t2 = Trainer(cfg, device='cpu', model=Tiny(), iters_per_epoch=4)
+    assert resume(t2, str(tmp_path / 'e.pth'))['iter'] == 3 and t2.iter == 3
+    for d in data[3:]:
+        l1, _ = t1.step(d)
+        l2, _ = t2.step(d)
+        assert torch.equal(l1, l2)
+    for (k, a), (_, b) in zip(t1.core.state_dict().items(), t2.core.state_dict().items()):
+        assert torch.equal(a, b), k
