@@ -4,5 +4,5 @@ from .coco import CocoDataset, CocoIndex, CocoPoseDataset  # noqa: F401
 from .contour import PolygonMasks, unify_polygons, uniformsample  # noqa: F401
 from .loader import (DevicePrep, DistributedGroupSampler, GroupSampler, build_dataloader, build_dataset,  # noqa: F401
                      collate, device_prep_pipeline)
-from .transforms import (Collect, Compose, DefaultFormatBundle, DeviceFormatBundle, LoadAnnotations,  # noqa: F401
-                         LoadImageFromFile, Normalize, Pad, RandomFlip, Resize)
+from .transforms import (Collect, Compose, DefaultFormatBundle, DeviceFormatBundle, ImageToTensor,  # noqa: F401
+                         LoadAnnotations, LoadImageFromFile, MultiScaleFlipAug, Normalize, Pad, RandomFlip, Resize)

@@ -100,6 +100,12 @@ def collate(samples, pin=False, canvas_multiple=None):
     is what the head's point validity uses (lsnet_head.py:770-779)."""
     def up(v):
         return v if not canvas_multiple else -(-v // canvas_multiple) * canvas_multiple
+    if isinstance(samples[0]['img'], list):
+        # test pipelines (MultiScaleFlipAug): every value is a list over augmentations -> one collated batch per
+        # augmentation, returned as the dict of lists ``LSDetector.forward_test(imgs, img_metas)`` takes
+        n_aug = len(samples[0]['img'])
+        per_aug = [collate([{k: v[a] for k, v in s.items()} for s in samples], pin, canvas_multiple) for a in range(n_aug)]
+        return {k: [b[k] for b in per_aug] for k in per_aug[0]}
     out = {k: [s[k] for s in samples] for k in samples[0] if k != 'img'}
     imgs = [s['img'] for s in samples]
     if imgs[0].dtype == torch.uint8:

@@ -406,6 +406,53 @@ class Collect:
 
 
 @PIPELINES.register_module()
+class ImageToTensor:
+    """formating.py:66-99: HWC arrays under ``keys`` -> CHW tensors."""
+
+    def __init__(self, keys):
+        self.keys = keys
+
+    def __call__(self, results):
+        for key in self.keys:
+            img = results[key]
+            if img.ndim < 3:
+                img = img[..., None]
+            results[key] = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)))
+        return results
+
+
+@PIPELINES.register_module()
+class MultiScaleFlipAug:
+    """test_time_aug.py:9-117, the wrapper of every test pipeline in the LSNet configs: the inner transforms run once
+    per (scale, flip, direction) with those three keys preset, and the per-augmentation dicts are transposed into one
+    dict of lists (a single scale without flip gives lists of length 1 — ``LSDetector.forward_test`` takes them)."""
+
+    def __init__(self, transforms, img_scale=None, scale_factor=None, flip=False, flip_direction='horizontal'):
+        self.transforms = Compose(transforms)
+        assert (img_scale is None) ^ (scale_factor is None), 'Must have but only one variable can be setted'
+        if img_scale is not None:
+            self.img_scale = [tuple(s) for s in (img_scale if isinstance(img_scale, list) else [img_scale])]
+            self.scale_key = 'scale'
+        else:
+            self.img_scale = scale_factor if isinstance(scale_factor, list) else [scale_factor]
+            self.scale_key = 'scale_factor'
+        self.flip = flip
+        self.flip_direction = flip_direction if isinstance(flip_direction, list) else [flip_direction]
+
+    def __call__(self, results):
+        aug = []
+        for scale in self.img_scale:
+            for flip in ([False, True] if self.flip else [False]):
+                for direction in self.flip_direction:
+                    r = results.copy()
+                    r[self.scale_key] = scale
+                    r['flip'] = flip
+                    r['flip_direction'] = direction
+                    aug.append(self.transforms(r))
+        return {key: [d[key] for d in aug] for key in aug[0]}
+
+
+@PIPELINES.register_module()
 class DeviceFormatBundle:
     """The ``device_prep`` replacement for Normalize + Pad + DefaultFormatBundle: the resized (and flipped) uint8 HWC
     image goes out as it is; ``pad_shape`` / ``img_norm_cfg`` are recorded as the reference stages would have, and the

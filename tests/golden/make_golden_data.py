@@ -104,6 +104,24 @@ def main():
                     rec[tag + '_mask_pts'] = np.concatenate([p for c in pm.masks for p in c]) if len(pm.masks) else \
                         np.zeros(0)
 
+    # ---- test pipelines (MultiScaleFlipAug) ----
+    for multi in (0, 1):
+        pipe = Compose(S.eval_pipeline(bool(multi)))
+        for i in (0, 1):
+            info, _ = parsed[(False, i)]
+            img = S.image(i)
+            out = pipe(dict(img_info=info, img=img, img_shape=img.shape, ori_shape=img.shape, img_fields=['img'],
+                            filename=info['filename'], ori_filename=info['filename'], img_prefix=None, bbox_fields=[],
+                            extreme_fields=[], mask_fields=[], seg_fields=[], keypoint_fields=[]))
+            tag = f'test_{multi}_{i}'
+            rec[tag + '_naug'] = np.array(len(out['img']))
+            for a, (im, meta) in enumerate(zip(out['img'], out['img_metas'])):
+                m = meta.data
+                rec[f'{tag}_{a}_img'] = im.numpy() if (multi == 0 or a == 3) else np.zeros(0, np.float32)
+                rec[f'{tag}_{a}_imgsum'] = np.array([im.double().sum().item(), im.double().abs().sum().item()])
+                rec[f'{tag}_{a}_meta'] = np.array(list(m['img_shape']) + list(m['pad_shape']) + [int(m['flip'])], np.int64)
+                rec[f'{tag}_{a}_scale_factor'] = np.asarray(m['scale_factor'], np.float32)
+
     # ---- the head's host-side polygon step on pipeline output (lsnet_head.py:1717-1756) ----
     import torch
     from mmdet.models.dense_heads.lsnet_head import LSHead

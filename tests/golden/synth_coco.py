@@ -112,3 +112,12 @@ def pipeline(task, multiscale=False):
         flip['keep_poly_clockwise'] = True
     return [load, resize, flip, dict(type='Normalize', **NORM), dict(type='Pad', size_divisor=32),
             dict(type='DefaultFormatBundle'), dict(type='Collect', keys=keys)]
+
+
+def eval_pipeline(multi=False):
+    """The test pipeline of the LSNet configs (configs/_base_/datasets/coco_lsvr.py:15-29) at the fixtures' scale;
+    ``multi``: two scales with flip (the shape of the multi-scale testing configs)."""
+    inner = [dict(type='Resize', keep_ratio=True), dict(type='RandomFlip'), dict(type='Normalize', **NORM),
+             dict(type='Pad', size_divisor=32), dict(type='ImageToTensor', keys=['img']),
+             dict(type='Collect', keys=['img'])]
+    return [dict(type='MultiScaleFlipAug', img_scale=MS_SCALES if multi else SCALE, flip=multi, transforms=inner)]

@@ -284,3 +284,33 @@ def test_reference_configs_resolve_their_train_pipelines():
             assert len(rs.img_scale) == 2 and rs.multiscale_mode == 'range'
         n += 1
     assert n == 15
+
+
+@pytest.mark.parametrize('multi', [0, 1])
+def test_eval_pipeline_matches_reference(multi):
+    """MultiScaleFlipAug test pipelines (single scale; two scales x flip): per-augmentation images bit-exact, metas
+    equal, and ``collate`` turns a test sample into the lists ``LSDetector.forward_test`` takes."""
+    ds = DATASETS.get('CocoDataset')(ann_file=S.coco_dict(False), pipeline=S.eval_pipeline(bool(multi)), test_mode=True)
+    assert 'MultiScaleFlipAug' in PIPELINES and 'ImageToTensor' in PIPELINES
+    for i in (0, 1):
+        info = ds.data_infos[i]
+        assert info['id'] == 10 + i                       # test mode keeps every image, in json order
+        im = S.image(i)
+        res = dict(img_info=info, img=im, img_shape=im.shape, ori_shape=im.shape, img_fields=['img'],
+                   filename=info['filename'], ori_filename=info['filename'])
+        ds.pre_pipeline(res)
+        out = ds.pipeline(res)
+        tag = f'test_{multi}_{i}'
+        assert len(out['img']) == int(G[tag + '_naug']) == (4 if multi else 1)
+        for a, (img, meta) in enumerate(zip(out['img'], out['img_metas'])):
+            got = list(meta['img_shape']) + list(meta['pad_shape']) + [int(meta['flip'])]
+            assert got == G[f'{tag}_{a}_meta'].tolist()
+            assert np.array_equal(np.asarray(meta['scale_factor'], np.float32), G[f'{tag}_{a}_scale_factor'])
+            ref = G[f'{tag}_{a}_img']
+            if ref.size:
+                assert np.array_equal(img.numpy(), ref)
+            s = np.array([img.double().sum().item(), img.double().abs().sum().item()])
+            assert np.allclose(s, G[f'{tag}_{a}_imgsum'], rtol=1e-9, atol=1e-6)
+        b = loader.collate([out])
+        assert isinstance(b['img'], list) and len(b['img']) == len(out['img'])
+        assert b['img'][0].shape == (1,) + tuple(out['img'][0].shape) and b['img_metas'][0][0] is out['img_metas'][0]
