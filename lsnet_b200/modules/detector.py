@@ -78,12 +78,61 @@ class LSDetector(nn.Module):
         return self.forward_test(img, img_metas, **kwargs)
 
     def forward_test(self, imgs, img_metas, **kwargs):
-        """base.py:118-159: one augmentation = simple_test; several = aug_test (not built)."""
+        """base.py:118-159: one augmentation = simple_test; several (MultiScaleFlipAug lists) = aug_test."""
         if torch.is_tensor(imgs):
             imgs, img_metas = [imgs], [img_metas]
-        if len(imgs) != 1:
-            raise NotImplementedError('test-time augmentation (aug_test_vote, lsnet.py:97-409) is out of scope')
-        return self.simple_test(imgs[0], img_metas[0], **kwargs)
+        if len(imgs) != len(img_metas):
+            raise ValueError(f'num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})')
+        if len(imgs) == 1:
+            return self.simple_test(imgs[0], img_metas[0], **kwargs)
+        if imgs[0].shape[0] != 1:
+            raise ValueError('aug test does not support inference with batch size > 1 (base.py:150-151)')
+        return self.aug_test(imgs, img_metas, **kwargs)
+
+    def aug_test(self, imgs, img_metas, rescale=False, show=False, out_dir=False):
+        """lsnet.py:402-409.  ``test_cfg.method == 'vote'`` is the multi-scale test of the reference's result tables;
+        the plain box-merge variant ('simple', bbox task only, mmdet's generic merge_aug_results + multiclass_nms) is
+        not built."""
+        method = self.test_cfg.get('method', 'simple') if self.test_cfg is not None else 'simple'
+        if method == 'simple':
+            raise NotImplementedError("test_cfg.method='simple' (aug_test_simple, lsnet.py:102-136) is not built: use "
+                                      "method='vote' with scale_ranges")
+        return self.aug_test_vote(imgs, img_metas, rescale, show, out_dir)
+
+    @torch.no_grad()
+    def aug_test_vote(self, imgs, img_metas, rescale=False, show=False, out_dir=False):
+        """lsnet.py:300-400: decode + NMS per augmentation on the device (one image each), then the scale-range filter,
+        mapping back and per-class instance voting of ``modules/tta.py``; returns the per-class result lists of
+        ``simple_test`` for ONE image."""
+        import numpy as np
+        from . import tta
+        head = self.bbox_head
+        dets, metas = [], []
+        for img, meta in zip(imgs, img_metas):
+            outs = head(self.extract_feat(img))
+            dets.append(head.get_bboxes(*outs, meta, rescale=False, nms=True)[0])
+            metas.append(meta[0])
+        boxes, vecs, labels = tta.vote_merge(dets, metas, head.task, head.num_classes, head.num_vectors,
+                                             self.test_cfg['scale_ranges'])
+        if not rescale:      # back into the first augmentation's frame (lsnet.py:367-374)
+            sf = np.asarray(metas[0]['scale_factor'], np.float32)
+            boxes = boxes.clone()
+            boxes[:, :4] *= boxes.new_tensor(sf)
+            vecs = vecs * vecs.new_tensor(np.tile(sf[:2], vecs.shape[1] // 2))
+        if head.task in ('pose_bbox', 'pose_kbox') and not (show or out_dir):
+            big = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]) > 1024        # lsnet.py:389-396
+            boxes, vecs, labels = boxes[big], vecs[big], labels[big]
+        return self._to_results(boxes, vecs, labels)
+
+    def _to_results(self, boxes, pts, labels):
+        """``bbox_extreme2result`` / ``bbox_poly2result`` (mmdet/core/bbox/transforms.py:198-218): per-class numpy lists."""
+        import numpy as np
+        nc, nv = self.bbox_head.num_classes, self.bbox_head.num_vectors
+        width = 8 if self.bbox_head.task == 'bbox' else 2 * nv
+        if boxes.shape[0] == 0:
+            return [[np.zeros((0, 5), np.float32) for _ in range(nc)], [np.zeros((0, width), np.float32) for _ in range(nc)]]
+        b, p, l = boxes.cpu().numpy(), pts.cpu().numpy(), labels.cpu().numpy()
+        return [[b[l == i] for i in range(nc)], [p[l == i] for i in range(nc)]]
 
     @torch.no_grad()
     def simple_test(self, img, img_metas, rescale=False, show=False, out_dir=False):
@@ -92,18 +141,7 @@ class LSDetector(nn.Module):
         x = self.extract_feat(img)
         outs = self.bbox_head(x)
         dets = self.bbox_head.get_bboxes(*outs, img_metas, rescale=rescale)
-        nc, nv = self.bbox_head.num_classes, self.bbox_head.num_vectors
-        width = 8 if self.bbox_head.task == 'bbox' else 2 * nv
-        results = []
-        for boxes, pts, labels in dets:
-            if boxes.shape[0] == 0:
-                import numpy as np
-                results.append([[np.zeros((0, 5), np.float32) for _ in range(nc)],
-                                [np.zeros((0, width), np.float32) for _ in range(nc)]])
-                continue
-            b, p, l = boxes.cpu().numpy(), pts.cpu().numpy(), labels.cpu().numpy()
-            results.append([[b[l == i] for i in range(nc)], [p[l == i] for i in range(nc)]])
-        return results
+        return [self._to_results(boxes, pts, labels) for boxes, pts, labels in dets]
 
     def _parse_losses(self, losses, sync_log=False):
         return parse_losses(losses, sync_log)

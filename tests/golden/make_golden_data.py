@@ -122,8 +122,33 @@ def main():
                 rec[f'{tag}_{a}_meta'] = np.array(list(m['img_shape']) + list(m['pad_shape']) + [int(m['flip'])], np.int64)
                 rec[f'{tag}_{a}_scale_factor'] = np.asarray(m['scale_factor'], np.float32)
 
-    # ---- the head's host-side polygon step on pipeline output (lsnet_head.py:1717-1756) ----
+    # ---- multi-scale testing by voting: the host half of aug_test_vote (lsnet.py:138-365) on synthetic detections ----
     import torch
+    from mmdet.models.detectors.lsnet import LSDetector
+    torch.Tensor.cuda = lambda self, *a, **k: self                 # instances_vote ends in .cuda(): stay on the CPU
+    for task in ('bbox', 'segm', 'pose_bbox'):
+        dets, metas = S.tta_case(task)
+        stub = types.SimpleNamespace(bbox_head=types.SimpleNamespace(task=task, num_classes=3))
+        ab, av, al = [], [], []
+        for i, (b, v, l) in enumerate(dets):                       # lsnet.py:313-320
+            b, v, l = torch.from_numpy(b), torch.from_numpy(v), torch.from_numpy(l)
+            keep = LSDetector.remove_boxes(stub, b, *S.TTA_SCALE_RANGES[i // 2])
+            rec[f'tta_{task}_keep_{i}'] = keep.numpy()
+            ab.append(b[keep, :]); av.append(v[keep, :]); al.append(l[keep])
+        mb, mv, ml = LSDetector.merge_aug_vote_results(stub, ab, av, al, [[m] for m in metas])      # :323-324
+        rec[f'tta_{task}_mapped_boxes'], rec[f'tta_{task}_mapped_vectors'] = mb.numpy(), mv.numpy()
+        ob, ov, ol = [], [], []
+        for j in range(3):                                         # :329-343
+            inds = (ml == j).nonzero().squeeze(1)
+            bj, vj, sj = LSDetector.instances_vote(stub, mb[inds, :4].view(-1, 4), mv[inds], mb[inds, 4])
+            if len(bj) > 0:
+                ob.append(torch.cat([bj, sj[:, None]], dim=1)); ov.append(vj)
+                ol.append(torch.full((bj.shape[0],), j, dtype=torch.int64))
+        rec[f'tta_{task}_boxes'] = torch.cat(ob).numpy()
+        rec[f'tta_{task}_vectors'] = torch.cat(ov).numpy()
+        rec[f'tta_{task}_labels'] = torch.cat(ol).numpy()
+
+    # ---- the head's host-side polygon step on pipeline output (lsnet_head.py:1717-1756) ----
     from mmdet.models.dense_heads.lsnet_head import LSHead
     stub = types.SimpleNamespace(component_polygon_area=lambda poly: LSHead.component_polygon_area(None, poly))
     masks = [samples[('segm', 1, i)]['gt_masks'].data for i in range(len(S.SIZES))]

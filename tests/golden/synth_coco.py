@@ -121,3 +121,40 @@ def eval_pipeline(multi=False):
              dict(type='Pad', size_divisor=32), dict(type='ImageToTensor', keys=['img']),
              dict(type='Collect', keys=['img'])]
     return [dict(type='MultiScaleFlipAug', img_scale=MS_SCALES if multi else SCALE, flip=multi, transforms=inner)]
+
+
+def tta_case(task, seed=0, n_obj=30, num_classes=3):
+    """Synthetic per-augmentation detections for the voting tests: ``n_obj`` objects in a 200x300 original image, seen by
+    4 augmentations (2 scales x {plain, flipped}) with jitter, random scores and occasional misses — so that clusters of
+    1, 2 and 4 members, soft-suppressed leftovers and single-detection classes all occur.  Returns
+    ([(bboxes (n,5), vectors (n,V), labels (n,))] as float32/int64 numpy, [meta dict]) in AUGMENTED coordinates."""
+    rng = np.random.RandomState(900 + seed)
+    H, W = 200, 300
+    V = dict(bbox=8, segm=72, pose_bbox=34)[task]
+    cx, cy = rng.uniform(30, W - 30, n_obj), rng.uniform(30, H - 30, n_obj)
+    bw, bh = rng.uniform(4, 120, n_obj), rng.uniform(4, 90, n_obj)
+    boxes = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    labels = rng.randint(0, num_classes - 1, n_obj)
+    labels[0] = num_classes - 1                                   # a class with exactly one object
+    vec = np.stack([boxes[:, [0]] + rng.rand(n_obj, V // 2) * bw[:, None],
+                    boxes[:, [1]] + rng.rand(n_obj, V // 2) * bh[:, None]], 2).reshape(n_obj, V)
+    dets, metas = [], []
+    for a, (scale, flip) in enumerate([(0.8, False), (0.8, True), (1.5, False), (1.5, True)]):
+        sf = np.array([scale, scale * 1.01, scale, scale * 1.01], np.float32)
+        shape = (int(H * sf[1] + 0.5), int(W * sf[0] + 0.5), 3)
+        seen = rng.rand(n_obj) < (1.0 if a == 0 else 0.7)
+        seen[0] = a == 2                                          # the lone-class object shows up in one augmentation only
+        b = (boxes[seen] + rng.randn(seen.sum(), 4) * 1.5) * sf
+        v = (vec[seen] + rng.randn(seen.sum(), V) * 1.0) * np.tile(sf[:2], V // 2)
+        if flip:
+            b = np.stack([shape[1] - b[:, 2], b[:, 1], shape[1] - b[:, 0], b[:, 3]], 1)
+            v = v.copy()
+            v[:, 0::2] = shape[1] - v[:, 0::2]                    # (landmark ORDER is whatever the network predicts)
+        s = rng.uniform(0.06, 0.95, seen.sum())
+        dets.append((np.concatenate([b, s[:, None]], 1).astype(np.float32), v.astype(np.float32),
+                     labels[seen].astype(np.int64)))
+        metas.append(dict(img_shape=shape, scale_factor=sf, flip=flip, flip_direction='horizontal'))
+    return dets, metas
+
+
+TTA_SCALE_RANGES = [[0, 90], [20, 10000]]

@@ -69,3 +69,77 @@ def test_simple_test_end_to_end():
         assert allb.shape[1] == 5 and np.isfinite(allb).all()
         assert (allb[:, 0] >= 0).all() and (allb[:, 2] <= 320).all() and (allb[:, 3] <= 256).all()
         assert np.concatenate(pts).shape[1] == 8
+
+
+def _vote_model():
+    import lsnet_b200 as L
+    from lsnet_b200.data import MODEL_CFG
+    cfg = MODEL_CFG['bbox_r50']
+    torch.manual_seed(0)
+    test_cfg = dict(TEST_CFG['bbox'], method='vote', scale_ranges=[[0, 100000], [0, 100000]])
+    model = L.build_detector(cfg['model'], train_cfg=cfg['train_cfg'], test_cfg=test_cfg).cuda().eval()
+    torch.nn.init.constant_(model.bbox_head.pts_cls_out.bias, -1.0)          # scores above the 0.05 threshold
+    return model
+
+
+def test_aug_test_vote_of_a_repeated_augmentation_is_simple_test():
+    """Voting over the SAME augmentation twice gives back simple_test's detections: every proper box meets its copy
+    (IoU 1), the pair merges into itself with its own score and the soft-suppressed copy scores 0; NMS has already
+    separated distinct detections below the vote threshold.  A randomly initialised head also decodes inverted /
+    empty boxes (x2 < x1 or y2 < y1): the scale filter drops those of negative area and the rest never overlap
+    anything, as in the reference (lsnet.py:159-164, 236-262) -- so the claim is checked on the proper boxes, and in
+    the other direction every voted detection must be one of simple_test's.  Matching is by nearest box with a
+    budget of two misses each way: the forward is not bit-reproducible, a detection on the top-100 cut may come or go."""
+    from lsnet_b200.data import synthetic_batch
+    model = _vote_model()
+    b = synthetic_batch(0, batch=1, img_hw=(256, 320))
+    img = b['img'].cuda()
+    meta = [dict(b['img_metas'][0], scale_factor=np.ones(4, np.float32), flip=False)]
+    ref = model.simple_test(img, meta)[0]
+    got = model(img=[img, img], img_metas=[meta, meta], return_loss=False)
+    assert len(got) == 2 and len(got[0]) == 80 and len(got[1]) == 80
+    miss_ref = miss_got = proper = 0
+    for c in range(80):
+        rb, rp, gb, gp = ref[0][c], ref[1][c], got[0][c], got[1][c]
+        assert gb.shape[1] == 5 and gp.shape[1] == 8 and len(gb) == len(gp)
+
+        def found(box, pts, pool_b, pool_p):
+            if len(pool_b) == 0:
+                return False
+            d = np.abs(pool_b[:, :4] - box[:4]).max(1)
+            j = int(d.argmin())
+            return d[j] < 1e-2 and abs(pool_b[j, 4] - box[4]) < 1e-3 and np.abs(pool_p[j] - pts).max() < 1e-2
+        for k in range(len(rb)):
+            if rb[k, 2] - rb[k, 0] > 0.5 and rb[k, 3] - rb[k, 1] > 0.5:
+                proper += 1
+                miss_ref += not found(rb[k], rp[k], gb, gp)
+        for k in range(len(gb)):
+            miss_got += not found(gb[k], gp[k], rb, rp)
+    assert proper >= 1 and miss_ref <= 2 and miss_got <= 2, (proper, miss_ref, miss_got)
+
+
+def test_multi_scale_flip_pipeline_to_voted_result(tmp_path):
+    """Image file -> MultiScaleFlipAug test pipeline (2 scales x flip) -> collate -> forward_test -> aug_test_vote."""
+    import cv2
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import synth_coco as S
+    from lsnet_b200 import datasets as D
+    from lsnet_b200.registry import DATASETS
+    for i in range(len(S.SIZES)):
+        cv2.imwrite(str(tmp_path / f'img_{i}.png'), S.image(i))
+    pipe = S.eval_pipeline(True)
+    pipe[0]['img_scale'] = [(448, 256), (640, 384)]
+    ds = DATASETS.get('CocoDataset')(ann_file=S.coco_dict(False), pipeline=[dict(type='LoadImageFromFile')] + pipe,
+                                     img_prefix=str(tmp_path), test_mode=True)
+    batch = D.collate([ds[0]])
+    assert len(batch['img']) == 4 and [m[0]['flip'] for m in batch['img_metas']] == [False, True, False, True]
+    model = _vote_model()
+    res = model(img=[im.cuda() for im in batch['img']], img_metas=batch['img_metas'], return_loss=False, rescale=True)
+    boxes, pts = res
+    assert len(boxes) == 80 and len(pts) == 80
+    allb = np.concatenate(boxes)
+    h, w = S.SIZES[0]
+    assert allb.shape[1] == 5 and np.isfinite(allb).all() and len(allb) > 0
+    # rescale=True: original-image coordinates (decoded boxes are clipped to each augmentation's image before mapping back)
+    assert allb[:, 0].min() >= -1e-3 and allb[:, 2].max() <= w + 1e-3 and allb[:, 3].max() <= h + 1e-3
