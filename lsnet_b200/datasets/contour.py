@@ -120,7 +120,24 @@ class PolygonMasks:
 
     def __init__(self, masks, height, width):
         assert isinstance(masks, list)
+        if len(masks) > 0:
+            assert isinstance(masks[0], list) and isinstance(masks[0][0], np.ndarray)
         self.masks, self.height, self.width = masks, height, width
+
+    def __getitem__(self, index):
+        """structures.py:340-361: an int, a list or an index array -> PolygonMasks of the selected instances."""
+        if isinstance(index, np.ndarray):
+            index = index.tolist()
+        if isinstance(index, list):
+            masks = [self.masks[i] for i in index]
+        else:
+            try:
+                masks = self.masks[index]
+            except Exception:
+                raise ValueError(f'Unsupported input of type {type(index)} for indexing!')
+        if len(masks) and isinstance(masks[0], np.ndarray):
+            masks = [masks]
+        return PolygonMasks(masks, self.height, self.width)
 
     def __len__(self):
         return len(self.masks)

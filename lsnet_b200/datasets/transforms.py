@@ -142,7 +142,7 @@ class Resize:
             self.img_scale = None
         else:
             self.img_scale = img_scale if isinstance(img_scale, list) else [img_scale]
-            self.img_scale = [tuple(s) for s in self.img_scale]
+            assert all(isinstance(s, tuple) for s in self.img_scale), 'img_scale: a tuple or a list of tuples'
         if ratio_range is not None:
             assert len(self.img_scale) == 1
         else:
@@ -431,13 +431,15 @@ class MultiScaleFlipAug:
         self.transforms = Compose(transforms)
         assert (img_scale is None) ^ (scale_factor is None), 'Must have but only one variable can be setted'
         if img_scale is not None:
-            self.img_scale = [tuple(s) for s in (img_scale if isinstance(img_scale, list) else [img_scale])]
+            self.img_scale = img_scale if isinstance(img_scale, list) else [img_scale]
             self.scale_key = 'scale'
+            assert all(isinstance(s, tuple) for s in self.img_scale), 'img_scale: a tuple or a list of tuples'
         else:
             self.img_scale = scale_factor if isinstance(scale_factor, list) else [scale_factor]
             self.scale_key = 'scale_factor'
         self.flip = flip
         self.flip_direction = flip_direction if isinstance(flip_direction, list) else [flip_direction]
+        assert all(isinstance(d, str) for d in self.flip_direction), 'flip_direction: a str or a list of str'
 
     def __call__(self, results):
         aug = []
