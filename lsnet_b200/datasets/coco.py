@@ -66,15 +66,42 @@ class CocoDataset:
                 img_prefix = osp.join(data_root, img_prefix)
         self.ann_file, self.img_prefix, self.seg_prefix, self.proposal_file = ann_file, img_prefix, seg_prefix, None
         self.test_mode, self.filter_empty_gt = test_mode, filter_empty_gt
-        if classes is not None:
-            self.CLASSES = tuple(classes)
+        self.CLASSES = self.get_classes(classes)
         self.data_infos = self.load_annotations(ann_file)
+        if self.custom_classes:
+            self.data_infos = self.get_subset_by_classes()
         if not test_mode:
             keep = self._filter_imgs()
             self.data_infos = [self.data_infos[i] for i in keep]
             self.img_ids = [self.img_ids[i] for i in keep]
             self._set_group_flag()
         self.pipeline = Compose(pipeline)
+
+    def get_classes(self, classes=None):
+        """custom.py:233-257: None keeps the dataset's CLASSES; a list / tuple overrides them (kept as given); a string
+        is a file with one class name per line."""
+        self.custom_classes = classes is not None
+        if classes is None:
+            return type(self).CLASSES
+        if isinstance(classes, str):
+            with open(classes) as f:
+                return [line.rstrip('\n\r') for line in f if line.strip()]
+        if isinstance(classes, (tuple, list)):
+            return classes
+        raise ValueError(f'Unsupported type {type(classes)} of classes.')
+
+    def get_subset_by_classes(self):
+        """coco.py:98-121: with custom classes only the images holding at least one instance of them are kept (json
+        order here; the reference iterates a set)."""
+        wanted = set(self.cat_ids)
+        keep = {i for i, anns in self.coco.img_anns.items() if any(a['category_id'] in wanted for a in anns)}
+        self.img_ids = [i for i in self.img_ids if i in keep]
+        infos = []
+        for i in self.img_ids:
+            info = dict(self.coco.imgs[i])
+            info['filename'] = info['file_name']
+            infos.append(info)
+        return infos
 
     # -- coco.py:32-60 --------------------------------------------------------------------------------------------
     def load_annotations(self, ann_file):

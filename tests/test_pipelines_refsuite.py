@@ -172,3 +172,34 @@ def test_polygon_masks():
         pm[torch.Tensor([1, 2])]
     for i, m in enumerate(pm):
         assert np.equal(m, pm.masks[i]).all()
+
+
+@pytest.mark.parametrize('name', ['CocoDataset', 'CocoPoseDataset'])
+def test_custom_classes_override_default(name, tmp_path):
+    """tests/test_dataset.py:15-86 (on a real annotation dict instead of MagicMocks)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import synth_coco as S
+    from lsnet_b200.registry import DATASETS
+    cls = DATASETS.get(name)
+    original = cls.CLASSES
+    ann = S.coco_dict(name == 'CocoPoseDataset')
+    d = cls(ann_file=ann, pipeline=[], classes=('bus', 'car'), test_mode=True)
+    assert d.CLASSES != original and d.CLASSES == ('bus', 'car') and d.custom_classes
+    d = cls(ann_file=ann, pipeline=[], classes=['bus', 'car'], test_mode=True)
+    assert d.CLASSES == ['bus', 'car'] and d.custom_classes
+    d = cls(ann_file=ann, pipeline=[], classes=['foo'], test_mode=True)
+    assert d.CLASSES == ['foo'] and d.custom_classes and len(d) == 0          # no image holds a 'foo'
+    d = cls(ann_file=ann, pipeline=[], classes=None, test_mode=True)
+    assert d.CLASSES == original and not d.custom_classes and cls.CLASSES == original
+    f = tmp_path / 'classes.txt'
+    f.write_text('bus\ncar\n')
+    d = cls(ann_file=ann, pipeline=[], classes=str(f), test_mode=True)
+    assert d.CLASSES == ['bus', 'car'] and d.custom_classes
+    if name == 'CocoDataset':
+        # the subset: images with at least one 'car' (category 3), labels re-indexed over the custom classes
+        d = cls(ann_file=ann, pipeline=[], classes=('car',))
+        has_car = sorted({a['image_id'] for a in ann['annotations'] if a['category_id'] == 3})
+        assert [i['id'] for i in d.data_infos] == [i for i in has_car if i < 90] and d.cat2label == {3: 0}
+        assert all((d.get_ann_info(k)['labels'] == 0).all() for k in range(len(d)))
