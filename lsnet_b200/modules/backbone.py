@@ -365,6 +365,13 @@ class ResNet(nn.Module):
         if deep_stem or avg_down or plugins is not None or conv_cfg is not None:
             raise NotImplementedError('deep_stem / avg_down / plugins / conv_cfg are not on the LSNet path')
         assert norm_cfg.get('type', 'BN') == 'BN'
+        # resnet.py:377-391: the constructor's own argument checks
+        assert 1 <= num_stages <= 4
+        assert len(strides) == len(dilations) == num_stages
+        assert max(out_indices) < num_stages
+        assert style in ('pytorch', 'caffe')
+        if dcn is not None:
+            assert len(stage_with_dcn) == num_stages
         block, stage_blocks = self.arch_settings[depth]
         self.depth, self.out_indices, self.frozen_stages = depth, out_indices, frozen_stages
         self.norm_eval, self.zero_init_residual, self.dcn = norm_eval, zero_init_residual, dcn
@@ -407,6 +414,8 @@ class ResNet(nn.Module):
                         p.requires_grad = False
         self._freeze_stages()
         self.feat_dim = inplanes
+
+    norm1 = property(lambda self: self.bn1)      # resnet.py:467-470 (the norm layer is registered as 'bn1')
 
     def _freeze_stages(self):          # resnet.py:569-585
         if self.frozen_stages >= 0:
