@@ -314,3 +314,27 @@ def test_eval_pipeline_matches_reference(multi):
         b = loader.collate([out])
         assert isinstance(b['img'], list) and len(b['img']) == len(out['img'])
         assert b['img'][0].shape == (1,) + tuple(out['img'][0].shape) and b['img_metas'][0][0] is out['img_metas'][0]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFGS), reason='reference tree not present')
+@pytest.mark.parametrize('cfg,device_prep', [('lsnet_segm_r50_fpn_1x_coco.py', False), ('lsnet_bbox_r50_fpn_1x_coco.py', True)])
+def test_train_script_dry_run_on_a_reference_config(tmp_path, capsys, cfg, device_prep):
+    """tools/train_coco.py --dry-run: the reference's config file, its dataset / pipeline section unchanged, on image
+    files + a COCO json -> the batches the captured step would receive."""
+    import importlib.util
+    import json
+    import cv2
+    for i in range(len(S.SIZES)):
+        cv2.imwrite(str(tmp_path / f'img_{i}.png'), S.image(i))
+    (tmp_path / 'ann.json').write_text(json.dumps(S.coco_dict(False)))
+    spec = importlib.util.spec_from_file_location('train_coco', os.path.join(os.path.dirname(HERE), 'tools', 'train_coco.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = [os.path.join(REF_CFGS, cfg), '--ann-file', str(tmp_path / 'ann.json'), '--img-prefix', str(tmp_path),
+            '--workers-per-gpu', '0', '--dry-run', '2'] + (['--device-prep'] if device_prep else [])
+    np.random.seed(0)
+    assert mod.main(argv) == 0
+    out = capsys.readouterr().out
+    assert 'CocoDataset: 6 images, 4 iterations' in out and 'batch 1: img' in out
+    assert ('torch.uint8' in out) == device_prep and ('DeviceFormatBundle' in out) == device_prep
+    assert ("'gt_masks'" in out) == ('segm' in cfg) and ("'gt_extremes'" in out) == ('bbox' in cfg)
