@@ -152,11 +152,18 @@ def build_conv_layer(cfg, *args, **kwargs):
 
 
 def install_into_mmdet():
-    """Register the B200 modules into an importable mmdet/mmcv (force=True) so existing configs pick them up."""
+    """Register the B200 modules into an importable mmdet/mmcv (force=True) so existing configs pick them up:
+    models, assigners / samplers, conv layers and -- when mmdet.datasets is importable -- datasets and pipelines."""
     from mmcv.cnn import CONV_LAYERS as M_CONV
-    from mmdet.core.bbox.builder import BBOX_ASSIGNERS as M_ASSIGN
+    from mmdet.core.bbox.builder import BBOX_ASSIGNERS as M_ASSIGN, BBOX_SAMPLERS as M_SAMPLE
     from mmdet.models.builder import BACKBONES as MB, DETECTORS as MD, HEADS as MH, LOSSES as ML, NECKS as MN
-    for src, dst in ((BACKBONES, MB), (NECKS, MN), (HEADS, MH), (LOSSES, ML), (DETECTORS, MD),
-                     (BBOX_ASSIGNERS, M_ASSIGN), (CONV_LAYERS, M_CONV)):
+    pairs = [(BACKBONES, MB), (NECKS, MN), (HEADS, MH), (LOSSES, ML), (DETECTORS, MD), (BBOX_ASSIGNERS, M_ASSIGN),
+             (BBOX_SAMPLERS, M_SAMPLE), (CONV_LAYERS, M_CONV)]
+    try:
+        from mmdet.datasets.builder import DATASETS as M_DATA, PIPELINES as M_PIPE
+        pairs += [(DATASETS, M_DATA), (PIPELINES, M_PIPE)]
+    except ImportError:          # mmdet.datasets needs pycocotools; the model side does not
+        pass
+    for src, dst in pairs:
         for name, cls in src.module_dict.items():
             dst.register_module(name=name, force=True, module=cls)
