@@ -1,0 +1,124 @@
+"""Host logic against the EXECUTED reference (subprocesses: its sys.modules stubs stay out of the other tests).
+INTEGRATION.md §1: ``lsnet_b200.registry.install_into_mmdet()`` against the UNMODIFIED reference mmdet /
+mmcv (imported from /root/reference through oracle/ref_harness.py, in a subprocess so that its sys.modules stubs stay out of
+the other tests).  After the call the reference's own ``build_detector`` / ``build_dataset`` / pipeline ``Compose`` build the
+B200 classes from the reference's config file."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = textwrap.dedent('''
+    import sys
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    ns = rh.load()
+    import mmdet.datasets                                    # the reference's registries, all of them
+    from mmdet.models.builder import DETECTORS, HEADS, BACKBONES
+    from mmdet.datasets.builder import PIPELINES, DATASETS
+    ref_head, ref_resize = HEADS.get('LSHead'), PIPELINES.get('Resize')
+    import lsnet_b200
+    lsnet_b200.registry.install_into_mmdet()
+    assert HEADS.get('LSHead') is lsnet_b200.HEADS.get('LSHead') is not ref_head
+    assert PIPELINES.get('Resize') is lsnet_b200.PIPELINES.get('Resize') is not ref_resize
+    assert DATASETS.get('CocoDataset') is lsnet_b200.DATASETS.get('CocoDataset')
+    cfg = ns.Config.fromfile(ns.root + '/configs/lsnet/lsnet_bbox_r50_fpn_1x_coco.py')
+    cfg.model.pretrained = None
+    model = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)     # mmdet's own builder
+    assert type(model).__module__.startswith('lsnet_b200.') and type(model.bbox_head).__module__.startswith('lsnet_b200.')
+    assert type(model.backbone).__module__.startswith('lsnet_b200.') and type(model.neck).__module__.startswith('lsnet_b200.')
+    assert type(model.bbox_head.cls_convs[0].conv).__module__.startswith('lsnet_b200.')      # CONV_LAYERS 'DCNv2'
+    assert sum(p.numel() for p in model.parameters()) == 38802018                           # SURVEY 8c
+    from mmdet.datasets.pipelines import Compose
+    pipe = Compose(cfg.data.train.pipeline)                                                 # mmdet's own Compose
+    assert all(type(t).__module__.startswith('lsnet_b200.') for t in pipe.transforms)
+    print('INSTALLED')
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_install_into_mmdet_swaps_the_reference_registries():
+    r = subprocess.run([sys.executable, '-c', SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'INSTALLED' in r.stdout, r.stderr[-3000:]
+
+
+LR_SCRIPT = textwrap.dedent('''
+    import sys, types, json
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    rh.load()
+    import torch
+    from mmcv.runner.hooks.lr_updater import StepLrUpdaterHook
+    from lsnet_b200.train import LrSchedule
+    out = {}
+    for name, cfg in (('1x', dict(warmup='linear', warmup_iters=500, warmup_ratio=0.001, step=[8, 11])),
+                      ('exp', dict(warmup='exp', warmup_iters=40, warmup_ratio=0.1, step=[2], gamma=0.5)),
+                      ('const', dict(warmup='constant', warmup_iters=30, warmup_ratio=1.0 / 3, step=[1, 3]))):
+        hook = StepLrUpdaterHook(by_epoch=True, **cfg)
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.01, momentum=0.9)
+        runner = types.SimpleNamespace(optimizer=opt, epoch=0, iter=0)
+        hook.before_run(runner)
+        ours = LrSchedule(0.01, dict(policy='step', **cfg), iters_per_epoch=60)
+        worst = 0.0
+        for epoch in range(13):                      # the runner's call order: epoch hook, then one iteration hook per step
+            runner.epoch = epoch
+            hook.before_train_epoch(runner)
+            for i in range(60):
+                hook.before_train_iter(runner)
+                ref = opt.param_groups[0]['lr']
+                worst = max(worst, abs(ref - ours(runner.iter)) / ref)
+                runner.iter += 1
+        out[name] = worst
+    print('LR', json.dumps(out))
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_lr_schedule_matches_the_executed_mmcv_hook():
+    """LrSchedule against mmcv's StepLrUpdaterHook driven through the runner's hook order (mmcv/runner/hooks/
+    lr_updater.py:100-172) for 13 epochs x 60 iterations: schedule_1x of the LSNet configs plus exp / constant warm-up."""
+    import json
+    r = subprocess.run([sys.executable, '-c', LR_SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    worst = json.loads([l for l in r.stdout.splitlines() if l.startswith('LR ')][0][3:])
+    assert all(v < 1e-12 for v in worst.values()), worst
+
+
+PARSE_SCRIPT = textwrap.dedent('''
+    import sys, json
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    rh.load()
+    import torch
+    from mmdet.models.detectors.base import BaseDetector
+    from lsnet_b200.modules.detector import parse_losses
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.rand(*s, generator=g)
+    losses = {'loss_cls': [r(()), r(()), r(()), r(()), r(())], 'loss_bbox_init': [r(3), r(())], 'loss_bbox_refine': r(4, 2),
+              'acc': r(()), 'num_pos': [r(())]}
+    ref_loss, ref_log = BaseDetector._parse_losses(None, losses)
+    loss, log = parse_losses(losses, sync_log=True)
+    assert list(log) == list(ref_log)                       # same keys, same order ('acc' / 'num_pos' logged, not summed)
+    worst = max(abs(log[k] - ref_log[k]) / abs(ref_log[k]) for k in log)
+    worst = max(worst, abs(float(loss) - float(ref_loss)) / float(ref_loss))
+    try:
+        parse_losses({'loss_x': 1.0})
+    except TypeError:
+        worst = max(worst, 0.0)
+    else:
+        worst = 1.0
+    print('PARSE', worst)
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_parse_losses_matches_the_executed_reference():
+    """parse_losses against BaseDetector._parse_losses (mmdet/models/detectors/base.py:176-209) on a loss dict with
+    per-level lists, non-scalar entries and logged-only keys."""
+    r = subprocess.run([sys.executable, '-c', PARSE_SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    worst = float([l for l in r.stdout.splitlines() if l.startswith('PARSE ')][0].split()[1])
+    assert worst < 1e-6, worst
