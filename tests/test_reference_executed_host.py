@@ -122,3 +122,73 @@ def test_parse_losses_matches_the_executed_reference():
     assert r.returncode == 0, r.stderr[-3000:]
     worst = float([l for l in r.stdout.splitlines() if l.startswith('PARSE ')][0].split()[1])
     assert worst < 1e-6, worst
+
+
+CONFIG_SCRIPT = textwrap.dedent('''
+    import sys, glob, os
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    ns = rh.load()
+    import lsnet_b200
+
+    def plain(v):
+        if isinstance(v, dict):
+            return {k: plain(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return type(v)(plain(x) for x in v)
+        return v
+    n = 0
+    for f in sorted(glob.glob(ns.root + '/configs/lsnet/*.py')):
+        ref = plain(ns.Config.fromfile(f)._cfg_dict.to_dict())
+        own = plain(lsnet_b200.Config.fromfile(f).to_dict())
+        assert own == ref, (os.path.basename(f), sorted(set(own) ^ set(ref)),
+                            [k for k in ref if k in own and own[k] != ref[k]])
+        n += 1
+    print('CONFIGS', n)
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_config_loader_equals_mmcv_config_on_every_lsnet_config():
+    """lsnet_b200.Config.fromfile against mmcv's Config.fromfile (mmcv/mmcv/utils/config.py: `_base_` inheritance, dict
+    merge, `_delete_`): the resulting dictionaries are EQUAL, key for key (tuples stay tuples), for all 17 files under
+    configs/lsnet/."""
+    r = subprocess.run([sys.executable, '-c', CONFIG_SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'CONFIGS 17' in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+
+
+INIT_SCRIPT = textwrap.dedent('''
+    import sys
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    ns = rh.load()
+    import torch, lsnet_b200
+    for name, n_dcn in (('lsnet_bbox_r50_fpn_1x_coco.py', 0), ('lsnet_segm_r50_fpn_1x_coco.py', 0),
+                        ('lsnet_pose_bbox_r50_fpn_1x_coco.py', 0), ('lsnet_segm_x101_fpn_mstrain_30e_coco.py', 0),
+                        ('lsnet_pose_kbox_x101_fpn_dconv_c3-c5_mstrain_2x_coco.py', 30)):
+        f = ns.root + '/configs/lsnet/' + name
+        cfg = ns.Config.fromfile(f); cfg.model.pretrained = None
+        ref = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        c2 = lsnet_b200.Config.fromfile(f); c2.model.pretrained = None
+        own = lsnet_b200.build_detector(c2.model, train_cfg=c2.train_cfg, test_cfg=c2.test_cfg)
+        torch.manual_seed(7); ref.init_weights(); a = torch.rand(1).item()
+        torch.manual_seed(7); own.init_weights(); b = torch.rand(1).item()
+        rs, os_ = ref.state_dict(), own.state_dict()
+        assert list(rs) == list(os_), name                                  # same keys in the same order
+        assert all(rs[k].shape == os_[k].shape for k in rs), name
+        diff = [k for k in rs if not torch.equal(rs[k], os_[k])]
+        # the trunk's DCN weights are drawn in the constructor (ResNet.init_weights only re-draws nn.Conv2d): they depend on
+        # the construction-time RNG stream, everything else is set by init_weights
+        assert len(diff) == n_dcn and all(k.startswith('backbone.') and k.endswith('.conv2.weight') for k in diff), (name, diff[:5])
+        assert a == b, name                                                 # init_weights consumed the same random stream
+    print('INIT OK')
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_init_weights_is_bit_identical_to_the_reference():
+    """Same seed before ``init_weights()`` -> the same initial model as the reference, tensor for tensor (state_dict
+    keys, order, shapes, values) for the R50 bbox / segm / pose and the X-101 configs; with DCN in the trunk the 30
+    constructor-drawn ``conv2.weight`` tensors are the only ones that differ."""
+    r = subprocess.run([sys.executable, '-c', INIT_SCRIPT], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and 'INIT OK' in r.stdout, r.stderr[-3000:]
