@@ -192,3 +192,71 @@ def test_init_weights_is_bit_identical_to_the_reference():
     constructor-drawn ``conv2.weight`` tensors are the only ones that differ."""
     r = subprocess.run([sys.executable, '-c', INIT_SCRIPT], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'INIT OK' in r.stdout, r.stderr[-3000:]
+
+
+CKPT_SCRIPT = textwrap.dedent('''
+    import sys, os, tempfile
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    ns = rh.load()
+    import torch, lsnet_b200
+    from mmcv.runner import load_checkpoint, save_checkpoint as mmcv_save
+    from lsnet_b200.train import Trainer, resume, save_checkpoint
+    f = ns.root + '/configs/lsnet/lsnet_bbox_r50_fpn_1x_coco.py'
+    cfg = ns.Config.fromfile(f); cfg.model.pretrained = None
+    tmp = tempfile.mkdtemp()
+
+    def fake_step(params, opt, seed):            # gradients without a forward pass (the kernels need a GPU)
+        g = torch.Generator().manual_seed(seed)
+        for p in params:
+            if p.requires_grad:
+                p.grad = torch.randn(p.shape, generator=g) * 1e-3
+        opt.step()
+
+    # reference -> here: a checkpoint written by mmcv's save_checkpoint after one SGD step of the reference model
+    torch.manual_seed(0)
+    ref = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg); ref.init_weights()
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)      # mmcv build_optimizer: all params
+    fake_step(list(ref.parameters()), ropt, 1)
+    mmcv_save(ref, os.path.join(tmp, 'ref.pth'), optimizer=ropt, meta=dict(epoch=5, iter=1234))
+    c2 = lsnet_b200.Config.fromfile(f); c2.model.pretrained = None
+    tr = Trainer(c2, device='cpu')
+    meta = resume(tr, os.path.join(tmp, 'ref.pth'))
+    assert meta['epoch'] == 5 and tr.iter == 1234
+    rs = ref.state_dict()
+    assert all(torch.equal(v, rs[k]) for k, v in tr.core.state_dict().items())
+    rp, op = list(ref.parameters()), list(tr.core.parameters())
+    n = 0
+    for a, b in zip(rp, op):
+        if a in ropt.state:
+            assert torch.equal(ropt.state[a]['momentum_buffer'], tr.optimizer.state[b]['momentum_buffer']); n += 1
+        else:
+            assert b not in tr.optimizer.state or not tr.optimizer.state[b]
+    assert n == sum(p.requires_grad for p in rp) == len(tr.params)
+    # ... and both continue identically
+    fake_step(rp, ropt, 2); fake_step(op, tr.optimizer, 2)
+    assert all(torch.equal(a, b) for a, b in zip(rp, op))
+
+    # here -> reference: our file through mmcv's load_checkpoint + the reference optimizer's load_state_dict
+    save_checkpoint(tr, os.path.join(tmp, 'own.pth'), epoch=6)
+    torch.manual_seed(9)
+    ref2 = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    ck = load_checkpoint(ref2, os.path.join(tmp, 'own.pth'), map_location='cpu', strict=True)
+    assert ck['meta']['epoch'] == 6 and ck['meta']['iter'] == 1234
+    ropt2 = torch.optim.SGD(ref2.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    ropt2.load_state_dict(ck['optimizer'])
+    assert all(torch.equal(a, b) for a, b in zip(ref2.parameters(), op))
+    fake_step(list(ref2.parameters()), ropt2, 3); fake_step(op, tr.optimizer, 3)
+    assert all(torch.equal(a, b) for a, b in zip(ref2.parameters(), op))
+    print('CKPT OK')
+''') % ROOT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_checkpoints_cross_the_boundary_both_ways():
+    """A checkpoint written by mmcv's ``save_checkpoint`` (reference model + its SGD over all parameters) resumes here
+    -- weights, momentum buffers, epoch / iter -- and both sides take the same next step; a checkpoint written by
+    ``lsnet_b200.train.save_checkpoint`` loads through mmcv's ``load_checkpoint(strict=True)`` and the reference
+    optimizer's ``load_state_dict`` and continues identically too."""
+    r = subprocess.run([sys.executable, '-c', CKPT_SCRIPT], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and 'CKPT OK' in r.stdout, r.stderr[-3000:]
