@@ -257,12 +257,24 @@ class Bottleneck(nn.Module):
     expansion = 4
 
     def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, style='pytorch', with_cp=False,
-                 dcn=None, groups=1, base_width=4, base_channels=64):
+                 dcn=None, groups=1, base_width=4, base_channels=64, ref_parent_draws=False):
         super().__init__()
         assert style in ('pytorch', 'caffe')
         width = planes if groups == 1 else int(planes * (base_width / base_channels)) * groups   # resnext.py:33-37
         s1, s2 = (1, stride) if style == 'pytorch' else (stride, 1)
         self.with_cp, self.with_dcn = with_cp, dcn is not None
+        if ref_parent_draws and os.environ.get('LSNET_REF_INIT_STREAM', '0') == '1':
+            # The reference's ResNeXt block first runs the plain ResNet Bottleneck constructor -- planes-wide convs, its
+            # own DCN pack -- and then replaces the three convs (resnext.py:14-24, 39-86).  Opt-in: draw the same random
+            # numbers, so that a seeded build reproduces the reference's constructor-initialised DCN weights bit for bit.
+            nn.Conv2d(inplanes, planes, 1, stride=s1, bias=False)
+            d0 = dict(dcn) if dcn is not None else None
+            if d0 is None or d0.pop('fallback_on_stride', False):
+                nn.Conv2d(planes, planes, 3, stride=s2, padding=dilation, dilation=dilation, bias=False)
+            else:
+                build_conv_layer(d0, planes, planes, kernel_size=3, stride=s2, padding=dilation, dilation=dilation,
+                                 bias=False)
+            nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
         self.conv1 = nn.Conv2d(inplanes, width, 1, stride=s1, bias=False)
         self.bn1 = nn.BatchNorm2d(width)
         fallback = False
@@ -353,6 +365,7 @@ class Bottleneck(nn.Module):
 @BACKBONES.register_module()
 class ResNet(nn.Module):
     arch_settings = {50: (Bottleneck, (3, 4, 6, 3)), 101: (Bottleneck, (3, 4, 23, 3)), 152: (Bottleneck, (3, 8, 36, 3))}
+    _resnext_blocks = False      # ResNeXt: the reference's block class constructs its convs twice (see Bottleneck)
 
     def __init__(self, depth, in_channels=3, stem_channels=64, base_channels=64, num_stages=4, strides=(1, 2, 2, 2),
                  dilations=(1, 1, 1, 1), out_indices=(0, 1, 2, 3), style='pytorch', deep_stem=False, avg_down=False,
@@ -392,7 +405,8 @@ class ResNet(nn.Module):
                     down = nn.Sequential(nn.Conv2d(inplanes, planes * block.expansion, 1, stride=stride, bias=False),
                                          nn.BatchNorm2d(planes * block.expansion))
                 layers.append(block(inplanes, planes, stride, dilations[i], down, style, with_cp,
-                                    dcn if stage_with_dcn[i] else None, groups, base_width, base_channels))
+                                    dcn if stage_with_dcn[i] else None, groups, base_width, base_channels,
+                                    ref_parent_draws=self._resnext_blocks))
                 inplanes = planes * block.expansion
             # backward-fusion topology (Bottleneck._inner_fused): a block's input is the previous block's ReLU output
             # (the first block of stage 1 reads the max-pool instead); the output of every block but the stage's last has
@@ -514,6 +528,7 @@ class ResNet(nn.Module):
 @BACKBONES.register_module()
 class ResNeXt(ResNet):
     """resnext.py:76-131: Bottleneck width = planes * base_width / 64 * groups."""
+    _resnext_blocks = True
 
     def __init__(self, groups=1, base_width=4, **kwargs):
         super().__init__(groups=groups, base_width=base_width, **kwargs)

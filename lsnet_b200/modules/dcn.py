@@ -119,6 +119,13 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
                                      padding=self.padding, dilation=self.dilation, bias=True)
         self.conv_offset.weight._lsnet_tapmajor = self.stride == (1, 1)
         self.init_offset()
+        if os.environ.get('LSNET_REF_INIT_STREAM', '0') == '1':
+            # the reference draws this weight a second time AFTER conv_offset's default initialisation (the base class
+            # constructor and the pack constructor both end in the overridden init_weights, deform_conv.py:470-472,
+            # 519-525); trunk DCN weights keep their constructor value (ResNet.init_weights only re-draws nn.Conv2d), so
+            # reproducing the reference's seeded initial model bit for bit needs the same second draw.  Opt-in: it shifts
+            # the random stream of everything constructed afterwards.
+            self.reset_parameters()
 
     def init_offset(self):
         self.conv_offset.weight.data.zero_()

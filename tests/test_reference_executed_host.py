@@ -181,6 +181,19 @@ INIT_SCRIPT = textwrap.dedent('''
         # the construction-time RNG stream, everything else is set by init_weights
         assert len(diff) == n_dcn and all(k.startswith('backbone.') and k.endswith('.conv2.weight') for k in diff), (name, diff[:5])
         assert a == b, name                                                 # init_weights consumed the same random stream
+    # with the reference's construction-time random stream reproduced (LSNET_REF_INIT_STREAM=1) and the seed set before
+    # the build as well, the DCN trunk is identical too
+    import os
+    os.environ['LSNET_REF_INIT_STREAM'] = '1'
+    f = ns.root + '/configs/lsnet/lsnet_bbox_x101_fpn_dconv_c3-c5_mstrain_2x_coco.py.py'
+    cfg = ns.Config.fromfile(f); cfg.model.pretrained = None
+    torch.manual_seed(3); ref = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    c2 = lsnet_b200.Config.fromfile(f); c2.model.pretrained = None
+    torch.manual_seed(3); own = lsnet_b200.build_detector(c2.model, train_cfg=c2.train_cfg, test_cfg=c2.test_cfg)
+    torch.manual_seed(7); ref.init_weights()
+    torch.manual_seed(7); own.init_weights()
+    rs, os_ = ref.state_dict(), own.state_dict()
+    assert list(rs) == list(os_) and all(torch.equal(rs[k], os_[k]) for k in rs), [k for k in rs if not torch.equal(rs[k], os_[k])][:5]
     print('INIT OK')
 ''') % ROOT
 
@@ -189,7 +202,8 @@ INIT_SCRIPT = textwrap.dedent('''
 def test_init_weights_is_bit_identical_to_the_reference():
     """Same seed before ``init_weights()`` -> the same initial model as the reference, tensor for tensor (state_dict
     keys, order, shapes, values) for the R50 bbox / segm / pose and the X-101 configs; with DCN in the trunk the 30
-    constructor-drawn ``conv2.weight`` tensors are the only ones that differ."""
+    constructor-drawn ``conv2.weight`` tensors are the only ones that differ -- and not even those with
+    ``LSNET_REF_INIT_STREAM=1`` and the seed set before the build too."""
     r = subprocess.run([sys.executable, '-c', INIT_SCRIPT], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'INIT OK' in r.stdout, r.stderr[-3000:]
 
