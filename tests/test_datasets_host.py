@@ -338,3 +338,28 @@ def test_train_script_dry_run_on_a_reference_config(tmp_path, capsys, cfg, devic
     assert 'CocoDataset: 6 images, 4 iterations' in out and 'batch 1: img' in out
     assert ('torch.uint8' in out) == device_prep and ('DeviceFormatBundle' in out) == device_prep
     assert ("'gt_masks'" in out) == ('segm' in cfg) and ("'gt_extremes'" in out) == ('bbox' in cfg)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFGS), reason='reference tree not present')
+def test_test_script_dry_run_on_a_reference_config(tmp_path, capsys):
+    """tools/test_coco.py --dry-run: the reference config's own test pipeline (MultiScaleFlipAug), optionally widened to
+    several scales + flip, over image files -> the per-image augmentation lists forward_test takes."""
+    import importlib.util
+    import json
+    import cv2
+    for i in range(len(S.SIZES)):
+        cv2.imwrite(str(tmp_path / f'img_{i}.png'), S.image(i))
+    ann = S.coco_dict(False)
+    ann['images'] = ann['images'][:len(S.SIZES)]
+    (tmp_path / 'ann.json').write_text(json.dumps(ann))
+    spec = importlib.util.spec_from_file_location('test_coco', os.path.join(os.path.dirname(HERE), 'tools', 'test_coco.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    base = [os.path.join(REF_CFGS, 'lsnet_bbox_r50_fpn_1x_coco.py'), '--ann-file', str(tmp_path / 'ann.json'),
+            '--img-prefix', str(tmp_path), '--workers', '0', '--dry-run', '2']
+    assert mod.main(base) == 0
+    out = capsys.readouterr().out
+    assert 'CocoDataset: 6 images' in out and 'image 1: 1 augmentation(s)' in out and 'flips [False]' in out
+    assert mod.main(base + ['--scales', '[(320, 192), (448, 256)]', '--flip']) == 0
+    out = capsys.readouterr().out
+    assert 'image 0: 4 augmentation(s)' in out and 'flips [False, True, False, True]' in out
