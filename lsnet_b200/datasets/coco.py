@@ -213,8 +213,83 @@ class CocoDataset:
             return data
 
 
+    # -- results -> COCO json (coco_pose.py:174-329; LSNet results are [boxes per class, landmark vectors per class]) --
+    @staticmethod
+    def xyxy2xywh(bbox):
+        b = bbox.tolist()
+        return [b[0], b[1], b[2] - b[0], b[3] - b[1]]
+
+    def _records(self, results):
+        """(image id, category id, box row (5,), vector row) of every detection, in the reference's nesting order
+        (image, class, detection)."""
+        for idx in range(len(self)):
+            boxes, vecs = results[idx][0], results[idx][1]
+            for label in range(len(boxes)):
+                for i in range(boxes[label].shape[0]):
+                    yield self.img_ids[idx], self.cat_ids[label], boxes[label][i], vecs[label][i]
+
+    def _det2json(self, results):
+        return [dict(image_id=im, bbox=self.xyxy2xywh(b), score=float(b[4]), category_id=c)
+                for im, c, b, _ in self._records(results)]
+
+    def _poly2json(self, results):
+        """Contour results as COCO polygon segmentations (one ring of ``num_vectors`` points per instance); mask AP then
+        comes from pycocotools, which rasterises polygons itself."""
+        return [dict(image_id=im, bbox=self.xyxy2xywh(b), score=float(b[4]), category_id=c,
+                     segmentation=[[float(x) for x in v]]) for im, c, b, v in self._records(results)]
+
+    def results2json(self, results, outfile_prefix):
+        """``<prefix>.bbox.json`` always; ``<prefix>.segm.json`` when the vectors are contours (more than the 4 extreme
+        points).  Returns the dict of written files (keys as coco.py:281-320)."""
+        import json as _json
+        files = dict(bbox=f'{outfile_prefix}.bbox.json', proposal=f'{outfile_prefix}.bbox.json')
+        with open(files['bbox'], 'w') as f:
+            _json.dump(self._det2json(results), f)
+        width = next((v.shape[1] for r in results for v in r[1] if v.shape[0]), 0)
+        if width > 8:
+            files['segm'] = f'{outfile_prefix}.segm.json'
+            with open(files['segm'], 'w') as f:
+                _json.dump(self._poly2json(results), f)
+        return files
+
+    def format_results(self, results, jsonfile_prefix=None, **kwargs):
+        """coco.py:342-368."""
+        import os.path as osp
+        import tempfile
+        assert isinstance(results, list), 'results must be a list'
+        assert len(results) == len(self), f'The length of results is not equal to the dataset len: {len(results)} != {len(self)}'
+        tmp = None
+        if jsonfile_prefix is None:
+            tmp = tempfile.TemporaryDirectory()
+            jsonfile_prefix = osp.join(tmp.name, 'results')
+        return self.results2json(results, jsonfile_prefix), tmp
+
+    def evaluate(self, results, metric='bbox', **kwargs):
+        raise NotImplementedError('COCO AP needs pycocotools (COCOeval), which is outside this path: write the json files '
+                                  'with format_results() and evaluate them with the COCO API')
+
+
 @DATASETS.register_module()
 class CocoPoseDataset(CocoDataset):
     """coco_pose.py:26-170: person keypoints, rows of 17 × [x, y, v]."""
     CLASSES = ('person',)
     LANDMARK_FIELD = ('keypoints', 'keypoints', 51)
+
+    def _kps2json(self, results):
+        """coco_pose.py:226-247: 17 (x, y) landmarks -> COCO keypoints with visibility 1, scored by the box score."""
+        out = []
+        for im, c, b, v in self._records(results):
+            kps = np.concatenate([v.reshape(-1, 2), np.ones((17, 1), dtype=np.float32)], axis=1).reshape(51).tolist()
+            out.append(dict(image_id=im, bbox=self.xyxy2xywh(b), keypoints=kps, score=float(b[4]), category_id=c))
+        return out
+
+    def results2json(self, results, outfile_prefix):
+        """coco_pose.py:287-329: ``.bbox.json`` and ``.kps.json``."""
+        import json as _json
+        files = dict(bbox=f'{outfile_prefix}.bbox.json', proposal=f'{outfile_prefix}.bbox.json',
+                     keypoints=f'{outfile_prefix}.kps.json')
+        with open(files['bbox'], 'w') as f:
+            _json.dump(self._det2json(results), f)
+        with open(files['keypoints'], 'w') as f:
+            _json.dump(self._kps2json(results), f)
+        return files

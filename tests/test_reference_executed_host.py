@@ -274,3 +274,60 @@ def test_checkpoints_cross_the_boundary_both_ways():
     optimizer's ``load_state_dict`` and continues identically too."""
     r = subprocess.run([sys.executable, '-c', CKPT_SCRIPT], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and 'CKPT OK' in r.stdout, r.stderr[-3000:]
+
+
+JSON_SCRIPT = textwrap.dedent('''
+    import sys, json, os, tempfile
+    sys.path.insert(0, %r)
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    rh.load()
+    import numpy as np
+    from mmdet.datasets.coco_pose import CocoPoseDataset as RefPose
+    import synth_coco as S
+    import lsnet_b200
+    rng = np.random.RandomState(0)
+
+    def fake_results(n_img, n_cls, width):
+        out = []
+        for _ in range(n_img):
+            ns = [int(rng.randint(0, 4)) for _ in range(n_cls)]
+            xy = [rng.rand(n, 2).astype(np.float32) * 50 for n in ns]
+            boxes = [np.concatenate([p, p + 1 + rng.rand(len(p), 2).astype(np.float32) * 30, rng.rand(len(p), 1).astype(np.float32)], 1)
+                     for p in xy]
+            out.append([boxes, [rng.rand(n, width).astype(np.float32) * 80 for n in ns]])
+        return out
+    own = lsnet_b200.DATASETS.get('CocoPoseDataset')(ann_file=S.coco_dict(True), pipeline=[], test_mode=True)
+    res = fake_results(len(own), 1, 34)
+
+    class Stub:                                  # what the reference methods read from the dataset object
+        img_ids, cat_ids = own.img_ids, own.cat_ids
+        xyxy2xywh = RefPose.xyxy2xywh
+        def __len__(self):
+            return len(own)
+    assert own._det2json(res) == RefPose._det2json(Stub(), res)
+    assert own._kps2json(res) == RefPose._kps2json(Stub(), res)
+    tmp = tempfile.mkdtemp()
+    files = own.results2json(res, os.path.join(tmp, 'r'))
+    assert sorted(files) == ['bbox', 'keypoints', 'proposal'] and json.load(open(files['keypoints'])) == own._kps2json(res)
+    det = lsnet_b200.DATASETS.get('CocoDataset')(ann_file=S.coco_dict(False), pipeline=[], test_mode=True)
+    r8, r72 = fake_results(len(det), len(det.cat_ids), 8), fake_results(len(det), len(det.cat_ids), 72)
+    class Stub2(Stub):
+        img_ids, cat_ids = det.img_ids, det.cat_ids
+        def __len__(self):
+            return len(det)
+    assert det._det2json(r8) == RefPose._det2json(Stub2(), r8)
+    assert sorted(det.results2json(r8, os.path.join(tmp, 'a'))) == ['bbox', 'proposal']
+    f72 = det.results2json(r72, os.path.join(tmp, 'b'))
+    segm = json.load(open(f72['segm']))
+    assert len(segm) == sum(len(b) for r in r72 for b in r[0]) and all(len(s['segmentation'][0]) == 72 for s in segm)
+    print('JSON OK')
+''') % (ROOT, os.path.join(ROOT, 'tests', 'golden'))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_results_to_coco_json_matches_the_reference():
+    """Result lists -> COCO json records: ``_det2json`` / ``_kps2json`` equal to the reference's (coco_pose.py:209-247) on
+    random LSNet-format results; the contour variant writes one polygon per instance."""
+    r = subprocess.run([sys.executable, '-c', JSON_SCRIPT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'JSON OK' in r.stdout, r.stderr[-3000:]

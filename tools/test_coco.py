@@ -79,7 +79,8 @@ def main(argv=None):
         results.append(r[0] if len(b['img']) == 1 else r)       # simple_test returns a list over the batch
     with open(args.out, 'wb') as f:
         pickle.dump(results, f)
-    print(f'wrote {len(results)} results to {args.out}')
+    files, _ = ds.format_results(results, jsonfile_prefix=os.path.splitext(args.out)[0])      # COCO json for the COCO API
+    print(f'wrote {len(results)} results to {args.out} and {sorted(set(files.values()))}')
     return 0
 
 
