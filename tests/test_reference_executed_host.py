@@ -4,6 +4,7 @@ mmcv (imported from /root/reference through oracle/ref_harness.py, in a subproce
 the other tests).  After the call the reference's own ``build_detector`` / ``build_dataset`` / pipeline ``Compose`` build the
 B200 classes from the reference's config file."""
 import os
+import re
 import subprocess
 import sys
 import textwrap
@@ -11,6 +12,37 @@ import textwrap
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SECTIONS = {}          # name -> script; all of them run in ONE subprocess (the reference import costs ~15 s)
+_RESULT = {}
+
+
+def _section(name):
+    """Run every registered script once (each in its own namespace, failures isolated) and return (ok, output) of one."""
+    if not _RESULT:
+        parts = ['import sys, traceback, io, contextlib']
+        # 'install' swaps the reference's registries for the B200 classes: it must run LAST, the other sections compare
+        # against the genuine reference classes
+        order = [n for n in _SECTIONS if n != 'install'] + ['install']
+        for n in order:
+            src = _SECTIONS[n]
+            parts.append(f'''
+_buf = io.StringIO()
+try:
+    with contextlib.redirect_stdout(_buf):
+        exec(compile({src!r}, {n!r}, 'exec'), {{'__name__': {n!r}}})
+    print('@@SECTION {n} OK')
+except BaseException:
+    print('@@SECTION {n} FAIL')
+    traceback.print_exc(file=sys.stdout)
+print(_buf.getvalue())
+print('@@END {n}')
+''')
+        r = subprocess.run([sys.executable, '-c', '\n'.join(parts)], capture_output=True, text=True, timeout=1500)
+        out = r.stdout
+        for n in _SECTIONS:
+            m = re.search(rf'@@SECTION {n} (OK|FAIL)\n(.*?)@@END {n}', out, re.S)
+            _RESULT[n] = (bool(m) and m.group(1) == 'OK', (m.group(2) if m else out[-2000:]) + r.stderr[-1500:])
+    return _RESULT[name]
 SCRIPT = textwrap.dedent('''
     import sys
     sys.path.insert(0, %r)
@@ -37,12 +69,13 @@ SCRIPT = textwrap.dedent('''
     assert all(type(t).__module__.startswith('lsnet_b200.') for t in pipe.transforms)
     print('INSTALLED')
 ''') % ROOT
+_SECTIONS['install'] = SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
 def test_install_into_mmdet_swaps_the_reference_registries():
-    r = subprocess.run([sys.executable, '-c', SCRIPT], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and 'INSTALLED' in r.stdout, r.stderr[-3000:]
+    ok, out = _section('install')
+    assert ok and 'INSTALLED' in out, out
 
 
 LR_SCRIPT = textwrap.dedent('''
@@ -74,6 +107,7 @@ LR_SCRIPT = textwrap.dedent('''
         out[name] = worst
     print('LR', json.dumps(out))
 ''') % ROOT
+_SECTIONS['lr'] = LR_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
@@ -81,9 +115,9 @@ def test_lr_schedule_matches_the_executed_mmcv_hook():
     """LrSchedule against mmcv's StepLrUpdaterHook driven through the runner's hook order (mmcv/runner/hooks/
     lr_updater.py:100-172) for 13 epochs x 60 iterations: schedule_1x of the LSNet configs plus exp / constant warm-up."""
     import json
-    r = subprocess.run([sys.executable, '-c', LR_SCRIPT], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
-    worst = json.loads([l for l in r.stdout.splitlines() if l.startswith('LR ')][0][3:])
+    ok, out = _section('lr')
+    assert ok, out
+    worst = json.loads([l for l in out.splitlines() if l.startswith('LR ')][0][3:])
     assert all(v < 1e-12 for v in worst.values()), worst
 
 
@@ -112,15 +146,16 @@ PARSE_SCRIPT = textwrap.dedent('''
         worst = 1.0
     print('PARSE', worst)
 ''') % ROOT
+_SECTIONS['parse'] = PARSE_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
 def test_parse_losses_matches_the_executed_reference():
     """parse_losses against BaseDetector._parse_losses (mmdet/models/detectors/base.py:176-209) on a loss dict with
     per-level lists, non-scalar entries and logged-only keys."""
-    r = subprocess.run([sys.executable, '-c', PARSE_SCRIPT], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
-    worst = float([l for l in r.stdout.splitlines() if l.startswith('PARSE ')][0].split()[1])
+    ok, out = _section('parse')
+    assert ok, out
+    worst = float([l for l in out.splitlines() if l.startswith('PARSE ')][0].split()[1])
     assert worst < 1e-6, worst
 
 
@@ -146,6 +181,7 @@ CONFIG_SCRIPT = textwrap.dedent('''
         n += 1
     print('CONFIGS', n)
 ''') % ROOT
+_SECTIONS['config'] = CONFIG_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
@@ -153,8 +189,8 @@ def test_config_loader_equals_mmcv_config_on_every_lsnet_config():
     """lsnet_b200.Config.fromfile against mmcv's Config.fromfile (mmcv/mmcv/utils/config.py: `_base_` inheritance, dict
     merge, `_delete_`): the resulting dictionaries are EQUAL, key for key (tuples stay tuples), for all 17 files under
     configs/lsnet/."""
-    r = subprocess.run([sys.executable, '-c', CONFIG_SCRIPT], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and 'CONFIGS 17' in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+    ok, out = _section('config')
+    assert ok and 'CONFIGS 17' in out, out
 
 
 INIT_SCRIPT = textwrap.dedent('''
@@ -194,8 +230,11 @@ INIT_SCRIPT = textwrap.dedent('''
     torch.manual_seed(7); own.init_weights()
     rs, os_ = ref.state_dict(), own.state_dict()
     assert list(rs) == list(os_) and all(torch.equal(rs[k], os_[k]) for k in rs), [k for k in rs if not torch.equal(rs[k], os_[k])][:5]
+    del os.environ['LSNET_REF_INIT_STREAM']
+    assert type(ref).__module__.startswith('mmdet.') and type(own).__module__.startswith('lsnet_b200.')
     print('INIT OK')
 ''') % ROOT
+_SECTIONS['init'] = INIT_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
@@ -204,8 +243,8 @@ def test_init_weights_is_bit_identical_to_the_reference():
     keys, order, shapes, values) for the R50 bbox / segm / pose and the X-101 configs; with DCN in the trunk the 30
     constructor-drawn ``conv2.weight`` tensors are the only ones that differ -- and not even those with
     ``LSNET_REF_INIT_STREAM=1`` and the seed set before the build too."""
-    r = subprocess.run([sys.executable, '-c', INIT_SCRIPT], capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and 'INIT OK' in r.stdout, r.stderr[-3000:]
+    ok, out = _section('init')
+    assert ok and 'INIT OK' in out, out
 
 
 CKPT_SCRIPT = textwrap.dedent('''
@@ -230,6 +269,7 @@ CKPT_SCRIPT = textwrap.dedent('''
     # reference -> here: a checkpoint written by mmcv's save_checkpoint after one SGD step of the reference model
     torch.manual_seed(0)
     ref = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg); ref.init_weights()
+    assert type(ref).__module__.startswith('mmdet.') and type(ref.bbox_head).__module__.startswith('mmdet.')
     ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)      # mmcv build_optimizer: all params
     fake_step(list(ref.parameters()), ropt, 1)
     mmcv_save(ref, os.path.join(tmp, 'ref.pth'), optimizer=ropt, meta=dict(epoch=5, iter=1234))
@@ -264,6 +304,7 @@ CKPT_SCRIPT = textwrap.dedent('''
     assert all(torch.equal(a, b) for a, b in zip(ref2.parameters(), op))
     print('CKPT OK')
 ''') % ROOT
+_SECTIONS['ckpt'] = CKPT_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
@@ -272,8 +313,8 @@ def test_checkpoints_cross_the_boundary_both_ways():
     -- weights, momentum buffers, epoch / iter -- and both sides take the same next step; a checkpoint written by
     ``lsnet_b200.train.save_checkpoint`` loads through mmcv's ``load_checkpoint(strict=True)`` and the reference
     optimizer's ``load_state_dict`` and continues identically too."""
-    r = subprocess.run([sys.executable, '-c', CKPT_SCRIPT], capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and 'CKPT OK' in r.stdout, r.stderr[-3000:]
+    ok, out = _section('ckpt')
+    assert ok and 'CKPT OK' in out, out
 
 
 JSON_SCRIPT = textwrap.dedent('''
@@ -323,11 +364,12 @@ JSON_SCRIPT = textwrap.dedent('''
     assert len(segm) == sum(len(b) for r in r72 for b in r[0]) and all(len(s['segmentation'][0]) == 72 for s in segm)
     print('JSON OK')
 ''') % (ROOT, os.path.join(ROOT, 'tests', 'golden'))
+_SECTIONS['json'] = JSON_SCRIPT
 
 
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
 def test_results_to_coco_json_matches_the_reference():
     """Result lists -> COCO json records: ``_det2json`` / ``_kps2json`` equal to the reference's (coco_pose.py:209-247) on
     random LSNet-format results; the contour variant writes one polygon per instance."""
-    r = subprocess.run([sys.executable, '-c', JSON_SCRIPT], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and 'JSON OK' in r.stdout, r.stderr[-3000:]
+    ok, out = _section('json')
+    assert ok and 'JSON OK' in out, out
