@@ -276,10 +276,10 @@ def keypoint_flip(k, img_shape, direction):
     f = k.copy()
     if direction == 'horizontal':
         f[:, 0::3] = img_shape[1] - f[:, 0::3]
-        f = f.reshape(f.shape[0], -1, 3)
+        f = f.reshape(f.shape[0], f.shape[1] // 3, 3)       # (explicit count: an image without instances has 0 rows)
         for a, b in KEYPOINT_FLIP_PAIRS:
             f[:, [a, b]] = f[:, [b, a]]
-        f = f.reshape(f.shape[0], -1)
+        f = f.reshape(f.shape[0], k.shape[1])
     elif direction == 'vertical':
         f[:, 1::3] = img_shape[0] - f[:, 1::3]
     else:
