@@ -91,3 +91,32 @@ def test_extreme_points_follow_their_box_through_a_flip(seed):
     assert abs(fe[1] - fb[1]) < 1e-3 and abs(fe[5] - fb[3]) < 1e-3           # top / bottom points on the top / bottom sides
     assert abs(fe[2] - fb[0]) < 1e-3 and abs(fe[6] - fb[2]) < 1e-3           # the LEFT point lies on the flipped box's left side
     assert abs(fe[8] - (fb[0] + fb[2]) / 2) < 1e-3                           # centre stays the centre
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 5), st.integers(1, 4), st.integers(0, 7))
+def test_group_sampler_partitions(seed, spg, world, epoch):
+    """Both samplers, any group sizes / batch size / world size: every rank draws the same number of samples, every
+    per-GPU batch comes from ONE aspect-ratio group, and together the ranks cover the whole dataset each epoch."""
+    import types
+    from lsnet_b200.datasets import DistributedGroupSampler, GroupSampler
+    rng = np.random.RandomState(seed)
+    n = int(rng.randint(1, 60))
+    flag = (rng.rand(n) < rng.rand()).astype(np.uint8)
+    ds = types.SimpleNamespace(flag=flag)
+    per_rank = []
+    for rank in range(world):
+        s = DistributedGroupSampler(ds, samples_per_gpu=spg, num_replicas=world, rank=rank)
+        s.set_epoch(epoch)
+        idx = list(s)
+        assert len(idx) == len(s) and len(idx) % spg == 0
+        for i in range(0, len(idx), spg):
+            assert len({int(flag[j]) for j in idx[i:i + spg]}) == 1
+        per_rank.append(idx)
+    assert len({len(p) for p in per_rank}) == 1
+    assert set(j for p in per_rank for j in p) == set(range(n))
+    np.random.seed(seed % 1000)
+    idx = list(GroupSampler(ds, samples_per_gpu=spg))
+    assert set(idx) == set(range(n)) and len(idx) % spg == 0
+    for i in range(0, len(idx), spg):
+        assert len({int(flag[j]) for j in idx[i:i + spg]}) == 1
