@@ -1,5 +1,5 @@
-"""The train pipelines of the LSNet configs, under the reference's PIPELINES names so
-``cfg.data.train.pipeline`` resolves unchanged:
+"""The train and test pipelines of the LSNet configs, under the reference's PIPELINES names so
+``cfg.data.train.pipeline`` / ``cfg.data.test.pipeline`` resolve unchanged:
 
     LoadImageFromFile -> LoadAnnotations(with_bbox, with_extreme | with_keypoint | with_mask+poly2mask=False)
     -> Resize(keep_ratio, single scale | multiscale range / value) -> RandomFlip -> Normalize -> Pad(size_divisor)
@@ -10,7 +10,10 @@ Reference behaviour: mmdet/datasets/pipelines/{loading.py:11-107,183-470, transf
 compose.py}.  Every stage takes and returns the same ``results`` dict with the same keys, so the stages can be mixed
 with reference ones.
 
-B200-first difference (opt-in, ``device_prep=True`` in ``build_dataloader``): Normalize / Pad / the NCHW transpose are
+(test: LoadImageFromFile -> MultiScaleFlipAug[Resize, RandomFlip, Normalize, Pad, ImageToTensor, Collect],
+coco_lsvr.py:15-29.)
+
+B200-first difference (opt-in, ``loader.device_prep_pipeline(pipeline)``): Normalize / Pad / the NCHW transpose are
 left out of the worker pipeline; the batch carries the resized uint8 HWC images and ONE kernel
 (``lsnet_image_prep_u8``, csrc/elementwise.cu) writes the normalised, zero-padded fp32 NCHW canvas on the GPU —
 4× fewer bytes over PCIe per step and no float image passes on the host.
