@@ -373,3 +373,62 @@ def test_results_to_coco_json_matches_the_reference():
     random LSNet-format results; the contour variant writes one polygon per instance."""
     ok, out = _section('json')
     assert ok and 'JSON OK' in out, out
+
+
+MIXED_SCRIPT = textwrap.dedent('''
+    import sys, copy, types
+    sys.path.insert(0, %r)
+    sys.path.insert(0, %r)
+    from oracle import ref_harness as rh
+    rh.load()
+    import numpy as np, torch
+    import mmdet.datasets.pipelines.loading as loading
+    from mmdet.datasets.builder import PIPELINES as REF
+    from mmcv.utils import build_from_cfg
+    import make_golden_data as M
+    loading.Polygon = M._Polygon
+    import synth_coco as S
+    import lsnet_b200
+    OWN = lsnet_b200.PIPELINES
+    assert REF.get('Resize').__module__.startswith('mmdet.')             # the registries have not been swapped yet
+    for task in ('bbox', 'segm', 'pose_bbox'):
+        ds = lsnet_b200.DATASETS.get('CocoPoseDataset' if task == 'pose_bbox' else 'CocoDataset')(
+            ann_file=S.coco_dict(task == 'pose_bbox'), pipeline=[])
+        cfgs = S.pipeline(task, True)
+        outs = []
+        for pick in (lambda i: REF, lambda i: (OWN if i %% 2 else REF), lambda i: (REF if i %% 2 else OWN)):
+            stages = [build_from_cfg(dict(c), pick(i)) if pick(i) is REF else lsnet_b200.registry.build_from_cfg(dict(c), pick(i))
+                      for i, c in enumerate(cfgs)]
+            i = 2
+            img = S.image(i)
+            r = dict(img_info=ds.data_infos[i], ann_info=copy.deepcopy(ds.get_ann_info(i)), img=img, img_shape=img.shape,
+                     ori_shape=img.shape, img_fields=['img'], filename='x', ori_filename='x')
+            ds.pre_pipeline(r)
+            np.random.seed(5)
+            for s_ in stages:
+                r = s_(r)
+            outs.append(r)
+        unwrap = lambda v: v.data if hasattr(v, 'data') and not torch.is_tensor(v) else v
+        ref = outs[0]
+        for o in outs[1:]:
+            assert set(o) == set(ref)
+            assert torch.equal(unwrap(o['img']), unwrap(ref['img']))
+            for k in ('gt_bboxes', 'gt_labels', 'gt_extremes', 'gt_keypoints'):
+                if k in ref:
+                    assert torch.equal(unwrap(o[k]), unwrap(ref[k])), (task, k)
+            if 'gt_masks' in ref:
+                a, b = unwrap(o['gt_masks']), unwrap(ref['gt_masks'])
+                assert all(np.array_equal(p, q) for x, y in zip(a.masks, b.masks) for p, q in zip(x, y))
+            ma, mb = unwrap(o['img_metas']), unwrap(ref['img_metas'])
+            assert ma['img_shape'] == mb['img_shape'] and ma['pad_shape'] == mb['pad_shape'] and ma['flip'] == mb['flip']
+    print('MIXED OK')
+''') % (ROOT, os.path.join(ROOT, 'tests', 'golden'))
+_SECTIONS['mixed'] = MIXED_SCRIPT
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
+def test_pipeline_stages_interleave_with_the_reference_stages():
+    """Every stage reads and writes the reference's ``results`` keys: pipelines that ALTERNATE reference stages and B200
+    stages (both phases) give exactly the all-reference output, for the three tasks."""
+    ok, out = _section('mixed')
+    assert ok and 'MIXED OK' in out, out
