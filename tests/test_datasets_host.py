@@ -236,7 +236,7 @@ def test_dataloader_end_to_end(tmp_path):
         cv2.imwrite(str(tmp_path / f'img_{i}.png'), S.image(i))
     cls = DATASETS.get('CocoDataset')
     ds = cls(ann_file=S.coco_dict(False), pipeline=pipe, img_prefix=str(tmp_path))
-    dl = D.build_dataloader(ds, samples_per_gpu=2, workers_per_gpu=2, dist=False, seed=3)     # worker processes
+    dl = D.build_dataloader(ds, samples_per_gpu=2, workers_per_gpu=2, dist=False, seed=3, timeout=180)   # worker processes
     np.random.seed(0)
     from lsnet_b200.data import MODEL_CFG
     from lsnet_b200.registry import build_head

@@ -127,7 +127,8 @@ def test_files_to_training_steps(tmp_path, task, device_prep):
     pose = task == 'pose_bbox'
     ds = DATASETS.get('CocoPoseDataset' if pose else 'CocoDataset')(
         ann_file=S.coco_dict(pose), pipeline=pipe, img_prefix=str(tmp_path))
-    dl = D.build_dataloader(ds, samples_per_gpu=3, workers_per_gpu=2, dist=False, seed=1, pin=True)
+    dl = D.build_dataloader(ds, samples_per_gpu=3, workers_per_gpu=2, dist=False, seed=1, pin=True,
+                            timeout=180)      # a stuck worker raises instead of hanging the suite
     cfg = MODEL_CFG[{'bbox': 'bbox_r50', 'segm': 'segm_r50', 'pose_bbox': 'pose_x101dcn'}[task]]
     if pose:        # the R50 trunk keeps the test short; the pose head is what the keypoint batches exercise
         cfg = dict(cfg, model=dict(cfg['model'], backbone=MODEL_CFG['bbox_r50']['model']['backbone']))
