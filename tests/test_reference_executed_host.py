@@ -199,10 +199,14 @@ INIT_SCRIPT = textwrap.dedent('''
     from oracle import ref_harness as rh
     ns = rh.load()
     import torch, lsnet_b200
-    for name, n_dcn in (('lsnet_bbox_r50_fpn_1x_coco.py', 0), ('lsnet_segm_r50_fpn_1x_coco.py', 0),
-                        ('lsnet_pose_bbox_r50_fpn_1x_coco.py', 0), ('lsnet_segm_x101_fpn_mstrain_30e_coco.py', 0),
-                        ('lsnet_pose_kbox_x101_fpn_dconv_c3-c5_mstrain_2x_coco.py', 30)):
-        f = ns.root + '/configs/lsnet/' + name
+    import glob, os
+    built = 0
+    for f in sorted(glob.glob(ns.root + '/configs/lsnet/*.py')):
+        name = os.path.basename(f)
+        if 'cpv' in name or 'res2' in name:                  # LSCPVDetector / Res2Net: outside the path (DESIGN 7)
+            continue
+        n_dcn = 30 if 'dconv' in name else 0                 # X-101-DCN: conv2 of the 4 + 23 + 3 blocks of c3-c5
+        built += 1
         cfg = ns.Config.fromfile(f); cfg.model.pretrained = None
         ref = ns.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
         c2 = lsnet_b200.Config.fromfile(f); c2.model.pretrained = None
@@ -217,6 +221,7 @@ INIT_SCRIPT = textwrap.dedent('''
         # the construction-time RNG stream, everything else is set by init_weights
         assert len(diff) == n_dcn and all(k.startswith('backbone.') and k.endswith('.conv2.weight') for k in diff), (name, diff[:5])
         assert a == b, name                                                 # init_weights consumed the same random stream
+    assert built == 12
     # with the reference's construction-time random stream reproduced (LSNET_REF_INIT_STREAM=1) and the seed set before
     # the build as well, the DCN trunk is identical too
     import os
@@ -240,7 +245,8 @@ _SECTIONS['init'] = INIT_SCRIPT
 @pytest.mark.skipif(not os.path.isdir('/root/reference/code/mmdet'), reason='reference tree not present')
 def test_init_weights_is_bit_identical_to_the_reference():
     """Same seed before ``init_weights()`` -> the same initial model as the reference, tensor for tensor (state_dict
-    keys, order, shapes, values) for the R50 bbox / segm / pose and the X-101 configs; with DCN in the trunk the 30
+    keys, order, shapes, values) for ALL 12 configs of configs/lsnet/ on this path (R50 and X-101 trunks; bbox, segm,
+    pose_bbox, pose_kbox heads; the 5 LSCPVDetector / Res2Net configs are outside it); with DCN in the trunk the 30
     constructor-drawn ``conv2.weight`` tensors are the only ones that differ -- and not even those with
     ``LSNET_REF_INIT_STREAM=1`` and the seed set before the build too."""
     ok, out = _section('init')
