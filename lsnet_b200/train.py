@@ -491,10 +491,20 @@ def _sgd(trainer, key):
     return trainer.momentum if key == 'momentum' else trainer.wd
 
 
+def load_checkpoint_file(path):
+    """``torch.load`` on the CPU, tensors-and-plain-containers only where the file allows it (what the reference's
+    checkpoints hold: state_dict, optimizer state, a meta dict of strings / numbers); files that pickle other objects
+    (e.g. a config object in ``meta``) fall back to the full unpickler, as mmcv's ``load_checkpoint`` always uses."""
+    try:
+        return torch.load(path, map_location='cpu', weights_only=True)
+    except Exception:
+        return torch.load(path, map_location='cpu', weights_only=False)
+
+
 def resume(trainer, path, strict=True):
     """``BaseRunner.resume`` (mmcv/mmcv/runner/base_runner.py:289-307): weights (``module.`` prefixes of a DataParallel
     checkpoint stripped, checkpoint.py:204-240), momentum buffers, epoch and iteration.  Returns ``meta``."""
-    ckpt = torch.load(path, map_location='cpu', weights_only=False)
+    ckpt = load_checkpoint_file(path)
     state = ckpt.get('state_dict', ckpt)
     state = {(k[7:] if k.startswith('module.') else k): v for k, v in state.items()}
     trainer.core.load_state_dict(state, strict=strict)          # copies INTO the (flat-buffer) parameter storage

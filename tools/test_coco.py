@@ -67,7 +67,8 @@ def main(argv=None):
         test_cfg.update(method='vote', scale_ranges=ast.literal_eval(args.vote))
     cfg.model.pretrained = None
     model = build_detector(cfg.model, train_cfg=None, test_cfg=test_cfg)
-    ck = torch.load(args.checkpoint, map_location='cpu', weights_only=False)
+    from lsnet_b200.train import load_checkpoint_file
+    ck = load_checkpoint_file(args.checkpoint)
     state = ck.get('state_dict', ck)
     model.load_state_dict({(k[7:] if k.startswith('module.') else k): v for k, v in state.items()}, strict=True)
     model.cuda().eval()
